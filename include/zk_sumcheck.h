@@ -1,0 +1,140 @@
+/*
+ * zk_sumcheck.h -- C ABI of the B200 sumcheck / GKR prover library (libzkb200.so).
+ *
+ * The reference (casweeney/zk-cryptography-research-implementations) is a pure-Rust workspace with
+ * no FFI; the drop-in boundary is its public generic API.  Each entry point below names the
+ * reference item it replaces (paths relative to the reference root).  A Rust `-sys` shim binds
+ * these unchanged: arkworks' `Fp<MontBackend<_,4>,4>` is `[u64;4]` in Montgomery form, which is
+ * exactly the element layout used here, so `&[F]` crosses as `*const u64`.
+ *
+ * Conventions
+ *   - every field element in or out: 4 x uint64_t little-endian limbs, Montgomery form, canonical
+ *   - status: 0 = ok; ZK_ERR_ASSERT = the reference would have panicked (zk_last_error() returns the
+ *     reference's panic text); ZK_ERR_CUDA = CUDA/NCCL failure; ZK_ERR_ARG = bad argument.
+ *     Nothing unwinds across the boundary.
+ *   - a zk_ctx is bound to one GPU and one stream and is not thread-safe (one per host thread /
+ *     one per rank); there is NO CPU fallback: without a usable GPU zk_ctx_create fails.
+ */
+#ifndef ZK_SUMCHECK_H
+#define ZK_SUMCHECK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ZK_BN254_FQ = 0, ZK_BN254_FR = 1, ZK_BLS12_381_FR = 2 };
+enum { ZK_OK = 0, ZK_ERR_ASSERT = -1, ZK_ERR_CUDA = -2, ZK_ERR_ARG = -3 };
+/* flags for the one-shot provers */
+enum {
+    ZK_FLAG_DIRECT_S1 = 1,   /* compute s(1) in the kernel every round instead of claim - s(0) */
+    ZK_FLAG_SKIP_ABSORB = 2  /* zk_prove_basic*: the caller already absorbed the table bytes */
+};
+
+typedef struct zk_ctx zk_ctx;
+typedef struct zk_table zk_table;
+typedef struct zk_sumpoly zk_sumpoly;
+typedef struct zk_transcript zk_transcript;
+
+/* ---- library / context ---- */
+const char *zk_version(void);
+int  zk_ctx_create(zk_ctx **out, int field_id, int device);
+/* same, launching on a stream the caller owns (e.g. torch's current stream); stream = cudaStream_t */
+int  zk_ctx_create_on_stream(zk_ctx **out, int field_id, int device, void *stream);
+void zk_ctx_destroy(zk_ctx *);
+const char *zk_last_error(const zk_ctx *);
+int  zk_ctx_synchronize(zk_ctx *);
+/* kernel accounting for bench.py: launches since the last reset; with profiling on, the summed
+ * CUDA-event time and algorithmic bytes of the round kernels (round_evals / fold_evals). */
+int  zk_ctx_set_profiling(zk_ctx *, int on);
+int  zk_ctx_reset_stats(zk_ctx *);
+int  zk_ctx_get_stats(zk_ctx *, uint64_t *launches, uint64_t *round_launches, double *round_ms, double *round_bytes);
+
+/* ---- field helpers on the host (ark-ff: F::from(u64), into_bigint, from_le_bytes_mod_order) ---- */
+int  zk_fe_from_u64(int field_id, uint64_t v, uint64_t out[4]);
+int  zk_fe_to_canonical(int field_id, const uint64_t in[4], uint64_t out[4]);
+int  zk_fe_from_canonical(int field_id, const uint64_t in[4], uint64_t out[4]);
+int  zk_fe_add(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+int  zk_fe_sub(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+int  zk_fe_mul(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+
+/* ---- transcript: transcripts/src/fiat_shamir/fiat_shamir_transcript.rs:5-43 (host, Keccak-256) ---- */
+zk_transcript *zk_transcript_new(void);                                              /* Transcript::new :12-16 */
+void zk_transcript_free(zk_transcript *);
+void zk_transcript_append(zk_transcript *, const uint8_t *data, size_t len);         /* append :22-24 */
+void zk_transcript_sample(zk_transcript *, uint8_t out[32]);                         /* sample_random_challenge :29-36 */
+void zk_transcript_challenge(zk_transcript *, int field_id, uint64_t out[4]);        /* random_challenge_as_field_element :38-43 */
+
+/* ---- tables: MultilinearPolynomial<F> (polynomials/src/multilinear/evaluation_form.rs:7-18) ---- */
+/* new(&[F]) :12-18 -- copies n elements from the host; n must be a power of two
+ * ("Evaluated values must be a power of 2") */
+int  zk_table_upload(zk_ctx *, const uint64_t *mont_limbs, uint64_t n, zk_table **out);
+/* synthetic table generated on the device: local entry j = global entry first + j*step */
+int  zk_table_generate(zk_ctx *, uint64_t seed, uint64_t table_id, uint64_t n, uint64_t first, uint64_t step, zk_table **out);
+/* refill an existing table in place with the same generator (bench: restore inputs between steps) */
+int  zk_table_regenerate(zk_ctx *, zk_table *, uint64_t seed, uint64_t table_id, uint64_t n, uint64_t first, uint64_t step);
+/* wrap caller-owned device memory (e.g. a torch tensor) without copying */
+int  zk_table_wrap(zk_ctx *, void *device_ptr, uint64_t n, zk_table **out);
+int  zk_table_clone(zk_ctx *, const zk_table *, zk_table **out);                      /* Clone */
+int  zk_table_download(zk_ctx *, const zk_table *, uint64_t *out_limbs);              /* .evaluated_values */
+uint64_t zk_table_len(const zk_table *);
+void *zk_table_device_ptr(const zk_table *);
+void zk_table_free(zk_ctx *, zk_table *);
+
+/* partial_evaluate(&Vec<F>, evaluating_variable, value) :61-106 -- halves the table (in place for var 0) */
+int  zk_mle_partial_evaluate(zk_ctx *, zk_table *t, uint32_t var, const uint64_t r[4]);
+/* evaluate(&self, &[F]) :21-33 -- non-destructive; n_values may be < log2(len) (returns entry 0) */
+int  zk_mle_evaluate(zk_ctx *, const zk_table *t, const uint64_t *values, uint32_t n_values, uint64_t out[4]);
+/* convert_to_bytes :35-43 -- 32*len bytes, big-endian canonical, converted on the GPU */
+int  zk_mle_to_bytes(zk_ctx *, const zk_table *t, uint8_t *out_host);
+/* scalar_mul :49-57, add_polynomials :145-163, polynomial_tensor_add/mul :108-143 -- new tables */
+int  zk_mle_scalar_mul(zk_ctx *, const zk_table *t, const uint64_t s[4], zk_table **out);
+int  zk_mle_add(zk_ctx *, const zk_table *a, const zk_table *b, zk_table **out);
+int  zk_mle_tensor_add(zk_ctx *, const zk_table *wb, const zk_table *wc, zk_table **out);
+int  zk_mle_tensor_mul(zk_ctx *, const zk_table *wb, const zk_table *wc, zk_table **out);
+/* split_polynomial_and_sum_each (sumcheck_protocol/src/basic_sumcheck/prover.rs:74-89): out = [sum left, sum right] */
+int  zk_sum_halves(zk_ctx *, const zk_table *t, uint64_t out[8]);
+
+/* ---- SumPolynomial / ProductPolynomial (polynomials/src/composed/{sum,product}_polynomial.rs) ----
+ * tables[p*D + d] is factor d of product p; the sumpoly takes ownership of the tables.
+ * "different number of variables" if the lengths differ. */
+int  zk_sumpoly_create(zk_ctx *, zk_table *const *tables, uint32_t P, uint32_t D, zk_sumpoly **out);
+void zk_sumpoly_free(zk_ctx *, zk_sumpoly *);
+uint64_t zk_sumpoly_len(const zk_sumpoly *);
+zk_table *zk_sumpoly_table(const zk_sumpoly *, uint32_t index);
+/* add_polynomials_element_wise (sum_polynomial.rs:57-76; product_polynomial.rs:58-73) -> new table */
+int  zk_sumpoly_reduce(zk_ctx *, const zk_sumpoly *, zk_table **out);
+/* generate_round_univariate (sumcheck_gkr_protocol.rs:113-143): evals[X] = sum_x f(X, x), X = 0..D */
+int  zk_sumcheck_round_evals(zk_ctx *, zk_sumpoly *, uint64_t *evals /* 4*(D+1) */);
+/* SumPolynomial::partial_evaluate(0, r) (sum_polynomial.rs:40-53) fused with the NEXT round's
+ * generate_round_univariate: one pass over the tables.  evals == NULL: fold only. */
+int  zk_sumcheck_fold_and_evals(zk_ctx *, zk_sumpoly *, const uint64_t r[4], uint64_t *evals);
+
+/* ---- one-shot provers (host transcript inside, tables stay on the GPU) ---- */
+/* sumcheck_gkr_protocol::prove (sumcheck_gkr_protocol.rs:24-67).  Consumes the sumpoly's tables (folded in
+ * place down to one entry each).  coeffs: n*(D+1) elements (round polynomials, coefficient form);
+ * challenges: n elements; final_values (may be NULL): P*D elements = the tables after the last fold. */
+int  zk_prove_product(zk_ctx *, zk_sumpoly *, const uint64_t claimed_sum[4], zk_transcript *,
+                      uint64_t *coeffs, uint64_t *challenges, uint64_t *final_values, uint32_t flags);
+/* basic_sumcheck Prover::init + Prover::prove (prover.rs:22-71) on a device table (consumed).
+ * claimed_sum: out; round_polys: n*2 elements ([sum left, sum right] per round); challenges (extra,
+ * may be NULL): n elements; final_value (may be NULL): the table after the last fold. */
+int  zk_prove_basic_device(zk_ctx *, zk_table *t, uint64_t claimed_sum[4], uint64_t *round_polys,
+                           uint64_t *challenges, uint64_t final_value[4], uint32_t flags);
+/* same from a HOST table (uploads it first): the end-to-end call a reference user makes */
+int  zk_prove_basic(zk_ctx *, const uint64_t *host_table, uint64_t n, uint64_t claimed_sum[4], uint64_t *round_polys,
+                    uint64_t *challenges, uint64_t final_value[4], uint32_t flags);
+/* product sumcheck from HOST tables laid out [P][D][n] (uploads, proves, frees) */
+int  zk_prove_product_host(zk_ctx *, const uint64_t *host_tables, uint32_t P, uint32_t D, uint64_t n,
+                           const uint64_t claimed_sum[4], zk_transcript *, uint64_t *coeffs, uint64_t *challenges,
+                           uint64_t *final_values, uint32_t flags);
+
+/* ---- measurement: register-resident field arithmetic, no memory traffic (the IMAD-pipe ceiling) ----
+ * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate. */
+int  zk_arith_probe(zk_ctx *, int kind, uint32_t iters, int blocks_per_sm, double *ops_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZK_SUMCHECK_H */

@@ -1,0 +1,93 @@
+"""ctypes loader of libzkb200.so (the C-ABI of include/zk_sumcheck.h).
+
+There is no CPU fallback: if the shared library is missing this raises, and if no GPU is usable
+`Context()` raises.  The library is built in-tree by `zk_cryptography_research_implementations_b200.build`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+
+u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+ZK_OK, ZK_ERR_ASSERT, ZK_ERR_CUDA, ZK_ERR_ARG = 0, -1, -2, -3
+FLAG_DIRECT_S1, FLAG_SKIP_ABSORB = 1, 2
+
+# name -> (restype, argtypes); every symbol include/zk_sumcheck.h declares
+SIGNATURES = {
+    "zk_version": (C.c_char_p, []),
+    "zk_ctx_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
+    "zk_ctx_create_on_stream": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, vp]),
+    "zk_ctx_destroy": (None, [vp]),
+    "zk_last_error": (C.c_char_p, [vp]),
+    "zk_ctx_synchronize": (C.c_int, [vp]),
+    "zk_ctx_set_profiling": (C.c_int, [vp, C.c_int]),
+    "zk_ctx_reset_stats": (C.c_int, [vp]),
+    "zk_ctx_get_stats": (C.c_int, [vp, u64p, u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "zk_fe_from_u64": (C.c_int, [C.c_int, C.c_uint64, u64p]),
+    "zk_fe_to_canonical": (C.c_int, [C.c_int, u64p, u64p]),
+    "zk_fe_from_canonical": (C.c_int, [C.c_int, u64p, u64p]),
+    "zk_fe_add": (C.c_int, [C.c_int, u64p, u64p, u64p]),
+    "zk_fe_sub": (C.c_int, [C.c_int, u64p, u64p, u64p]),
+    "zk_fe_mul": (C.c_int, [C.c_int, u64p, u64p, u64p]),
+    "zk_transcript_new": (vp, []),
+    "zk_transcript_free": (None, [vp]),
+    "zk_transcript_append": (None, [vp, C.c_char_p, C.c_size_t]),
+    "zk_transcript_sample": (None, [vp, C.c_char_p]),
+    "zk_transcript_challenge": (None, [vp, C.c_int, u64p]),
+    "zk_table_upload": (C.c_int, [vp, u64p, C.c_uint64, C.POINTER(vp)]),
+    "zk_table_generate": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
+    "zk_table_regenerate": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "zk_table_wrap": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(vp)]),
+    "zk_table_clone": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "zk_table_download": (C.c_int, [vp, vp, u64p]),
+    "zk_table_len": (C.c_uint64, [vp]),
+    "zk_table_device_ptr": (vp, [vp]),
+    "zk_table_free": (None, [vp, vp]),
+    "zk_mle_partial_evaluate": (C.c_int, [vp, vp, C.c_uint32, u64p]),
+    "zk_mle_evaluate": (C.c_int, [vp, vp, u64p, C.c_uint32, u64p]),
+    "zk_mle_to_bytes": (C.c_int, [vp, vp, u8p]),
+    "zk_mle_scalar_mul": (C.c_int, [vp, vp, u64p, C.POINTER(vp)]),
+    "zk_mle_add": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
+    "zk_mle_tensor_add": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
+    "zk_mle_tensor_mul": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
+    "zk_sum_halves": (C.c_int, [vp, vp, u64p]),
+    "zk_sumpoly_create": (C.c_int, [vp, C.POINTER(vp), C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "zk_sumpoly_free": (None, [vp, vp]),
+    "zk_sumpoly_len": (C.c_uint64, [vp]),
+    "zk_sumpoly_table": (vp, [vp, C.c_uint32]),
+    "zk_sumpoly_reduce": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "zk_sumcheck_round_evals": (C.c_int, [vp, vp, u64p]),
+    "zk_sumcheck_fold_and_evals": (C.c_int, [vp, vp, u64p, u64p]),
+    "zk_prove_product": (C.c_int, [vp, vp, u64p, vp, u64p, u64p, u64p, C.c_uint32]),
+    "zk_prove_basic_device": (C.c_int, [vp, vp, u64p, u64p, u64p, u64p, C.c_uint32]),
+    "zk_prove_basic": (C.c_int, [vp, u64p, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint32]),
+    "zk_prove_product_host": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, C.c_uint64, u64p, vp, u64p, u64p, u64p,
+                                        C.c_uint32]),
+    "zk_arith_probe": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libzkb200.so is not built (%s). Run `python -m zk_cryptography_research_implementations_b200.build`; "
+            "there is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

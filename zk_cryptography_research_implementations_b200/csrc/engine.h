@@ -1,0 +1,53 @@
+// engine.h -- the opaque handle types of include/zk_sumcheck.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "host_field.h"
+
+namespace zk { struct Fe; }
+
+struct zk_ctx {
+    explicit zk_ctx(int field_id) : fid(field_id), field(field_id) {}
+    int fid;
+    int device = 0;
+    int sm_count = 148;
+    int max_grid = 148 * 8;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    zk::HostField field;
+    std::map<int, zk::Interpolator> interps;   // one inverse Vandermonde per degree
+    // grid-wide reduction scratch + the published round evaluations (mapped pinned host memory)
+    zk::Fe* partials = nullptr;
+    unsigned* ticket = nullptr;
+    zk::Fe* result_host = nullptr;
+    zk::Fe* result_dev = nullptr;
+    // general scratch (evaluate / convert_to_bytes / out-of-place folds)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* pinned = nullptr;
+    // accounting
+    bool profiling = false;
+    uint64_t launches = 0, round_launches = 0;
+    double round_ms = 0, round_bytes = 0;
+    std::vector<cudaEvent_t> events;
+    size_t ev_used = 0;
+    std::string err;
+};
+
+struct zk_table {
+    zk::Fe* d = nullptr;
+    uint64_t len = 0, cap = 0;
+    bool owned = true;
+};
+
+struct zk_sumpoly {
+    std::vector<zk_table*> tabs;   // [p * D + d]
+    uint32_t P = 0, D = 0;
+    uint64_t len = 0;
+};
+
+struct zk_transcript {
+    zk::HostTranscript t;
+};

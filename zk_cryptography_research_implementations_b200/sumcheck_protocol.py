@@ -1,0 +1,127 @@
+"""`sumcheck_protocol` crate mirror: the two provers, running on the GPU.
+
+  basic_sumcheck.prover      sumcheck_protocol/src/basic_sumcheck/prover.rs
+  gkr_sumcheck               sumcheck_protocol/src/gkr_sumcheck/sumcheck_gkr_protocol.rs
+
+The verifiers are out of scope; tests verify our proofs with the oracle's
+restatement of the reference verifier.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .core import Context, DeviceTable, ReferencePanic, _ptr, as_elems
+from .polynomials import DenseUnivariatePolynomial, MultilinearPolynomial, SumPolynomial
+from .transcripts import Transcript
+
+
+# =============================================================== basic_sumcheck
+@dataclass
+class SumcheckProof:
+    """`SumcheckProof<F>` (prover.rs:15-19); round polynomials are 2-entry evaluation tables."""
+    initial_polynomial: np.ndarray            # (N, 4)
+    initial_claimed_sum: np.ndarray           # (4,)
+    round_univariate_polynomials: np.ndarray  # (n, 2, 4)
+    # extras (not part of the reference proof; handy for parity checks)
+    challenges: Optional[np.ndarray] = None
+    final_evaluation: Optional[np.ndarray] = None
+
+
+class Prover:
+    """`Prover<F>` (prover.rs:7-13)."""
+
+    def __init__(self):
+        self.is_initialized = False
+
+    @classmethod
+    def init(cls, ctx: Context, polynomial_evaluated_values) -> "Prover":   # prover.rs:22-33
+        self = cls()
+        ev = as_elems(polynomial_evaluated_values).reshape(-1, 4)
+        if ev.shape[0] == 0 or ev.shape[0] & (ev.shape[0] - 1):
+            raise ReferencePanic("Evaluated values must be a power of 2")
+        self.ctx = ctx
+        self.initial_polynomial = ev.copy()
+        self.is_initialized = True
+        return self
+
+    def prove(self) -> SumcheckProof:                                        # prover.rs:35-71
+        if not self.is_initialized:
+            raise ReferencePanic("Can't prove without init")
+        ctx = self.ctx
+        N = self.initial_polynomial.shape[0]
+        n = N.bit_length() - 1
+        claimed = np.zeros(4, dtype=np.uint64)
+        rounds = np.zeros((max(n, 1), 2, 4), dtype=np.uint64)
+        chal = np.zeros((max(n, 1), 4), dtype=np.uint64)
+        fin = np.zeros(4, dtype=np.uint64)
+        ctx.check(ctx.lib.zk_prove_basic(ctx.h, _ptr(self.initial_polynomial), N, _ptr(claimed), _ptr(rounds),
+                                         _ptr(chal), _ptr(fin), 0))
+        self.initial_claimed_sum = claimed
+        return SumcheckProof(self.initial_polynomial.copy(), claimed, rounds[:n], chal[:n], fin)
+
+
+def split_polynomial_and_sum_each(ctx: Context, polynomial_evaluated_values) -> np.ndarray:   # prover.rs:74-89
+    t = ctx.upload(as_elems(polynomial_evaluated_values).reshape(-1, 4))
+    out = np.zeros((2, 4), dtype=np.uint64)
+    ctx.check(ctx.lib.zk_sum_halves(ctx.h, t.h, _ptr(out)))
+    return out
+
+
+# =============================================================== gkr_sumcheck
+@dataclass
+class SumcheckProverProof:
+    """`SumcheckProverProof<F>` (sumcheck_gkr_protocol.rs:9-13)."""
+    claimed_sum: np.ndarray
+    round_univariate_polynomials: List[DenseUnivariatePolynomial]
+    random_challenges: np.ndarray              # (n, 4)
+    final_values: Optional[np.ndarray] = None  # extra: tables after the last fold, (P*D, 4)
+
+
+def generate_round_univariate(current_polynomial: SumPolynomial) -> np.ndarray:   # sumcheck_gkr_protocol.rs:113-143
+    ctx = current_polynomial.ctx
+    sp = current_polynomial._device_sumpoly(clone=True)
+    try:
+        out = np.zeros((current_polynomial.degree() + 1, 4), dtype=np.uint64)
+        ctx.check(ctx.lib.zk_sumcheck_round_evals(ctx.h, sp, _ptr(out)))
+        return out
+    finally:
+        ctx.lib.zk_sumpoly_free(ctx.h, sp)
+
+
+def prove(sum_polynomial: SumPolynomial, claimed_sum, transcript: Transcript, flags: int = 0) -> SumcheckProverProof:
+    """`prove` (sumcheck_gkr_protocol.rs:24-67).  Takes the polynomial by value like the reference
+    (its tables are consumed); the transcript is borrowed and advanced."""
+    ctx = sum_polynomial.ctx
+    P, D = len(sum_polynomial.product_polynomials), sum_polynomial.degree()
+    if P < 2:
+        raise ReferencePanic("more than one product polynomial required for add operation")
+    if D < 2:
+        raise ReferencePanic("more than one polynomial required for mul operation")
+    n = sum_polynomial.number_of_variables()
+    sp = sum_polynomial._device_sumpoly(clone=False)
+    try:
+        coeffs = np.zeros((max(n, 1), D + 1, 4), dtype=np.uint64)
+        chal = np.zeros((max(n, 1), 4), dtype=np.uint64)
+        fin = np.zeros((P * D, 4), dtype=np.uint64)
+        claimed = as_elems(claimed_sum).copy()
+        ctx.check(ctx.lib.zk_prove_product(ctx.h, sp, _ptr(claimed), transcript.h, _ptr(coeffs), _ptr(chal), _ptr(fin),
+                                           flags))
+    finally:
+        ctx.lib.zk_sumpoly_free(ctx.h, sp)
+    polys = [DenseUnivariatePolynomial(ctx.field, coeffs[k]) for k in range(n)]
+    return SumcheckProverProof(claimed, polys, chal[:n], fin)
+
+
+def univariate_to_bytes(field: int, univariate_poly) -> bytes:      # sumcheck_gkr_protocol.rs:145-150 (little-endian)
+    from .core import fe_to_ints
+    return b"".join(v.to_bytes(32, "little") for v in fe_to_ints(field, univariate_poly))
+
+
+def field_element_to_bytes(field: int, field_element) -> bytes:     # sumcheck_gkr_protocol.rs:152-154 / prover.rs:91-93
+    from .core import fe_to_ints
+    return fe_to_ints(field, field_element)[0].to_bytes(32, "big")
