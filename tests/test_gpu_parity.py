@@ -313,7 +313,8 @@ def test_large_product_sumcheck_properties(zk, co, ctx_for, fid, P, D, n):
         ctx.check(ctx.lib.zk_sumcheck_round_evals(ctx.h, h, _ptr(ev)))
         claimed = zk.fe_binop("add", fid, ev[0], ev[1])
         coeffs = np.zeros((n, D + 1, 4), dtype=np.uint64); ch = np.zeros((n, 4), dtype=np.uint64); fin = np.zeros((P * D, 4), dtype=np.uint64)
-        ctx.check(ctx.lib.zk_prove_product(ctx.h, h, _ptr(claimed), Transcript().h, _ptr(coeffs), _ptr(ch), _ptr(fin), flags))
+        tr = Transcript()   # keep it alive across the call
+        ctx.check(ctx.lib.zk_prove_product(ctx.h, h, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(ch), _ptr(fin), flags))
         ctx.lib.zk_sumpoly_free(ctx.h, h)
         return claimed, coeffs, ch, fin
 

@@ -38,7 +38,8 @@ for fid in (0, 2):
                 rp = np.zeros((n, 2, 4), dtype=np.uint64)
                 ctx.check(ctx.lib.zk_prove_basic_device(ctx.h, ctx.lib.zk_sumpoly_table(h, 0), _ptr(claimed), _ptr(rp), _ptr(ch), _ptr(fin), 2))
             else:
-                ctx.check(ctx.lib.zk_prove_product(ctx.h, h, _ptr(claimed), Transcript().h, _ptr(coeffs), _ptr(ch), _ptr(fin), 0))
+                tr = Transcript()
+                ctx.check(ctx.lib.zk_prove_product(ctx.h, h, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(ch), _ptr(fin), 0))
             dt = time.perf_counter() - t0
             st = ctx.stats()
         key = "prove_f%d_P%dD%d_n%d" % (fid, P, D, n)

@@ -53,6 +53,7 @@ static int grid_for(const zk_ctx* ctx, uint64_t work, int blocks_per_sm) {
     uint64_t blocks = (work + kThreads - 1) / kThreads;
     uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
     if (blocks > cap) blocks = cap;
+    if (ctx->grid_cap > 0 && blocks > (uint64_t)ctx->grid_cap) blocks = ctx->grid_cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
 }
@@ -126,6 +127,7 @@ static int ctx_create(zk_ctx** out, int fid, int device, void* stream, bool own_
     }
     ctx->own_stream = own_stream;
     ctx->max_grid = ctx->sm_count * 8;
+    if (const char* cap = getenv("ZKB200_GRID_CAP")) ctx->grid_cap = atoi(cap);
     ZK_CUDA(cudaMalloc(&ctx->partials, (size_t)ctx->max_grid * kMaxEvals * sizeof(Fe)));
     ZK_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
     ZK_CUDA(cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream));
@@ -471,7 +473,7 @@ extern "C" void zk_sumpoly_free(zk_ctx* ctx, zk_sumpoly* sp) {
     for (zk_table* t : sp->tabs) zk_table_free(ctx, t);
     delete sp;
 }
-extern "C" uint64_t zk_sumpoly_len(const zk_sumpoly* sp) { return sp->len; }
+extern "C" uint64_t zk_sumpoly_len(const zk_sumpoly* sp) { return sp->tabs[0]->len; }
 extern "C" zk_table* zk_sumpoly_table(const zk_sumpoly* sp, uint32_t i) { return i < sp->tabs.size() ? sp->tabs[i] : nullptr; }
 
 static TablePtrs ptrs_of(const zk_sumpoly* sp) {
@@ -483,8 +485,17 @@ static void set_len(zk_sumpoly* sp, uint64_t len) {
     sp->len = len;
     for (zk_table* t : sp->tabs) t->len = len;
 }
+// the tables may have been refilled (zk_table_regenerate) since the last operation
+static int sync_len(zk_ctx* ctx, zk_sumpoly* sp) {
+    for (zk_table* t : sp->tabs)
+        if (t->len != sp->tabs[0]->len) return fail(ctx, ZK_ERR_ASSERT, "different number of variables");
+    sp->len = sp->tabs[0]->len;
+    return ZK_OK;
+}
 
-extern "C" int zk_sumpoly_reduce(zk_ctx* ctx, const zk_sumpoly* sp, zk_table** out) {
+extern "C" int zk_sumpoly_reduce(zk_ctx* ctx, const zk_sumpoly* sp_, zk_table** out) {
+    zk_sumpoly* sp = const_cast<zk_sumpoly*>(sp_);
+    if (int rc0 = sync_len(ctx, sp)) return rc0;
     if (sp->P < 2) return fail(ctx, ZK_ERR_ASSERT, "more than one product polynomial required for add operation");
     if (sp->D < 2) return fail(ctx, ZK_ERR_ASSERT, "more than one polynomial required for mul operation");
     int rc = table_alloc(ctx, sp->len, out);
@@ -494,6 +505,7 @@ extern "C" int zk_sumpoly_reduce(zk_ctx* ctx, const zk_sumpoly* sp, zk_table** o
 }
 
 extern "C" int zk_sumcheck_round_evals(zk_ctx* ctx, zk_sumpoly* sp, uint64_t* evals) {
+    if (int rc0 = sync_len(ctx, sp)) return rc0;
     if (sp->len < 2) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
     int rc = launch_round_evals(ctx, ptrs_of(sp), sp->P, sp->D, sp->len);
     if (rc) return rc;
@@ -501,6 +513,7 @@ extern "C" int zk_sumcheck_round_evals(zk_ctx* ctx, zk_sumpoly* sp, uint64_t* ev
 }
 
 extern "C" int zk_sumcheck_fold_and_evals(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t r[4], uint64_t* evals) {
+    if (int rc0 = sync_len(ctx, sp)) return rc0;
     if (sp->len < 2) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
     HFe rr;
     memcpy(rr.l, r, 32);
@@ -529,6 +542,7 @@ static const Interpolator& interp_for(zk_ctx* ctx, int degree) {
 // sumcheck_gkr_protocol::prove -- sumcheck_gkr_protocol.rs:24-67
 extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t claimed_sum[4], zk_transcript* tr,
                                 uint64_t* coeffs_out, uint64_t* challenges_out, uint64_t* final_values, uint32_t flags) {
+    if (int rc0 = sync_len(ctx, sp)) return rc0;
     if (!is_pow2(sp->len)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
     const HostField& f = ctx->field;
     const int D = sp->D, P = sp->P, NE = D + 1;

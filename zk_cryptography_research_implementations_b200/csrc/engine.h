@@ -14,6 +14,7 @@ struct zk_ctx {
     int device = 0;
     int sm_count = 148;
     int max_grid = 148 * 8;
+    int grid_cap = 0;   // ZKB200_GRID_CAP: test hook, caps every grid (forces long grid-stride loops)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     zk::HostField field;

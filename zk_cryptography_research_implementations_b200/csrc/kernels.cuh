@@ -427,11 +427,13 @@ __global__ void __launch_bounds__(kThreads) arith_probe_kernel(Fe* out, uint32_t
             else { Fp<FID>::mul_acc(acc[c], x[c], y[c]); x[c].v[0] ^= acc[c][16]; }
         }
     }
-    Fe r = x[0];
+    Fe r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r.v[k] ^= x[c].v[k] ^ acc[c][k] ^ acc[c][k + 8];
+        for (int k = 0; k < 8; ++k) r.v[k] += x[c].v[k] * (2 * c + 1) + acc[c][k] + acc[c][k + 8];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 

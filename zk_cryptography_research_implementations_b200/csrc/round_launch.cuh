@@ -11,6 +11,7 @@ inline int launch_grid(const zk_ctx* ctx, uint64_t work, int blocks_per_sm) {
     uint64_t blocks = (work + kThreads - 1) / kThreads;
     uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
     if (blocks > cap) blocks = cap;
+    if (ctx->grid_cap > 0 && blocks > (uint64_t)ctx->grid_cap) blocks = ctx->grid_cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
 }
