@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""bench.py -- sumcheck prove throughput (field elements / s) on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--log2 n]
+
+A "step" is one complete sumcheck prove (all rounds, host Fiat-Shamir included) over one set of
+synthetic tables.  Default workload (every N): BASELINE.json configs[2], the configuration the
+north-star targets are quoted on -- degree-2 product sumcheck f*g over 2^30 entries (BN254 Fq,
+64 GiB of tables), strong scaling over the ranks (tables sharded on the low index bits, one tiny
+NCCL all-gather per round).  `--workload plain24` is configs[1] (plain sumcheck, 2^24, BLS12-381 Fr).
+
+Printed by rank 0: ONE JSON line (contract in the task statement) with `roofline` (dominant kernel vs
+the measured HBM peak), `cpu_baseline` (the oracle's single-thread restatement of the reference prover
+on a bounded sample), `e2e` (same prove through the C-ABI from pinned HOST tables, copies inside the
+timed region), `gpu_launches`, `clocks`.
+
+`--impl reference` times the reference's own algorithm on the host: the reference is single-threaded
+Rust that cannot be compiled in this image, so this runs the oracle's C restatement (oracle/zkoracle.c,
+reference pass structure, 1 thread) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 0xB200
+WORKLOADS = {
+    # name: (field id, field name, P, D, default log2 N, description)
+    "product30": (0, "BN254_FQ", 1, 2, 30, "degree-2 product sumcheck f*g (BASELINE.json configs[2])"),
+    "plain24": (2, "BLS12_381_FR", 1, 1, 24, "plain sumcheck of one MLE (BASELINE.json configs[1])"),
+    "gkr22": (0, "BN254_FQ", 2, 2, 22, "GKR-shaped 2x2 sumcheck add*(Wb+Wc)+mul*(Wb*Wc) tables"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------- CPU baseline
+def cpu_prove_once(field: int, P: int, D: int, log2: int):
+    """one prove of the oracle (reference pass structure, single thread) on a 2^log2 sample; seconds"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import coracle as co
+    from zk_cryptography_research_implementations_b200 import core
+    n = 1 << log2
+    rng = np.random.default_rng(SEED)
+    if D == 1:
+        tab = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+        tab[:, 3] &= np.uint64((1 << 58) - 1)
+        t0 = time.perf_counter()
+        co.basic_prove(field, tab)
+        return time.perf_counter() - t0
+    # the reference panics on a single product (sum_polynomial.rs:58-61): f*g is posed as f*g + 0*0
+    Pref = max(P, 2)
+    tabs = np.zeros((Pref, D, n, 4), dtype=np.uint64)
+    tabs[:P] = rng.integers(0, 1 << 62, size=(P, D, n, 4), dtype=np.uint64)
+    tabs[..., 3] &= np.uint64((1 << 58) - 1)
+    claimed = np.zeros(4, dtype=np.uint64)
+    t0 = time.perf_counter()
+    co.product_prove(field, tabs, claimed, co.Transcript())
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    field, fname, P, D, log2_default, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log2 = args.log2 or log2_default
+    sample_log2 = min(log2, args.cpu_log2)
+    for _ in range(args.warmup):
+        cpu_prove_once(field, P, D, min(sample_log2, 16))
+    times = [cpu_prove_once(field, P, D, sample_log2) for _ in range(args.steps)]
+    t = statistics.mean(times)
+    value = (1 << sample_log2) / t
+    sample = "2^%d-entry sample of the 2^%d workload, oracle C restatement of the reference prover%s, 1 thread" % (
+        sample_log2, log2, " (posed as f*g + 0*0, the only form the reference accepts)" if (P == 1 and D > 1) else "")
+    line = {
+        "impl": "reference", "metric": "sumcheck_prove_field_elements_per_s", "value": value, "unit": "elements/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery limbs)",
+        "data": "synthetic",
+        "config": config_dict(args.workload, wl, log2, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(name, wl, log2, gpus):
+    field, fname, P, D, _, desc = wl
+    return {"workload": "%s: %s" % (name, desc), "field": fname, "log2_entries": log2, "tables": P * D, "P": P, "D": D,
+            "table_bytes_total": (P * D) << (log2 + 5), "sharding": "low index bits across %d rank(s)" % gpus,
+            "l2": "inputs regenerated in HBM between steps (untimed); tables are %s than the 126 MB L2"
+                  % ("larger" if ((P * D) << (log2 + 5)) // max(gpus, 1) > 126e6 else "NOT larger"),
+            "seed": SEED}
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index: int):
+        self.path = "/tmp/zk_clocks_%d.csv" % os.getpid()
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import zk_cryptography_research_implementations_b200 as zk
+    from zk_cryptography_research_implementations_b200 import sharded
+    from zk_cryptography_research_implementations_b200.core import _ptr
+    from zk_cryptography_research_implementations_b200.transcripts import Transcript
+
+    field, fname, P, D, log2_default, desc = wl
+    log2 = args.log2 or log2_default
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = zk.Context(field, local_rank, stream=stream)
+    if world > 1:
+        sharded.init_comm(ctx)
+    lib = ctx.lib
+    T = P * D
+    N = 1 << log2
+    m = N // world                     # local entries per table
+    if m < 1:
+        raise SystemExit("table smaller than the number of ranks")
+    n_rounds = log2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident tables (this rank's shard), generated on the device
+    tabs = [ctx.generate(SEED, i, m, first=rank, step=world) for i in range(T)]
+    handles = [t.release() for t in tabs]
+    arr = (C.c_void_p * T)(*handles)
+    sp = C.c_void_p()
+    ctx.check(lib.zk_sumpoly_create(ctx.h, arr, P, D, C.byref(sp)))
+
+    def regenerate():
+        for i in range(T):
+            ctx.check(lib.zk_table_regenerate(ctx.h, lib.zk_sumpoly_table(sp, i), SEED, i, m, rank, world))
+
+    coeffs = np.zeros((n_rounds, D + 1, 4), dtype=np.uint64)
+    chal = np.zeros((n_rounds, 4), dtype=np.uint64)
+    fin = np.zeros((T, 4), dtype=np.uint64)
+    rpolys = np.zeros((n_rounds, 2, 4), dtype=np.uint64)
+    claimed = np.zeros(4, dtype=np.uint64)
+
+    def prove_resident():
+        if D == 1:
+            # plain sumcheck rounds; the 32*N-byte Keccak absorb of the table is host transcript work,
+            # reported separately (absorb_ms) and included in e2e
+            ctx.check(lib.zk_prove_basic_device(ctx.h, lib.zk_sumpoly_table(sp, 0), _ptr(claimed), _ptr(rpolys), _ptr(chal),
+                                                _ptr(fin), 2))
+        else:
+            tr = Transcript()
+            ctx.check(lib.zk_prove_product_sharded(ctx.h, sp, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(chal), _ptr(fin), 0,
+                                                   args.collapse_len))
+
+    if D == 1 and world > 1:
+        raise SystemExit("plain24 is a single-GPU workload (its transcript absorbs the whole table on the host)")
+
+    def timed_steps(fn, prep, steps, warmup, profile):
+        for _ in range(warmup):
+            prep(); barrier(); fn(); barrier()
+        ctx.set_profiling(profile)
+        ctx.reset_stats()
+        times = []
+        for _ in range(steps):
+            prep()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            barrier()
+            times.append(e0.elapsed_time(e1))
+        st = ctx.stats()
+        ctx.set_profiling(False)
+        t = torch.tensor([statistics.mean(times)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), st
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, st = timed_steps(prove_resident, regenerate, args.steps, args.warmup, True)
+    clocks = sampler.stop() if sampler else None
+    value = N / (ms * 1e-3)
+    proof_digest = int(np.bitwise_xor.reduce((coeffs if D > 1 else rpolys).reshape(-1))) & 0xFFFFFFFF
+
+    # ---- roofline of the dominant kernel family (round kernels), CUDA events on the launching stream
+    hbm_peak, peak_src = peaks()
+    achieved = st["round_bytes"] / (st["round_ms"] * 1e-3) / 1e9 if st["round_ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "fold_evals_kernel / round_evals_kernel <%s,P=%d,D=%d> (all %d launches of %d steps, rank 0)"
+                          % (fname, P, D, st["round_launches"], args.steps),
+                "algorithmic_bytes_per_step_per_rank": st["round_bytes"] / max(args.steps, 1),
+                "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)}
+    launches = st["launches"]
+
+    # ---- integer-multiply ceiling (register-resident probe, same clocks)
+    integer = {}
+    if rank == 0 and not args.no_probe:
+        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced")):
+            ops, pms = C.c_double(), C.c_double()
+            ctx.check(lib.zk_arith_probe(ctx.h, kind, 1500, 2, C.byref(ops), C.byref(pms)))
+            integer[name + "_Gops"] = ops.value / 1e9
+
+    # ---- e2e: the same prove through the C-ABI from pinned HOST tables (H2D of the inputs every step)
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for i in range(T):
+            p = C.c_void_p()
+            if lib.zk_pinned_alloc(C.c_size_t(m * 32), C.byref(p)) != 0:
+                raise SystemExit("cudaHostAlloc of %d bytes failed" % (m * 32))
+            host.append(p)
+        regenerate()
+        for i in range(T):
+            ctx.check(lib.zk_table_download(ctx.h, lib.zk_sumpoly_table(sp, i), C.cast(host[i], C.POINTER(C.c_uint64))))
+
+        def upload_and_prove():
+            for i in range(T):
+                ctx.check(lib.zk_table_upload_into(ctx.h, lib.zk_sumpoly_table(sp, i), host[i], m))
+            if D == 1:
+                ctx.check(lib.zk_prove_basic_device(ctx.h, lib.zk_sumpoly_table(sp, 0), _ptr(claimed), _ptr(rpolys), _ptr(chal),
+                                                    _ptr(fin), 0))   # full prove(): table absorb included
+            else:
+                tr = Transcript()
+                ctx.check(lib.zk_prove_product_sharded(ctx.h, sp, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(chal), _ptr(fin), 0,
+                                                       args.collapse_len))
+
+        e_steps = max(1, min(args.steps, args.e2e_steps))
+        ms_e2e, _ = timed_steps(upload_and_prove, lambda: None, e_steps, 1, False)
+        d2h = (n_rounds * (D + 1 if D > 1 else 2) + T + 1) * 32
+        e2e = {"value": N / (ms_e2e * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": T * m * 32 * world,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
+               "call": "zk_table_upload_into (pinned host -> HBM) + %s" % ("zk_prove_basic_device incl. the Keccak absorb of the table"
+                                                                           if D == 1 else "zk_prove_product_sharded")}
+        for p in host:
+            lib.zk_pinned_free(p)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample_log2 = min(log2, args.cpu_log2)
+        t = cpu_prove_once(field, P, D, sample_log2)
+        cpu = {"value": (1 << sample_log2) / t, "unit": "elements/s", "cores": 1, "kind": "port",
+               "sample": "one prove of a 2^%d-entry sample (%.1f s) by oracle/zkoracle.c -- C restatement of the single-threaded "
+                         "reference prover with its pass structure; host has %d cores" % (sample_log2, t, os.cpu_count() or 0)}
+
+    if rank == 0:
+        line = {
+            "metric": "sumcheck_prove_field_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
+            "config": config_dict(args.workload, wl, log2, world),
+            "roofline": roofline, "integer_roofline": integer, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "proof_digest": proof_digest,
+        }
+        if D == 1:
+            line["config"]["note"] = ("value = the n fused rounds with the host Fiat-Shamir per round, table already absorbed; "
+                                      "e2e = full Prover::prove from a host table incl. the 32*N-byte serial Keccak absorb")
+        print(json.dumps(line), flush=True)
+    lib.zk_sumpoly_free(ctx.h, sp)
+    barrier()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="product30", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2", type=int, default=0, help="override log2(entries per table)")
+    ap.add_argument("--collapse-len", type=int, default=1 << 12, dest="collapse_len")
+    ap.add_argument("--cpu-log2", type=int, default=21, dest="cpu_log2", help="size of the CPU baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-probe", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,11 @@ int  zk_fe_add(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t 
 int  zk_fe_sub(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
 int  zk_fe_mul(int field_id, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
 
+/* DenseUnivariatePolynomial::lagrange_interpolate on x = 0..n_evals-1 (polynomials/src/univariate/dense_univariate.rs:74-98)
+ * and ::evaluate (:57-68) */
+int  zk_interpolate_evals(int field_id, uint32_t n_evals, const uint64_t *evals, uint64_t *coeffs);
+int  zk_univariate_evaluate(int field_id, const uint64_t *coeffs, uint32_t n, const uint64_t x[4], uint64_t out[4]);
+
 /* ---- transcript: transcripts/src/fiat_shamir/fiat_shamir_transcript.rs:5-43 (host, Keccak-256) ---- */
 zk_transcript *zk_transcript_new(void);                                              /* Transcript::new :12-16 */
 void zk_transcript_free(zk_transcript *);
@@ -78,6 +83,10 @@ int  zk_table_regenerate(zk_ctx *, zk_table *, uint64_t seed, uint64_t table_id,
 int  zk_table_wrap(zk_ctx *, void *device_ptr, uint64_t n, zk_table **out);
 int  zk_table_clone(zk_ctx *, const zk_table *, zk_table **out);                      /* Clone */
 int  zk_table_download(zk_ctx *, const zk_table *, uint64_t *out_limbs);              /* .evaluated_values */
+/* refill an existing table from host memory, asynchronously on the context's stream (end-to-end input copy) */
+int  zk_table_upload_into(zk_ctx *, zk_table *, const uint64_t *mont_limbs, uint64_t n);
+int  zk_pinned_alloc(size_t bytes, void **out);     /* page-locked host memory for the copies above */
+void zk_pinned_free(void *p);
 uint64_t zk_table_len(const zk_table *);
 void *zk_table_device_ptr(const zk_table *);
 void zk_table_free(zk_ctx *, zk_table *);
@@ -129,6 +138,22 @@ int  zk_prove_basic(zk_ctx *, const uint64_t *host_table, uint64_t n, uint64_t c
 int  zk_prove_product_host(zk_ctx *, const uint64_t *host_tables, uint32_t P, uint32_t D, uint64_t n,
                            const uint64_t claimed_sum[4], zk_transcript *, uint64_t *coeffs, uint64_t *challenges,
                            uint64_t *final_values, uint32_t flags);
+
+/* ---- one process per GPU: tables sharded on the LOW index bits (rank q holds entries q, q+G, q+2G, ...) ----
+ * NCCL over NVLink/NVSwitch carries one all-gather of (D+1) elements per round; folds stay local.
+ * Rank 0 calls zk_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed, MPI, ...). */
+int  zk_comm_unique_id(uint8_t out[128]);
+int  zk_comm_init(zk_ctx *, int rank, int world, const uint8_t id[128]);   /* world: power of two */
+int  zk_comm_destroy(zk_ctx *);
+int  zk_comm_rank(const zk_ctx *);
+int  zk_comm_world(const zk_ctx *);
+/* sumcheck_gkr_protocol::prove with `sp` holding this rank's shard; same outputs on every rank.  When the
+ * local tables are down to `collapse_len` entries they are gathered and the rest runs unsharded. */
+int  zk_prove_product_sharded(zk_ctx *, zk_sumpoly *sp, const uint64_t claimed_sum[4], zk_transcript *,
+                              uint64_t *coeffs, uint64_t *challenges, uint64_t *final_values, uint32_t flags,
+                              uint64_t collapse_len);
+/* MultilinearPolynomial::evaluate over a sharded table (values: all log2(global length) challenges) */
+int  zk_mle_evaluate_sharded(zk_ctx *, const zk_table *local, const uint64_t *values, uint32_t n_values, uint64_t out[4]);
 
 /* ---- measurement: register-resident field arithmetic, no memory traffic (the IMAD-pipe ceiling) ----
  * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate. */

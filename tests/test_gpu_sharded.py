@@ -1,0 +1,93 @@
+"""Two ranks on two GPUs (skipped with fewer): the native sharded prover (NCCL all-gather per round,
+csrc/comm.cu) and the Python round loop over torch.distributed, both against the unsharded oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import coracle as co
+    import zk_cryptography_research_implementations_b200 as zk
+    from zk_cryptography_research_implementations_b200 import sharded
+    from zk_cryptography_research_implementations_b200.core import _ptr
+    from zk_cryptography_research_implementations_b200.transcripts import Transcript
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    ok = True
+    try:
+        fid = 0
+        ctx = zk.Context(fid, rank)
+        sharded.init_comm(ctx)
+        for (P, D, n, collapse) in [(2, 2, 9, 1), (2, 2, 12, 64), (1, 2, 14, 256), (2, 3, 8, 4)]:
+            N = 1 << n
+            full = np.stack([np.stack([np.array(zk.fe_from_ints(fid, zk.synthetic_table_ints(fid, 5, p * D + d, N))) for d in range(D)]) for p in range(P)])
+            Pref = max(P, 2)
+            ref_tabs = np.zeros((Pref, D, N, 4), dtype=np.uint64)
+            ref_tabs[:P] = full
+            claimed = np.zeros(4, dtype=np.uint64)
+            co.lib().zko_fe_sum(fid, co._p(co.sumpoly_reduce(fid, ref_tabs)), N, co._p(claimed))
+            want = co.product_prove(fid, ref_tabs, claimed, co.Transcript())
+            # native driver, shard generated on the device
+            tabs = [ctx.generate(5, i, N // world, first=rank, step=world) for i in range(P * D)]
+            arr = (C.c_void_p * (P * D))(*[t.release() for t in tabs])
+            sp = C.c_void_p()
+            ctx.check(ctx.lib.zk_sumpoly_create(ctx.h, arr, P, D, C.byref(sp)))
+            tr = Transcript()
+            got = sharded.prove_product_native(ctx, sp, P, D, n, claimed, tr, collapse_len=collapse)
+            ctx.lib.zk_sumpoly_free(ctx.h, sp)
+            ok &= np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2].reshape(P, D, 4), want[2][:P])
+            # Python round loop over torch.distributed (NCCL), CUDA engine
+            shard = np.stack([np.stack([sharded.shard_of(full[p, d], rank, world) for d in range(D)]) for p in range(P)])
+            eng = sharded.CudaShardEngine(ctx, shard)
+            got2 = sharded.prove_product(eng, fid, n, claimed, Transcript(), collapse_len=collapse)
+            eng.close()
+            ok &= np.array_equal(got2[0], want[0]) and np.array_equal(got2[1], want[1])
+            # sharded MLE evaluate
+            local = ctx.generate(5, 0, N // world, first=rank, step=world)
+            out = np.zeros(4, dtype=np.uint64)
+            ctx.check(ctx.lib.zk_mle_evaluate_sharded(ctx.h, local.h, _ptr(np.ascontiguousarray(want[1])), n, _ptr(out)))
+            ok &= np.array_equal(out, co.mle_evaluate(fid, full[0, 0], want[1]))
+        q.put((rank, bool(ok)))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_prover_matches_oracle():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]

@@ -35,6 +35,8 @@ SIGNATURES = {
     "zk_fe_add": (C.c_int, [C.c_int, u64p, u64p, u64p]),
     "zk_fe_sub": (C.c_int, [C.c_int, u64p, u64p, u64p]),
     "zk_fe_mul": (C.c_int, [C.c_int, u64p, u64p, u64p]),
+    "zk_interpolate_evals": (C.c_int, [C.c_int, C.c_uint32, u64p, u64p]),
+    "zk_univariate_evaluate": (C.c_int, [C.c_int, u64p, C.c_uint32, u64p, u64p]),
     "zk_transcript_new": (vp, []),
     "zk_transcript_free": (None, [vp]),
     "zk_transcript_append": (None, [vp, C.c_char_p, C.c_size_t]),
@@ -46,6 +48,9 @@ SIGNATURES = {
     "zk_table_wrap": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(vp)]),
     "zk_table_clone": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "zk_table_download": (C.c_int, [vp, vp, u64p]),
+    "zk_table_upload_into": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "zk_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "zk_pinned_free": (None, [vp]),
     "zk_table_len": (C.c_uint64, [vp]),
     "zk_table_device_ptr": (vp, [vp]),
     "zk_table_free": (None, [vp, vp]),
@@ -69,6 +74,13 @@ SIGNATURES = {
     "zk_prove_basic": (C.c_int, [vp, u64p, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint32]),
     "zk_prove_product_host": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, C.c_uint64, u64p, vp, u64p, u64p, u64p,
                                         C.c_uint32]),
+    "zk_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "zk_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
+    "zk_comm_destroy": (C.c_int, [vp]),
+    "zk_comm_rank": (C.c_int, [vp]),
+    "zk_comm_world": (C.c_int, [vp]),
+    "zk_prove_product_sharded": (C.c_int, [vp, vp, u64p, vp, u64p, u64p, u64p, C.c_uint32, C.c_uint64]),
+    "zk_mle_evaluate_sharded": (C.c_int, [vp, vp, u64p, C.c_uint32, u64p]),
     "zk_arith_probe": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -1,0 +1,278 @@
+// comm.cu -- one process per GPU: tables sharded across ranks, one tiny exchange per round.
+//
+// Partition: with G = 2^g ranks, rank q holds the entries whose LOW g index bits are q
+// (local j <-> global j*G + q).  The prover binds variables MSB first, so every fold pairs
+// (j, j + M/2) inside one rank: folds never communicate.  Per round each rank's kernel produces
+// partial evaluations of the round polynomial; an NCCL all-gather over NVLink moves the G x (d+1)
+// elements, every rank adds them in the field and runs the same host transcript, so the challenge
+// needs no broadcast.  When the local tables shrink to `collapse_len` entries they are all-gathered
+// and interleaved, and the remaining rounds run redundantly on every rank with no communication.
+//
+// NCCL is resolved with dlopen (the copy torch already loaded), so the library still loads on a
+// CPU-only box; nothing here runs without a GPU.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+using namespace zk;
+
+#define ZK_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) {                                            \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); \
+            return ZK_ERR_CUDA;                                              \
+        }                                                                    \
+    } while (0)
+
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define ZK_SYM(field, name)                                                         \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, name));                 \
+    if (!field) { error = std::string("dlsym ") + name; handle = nullptr; return false; }
+        ZK_SYM(GetUniqueId, "ncclGetUniqueId")
+        ZK_SYM(CommInitRank, "ncclCommInitRank")
+        ZK_SYM(CommDestroy, "ncclCommDestroy")
+        ZK_SYM(AllGather, "ncclAllGather")
+        ZK_SYM(GroupStart, "ncclGroupStart")
+        ZK_SYM(GroupEnd, "ncclGroupEnd")
+        ZK_SYM(GetErrorString, "ncclGetErrorString")
+#undef ZK_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+#define ZK_NCCL(call)                                                                   \
+    do {                                                                                \
+        ncclResult_t r__ = (call);                                                      \
+        if (r__ != ncclSuccess) {                                                       \
+            ctx->err = std::string(#call) + ": " + g_nccl.GetErrorString(r__);          \
+            return ZK_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+inline bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
+inline uint32_t ilog2(uint64_t n) { uint32_t k = 0; while (n >>= 1) ++k; return k; }
+
+// gathered[q][j] (rank-major, m entries per rank) -> out[j * G + q]: the sharded variables become
+// the low index bits of one table again
+__global__ void __launch_bounds__(kThreads) interleave_kernel(const Fe* gathered, Fe* out, uint64_t m, uint32_t G) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, total = m * G;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        uint64_t j = i / G, q = i % G;
+        st256(out + i, ld256(gathered + q * m + j));
+    }
+}
+}  // namespace
+
+extern "C" int zk_comm_unique_id(uint8_t out[128]) {
+    if (!g_nccl.load()) return ZK_ERR_CUDA;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ZK_ERR_CUDA;
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    memcpy(out, &id, 128);
+    return ZK_OK;
+}
+
+extern "C" int zk_comm_init(zk_ctx* ctx, int rank, int world, const uint8_t id_bytes[128]) {
+    if (world < 1 || !is_pow2((uint64_t)world) || rank < 0 || rank >= world) return fail(ctx, ZK_ERR_ARG, "world must be a power of two, 0 <= rank < world");
+    if (ctx->nccl_comm) return fail(ctx, ZK_ERR_ARG, "communicator already initialised");
+    if (!g_nccl.load()) { ctx->err = g_nccl.error; return ZK_ERR_CUDA; }
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, 128);
+    ncclComm_t comm;
+    ZK_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    ZK_CUDA(cudaMalloc(&ctx->xchg_send, kMaxEvals * sizeof(Fe)));
+    ZK_CUDA(cudaMalloc(&ctx->xchg_recv, (size_t)world * kMaxEvals * sizeof(Fe)));
+    ZK_CUDA(cudaHostAlloc(&ctx->xchg_host, (size_t)world * kMaxEvals * sizeof(Fe), cudaHostAllocDefault));
+    return ZK_OK;
+}
+
+extern "C" int zk_comm_destroy(zk_ctx* ctx) {
+    if (!ctx->nccl_comm) return ZK_OK;
+    cudaStreamSynchronize(ctx->stream);
+    g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    cudaFree(ctx->xchg_send);
+    cudaFree(ctx->xchg_recv);
+    cudaFreeHost(ctx->xchg_host);
+    ctx->xchg_send = ctx->xchg_recv = ctx->xchg_host = nullptr;
+    ctx->world = 1;
+    ctx->rank = 0;
+    return ZK_OK;
+}
+
+extern "C" int zk_comm_rank(const zk_ctx* ctx) { return ctx->rank; }
+extern "C" int zk_comm_world(const zk_ctx* ctx) { return ctx->world; }
+
+// all ranks: sum over ranks of the `ne` elements the last round kernel published (field addition is
+// not an NCCL reduction, so: all-gather the raw elements, add mod p on the host)
+static int exchange_sum(zk_ctx* ctx, HFe* vals, int ne) {
+    const HostField& f = ctx->field;
+    const int G = ctx->world;
+    const size_t bytes = (size_t)ne * sizeof(Fe);
+    // the kernel published into mapped host memory; stage a device copy for NCCL on the same stream
+    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_send, ctx->result_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    ZK_NCCL(g_nccl.AllGather(ctx->xchg_send, ctx->xchg_recv, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_host, ctx->xchg_recv, bytes * G, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    const HFe* all = reinterpret_cast<const HFe*>(ctx->xchg_host);
+    for (int e = 0; e < ne; ++e) {
+        HFe acc = f.zero();
+        for (int q = 0; q < G; ++q) acc = f.add(acc, all[(size_t)q * ne + e]);
+        vals[e] = acc;
+    }
+    return ZK_OK;
+}
+
+// all-gather every table of the sumpoly and interleave: afterwards each rank holds the full tables
+static int collapse(zk_ctx* ctx, zk_sumpoly* sp) {
+    const int G = ctx->world;
+    const uint64_t m = sp->len;
+    int rc = ensure_scratch(ctx, (size_t)G * m * sizeof(Fe));
+    if (rc) return rc;
+    for (zk_table* t : sp->tabs) {
+        ZK_NCCL(g_nccl.AllGather(t->d, ctx->scratch, (size_t)m * sizeof(Fe), ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+        if (t->cap < m * G) {
+            if (!t->owned) return fail(ctx, ZK_ERR_ARG, "collapse: wrapped table too small to hold the gathered table");
+            ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+            ZK_CUDA(cudaFree(t->d));
+            ZK_CUDA(cudaMalloc(&t->d, (size_t)m * G * sizeof(Fe)));
+            t->cap = m * G;
+        }
+        uint64_t blocks = (m * G + kThreads - 1) / kThreads;
+        if (blocks > (uint64_t)ctx->sm_count * 4) blocks = (uint64_t)ctx->sm_count * 4;
+        interleave_kernel<<<(int)blocks, kThreads, 0, ctx->stream>>>((const Fe*)ctx->scratch, t->d, m, (uint32_t)G);
+        ctx->launches++;
+        ZK_CUDA(cudaGetLastError());
+    }
+    set_len(sp, m * G);
+    return ZK_OK;
+}
+
+// sumcheck_gkr_protocol::prove over tables sharded across the communicator's ranks.
+// `sp` holds this rank's shard (global length = world * local length).  Outputs as zk_prove_product;
+// every rank returns the same proof.
+extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t claimed_sum[4], zk_transcript* tr,
+                                        uint64_t* coeffs_out, uint64_t* challenges_out, uint64_t* final_values,
+                                        uint32_t flags, uint64_t collapse_len) {
+    if (int rc0 = sync_len(ctx, sp)) return rc0;
+    if (ctx->world == 1) return zk_prove_product(ctx, sp, claimed_sum, tr, coeffs_out, challenges_out, final_values, flags);
+    if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_ARG, "zk_comm_init has not been called");
+    if (!is_pow2(sp->len)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
+    if (collapse_len < 1) collapse_len = 1;
+    const HostField& f = ctx->field;
+    const int D = sp->D, P = sp->P, NE = D + 1, G = ctx->world;
+    const uint32_t n = ilog2(sp->len) + ilog2((uint64_t)G);
+    const Interpolator& ip = interp_for(ctx, D);
+    HFe claim;
+    memcpy(claim.l, claimed_sum, 32);
+    tr->t.append_be(f, claim);
+    HFe evals[kMaxEvals], coeffs[kMaxEvals], r = f.zero(), running = claim;
+    bool sharded = true;
+    for (uint32_t k = 0; k < n; ++k) {
+        const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
+        int rc;
+        bool need_plain_evals = (k == 0);
+        if (k > 0 && sharded && sp->len / 2 <= collapse_len) {
+            // fold by r_{k-1} locally, then gather: the remaining rounds run on the full table
+            rc = launch_fold0(ctx, ptrs_of(sp), P * D, sp->len, make_fold_table(f, r));
+            if (rc) return rc;
+            set_len(sp, sp->len / 2);
+            rc = collapse(ctx, sp);
+            if (rc) return rc;
+            sharded = false;
+            need_plain_evals = true;
+        }
+        if (k == 0 && sp->len <= collapse_len) {   // tiny input: gather straight away
+            rc = collapse(ctx, sp);
+            if (rc) return rc;
+            sharded = false;
+        }
+        TablePtrs tp = ptrs_of(sp);
+        if (need_plain_evals) {
+            rc = launch_round_evals(ctx, tp, P, D, sp->len);
+        } else {
+            rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1);
+            set_len(sp, sp->len / 2);
+        }
+        if (rc) return rc;
+        if (sharded) rc = exchange_sum(ctx, evals, NE);
+        else rc = fetch_result(ctx, evals, NE);
+        if (rc) return rc;
+        if (skip1 && !need_plain_evals) evals[1] = f.sub(running, evals[0]);
+        ip.coefficients(evals, coeffs);
+        uint8_t bytes[32 * kMaxEvals];
+        for (int i = 0; i < NE; ++i) f.to_bytes_le(coeffs[i], bytes + 32 * i);
+        tr->t.append(bytes, 32 * NE);
+        r = tr->t.challenge(f);
+        running = f.horner(coeffs, NE, r);
+        memcpy(coeffs_out + (size_t)k * NE * 4, coeffs, 32 * NE);
+        memcpy(challenges_out + (size_t)k * 4, r.l, 32);
+    }
+    if (sharded) return fail(ctx, ZK_ERR_ARG, "internal: tables still sharded after the last round");
+    int rc = launch_fold0(ctx, ptrs_of(sp), P * D, sp->len, make_fold_table(f, r));
+    if (rc) return rc;
+    set_len(sp, sp->len / 2);
+    if (final_values) {
+        for (int t = 0; t < P * D; ++t)
+            ZK_CUDA(cudaMemcpyAsync(final_values + 4 * t, sp->tabs[t]->d, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+// MultilinearPolynomial::evaluate over a sharded table: each rank binds the leading n-g variables of
+// its shard (no communication), the G survivors are gathered and the last g variables are bound on
+// the host.  `values` holds all n challenges; every rank returns the same element.
+extern "C" int zk_mle_evaluate_sharded(zk_ctx* ctx, const zk_table* local, const uint64_t* values, uint32_t n_values, uint64_t out[4]) {
+    if (ctx->world == 1) return zk_mle_evaluate(ctx, local, values, n_values, out);
+    if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_ARG, "zk_comm_init has not been called");
+    const int G = ctx->world;
+    const uint32_t g = ilog2((uint64_t)G), nl = ilog2(zk_table_len(local));
+    if (n_values != nl + g) return fail(ctx, ZK_ERR_ARG, "sharded evaluate needs exactly log2(global length) values");
+    HFe mine;
+    int rc = zk_mle_evaluate(ctx, local, values, nl, mine.l);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_send, mine.l, sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_NCCL(g_nccl.AllGather(ctx->xchg_send, ctx->xchg_recv, sizeof(Fe), ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_host, ctx->xchg_recv, sizeof(Fe) * G, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the gathered vector is the table over the g low variables (entry q = shard q); bind them MSB first
+    const HostField& f = ctx->field;
+    std::vector<HFe> cur(reinterpret_cast<const HFe*>(ctx->xchg_host), reinterpret_cast<const HFe*>(ctx->xchg_host) + G);
+    for (uint32_t i = 0; i < g; ++i) {
+        HFe rr;
+        memcpy(rr.l, values + 4 * (nl + i), 32);
+        size_t half = cur.size() / 2;
+        for (size_t j = 0; j < half; ++j) cur[j] = f.add(cur[j], f.mul(rr, f.sub(cur[j + half], cur[j])));
+        cur.resize(half);
+    }
+    memcpy(out, cur[0].l, 32);
+    return ZK_OK;
+}

@@ -32,12 +32,12 @@ using namespace zk;
 static inline bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
 static inline uint32_t ilog2(uint64_t n) { uint32_t k = 0; while (n >>= 1) ++k; return k; }
 
-static int fail(zk_ctx* ctx, int code, const char* msg) {
+int fail(zk_ctx* ctx, int code, const char* msg) {
     ctx->err = msg;
     return code;
 }
 
-static FoldTable make_fold_table(const HostField& f, const HFe& r_mont) {
+FoldTable make_fold_table(const HostField& f, const HFe& r_mont) {
     // tab[i] = r * 2^(32 i) mod p as PLAIN integers (see fp.cuh FoldScalar)
     FoldTable ft;
     HFe cur = f.from_mont(r_mont);
@@ -148,7 +148,9 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    zk_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
     cudaFreeHost(ctx->result_host);
@@ -177,7 +179,7 @@ extern "C" int zk_ctx_get_stats(zk_ctx* ctx, uint64_t* launches, uint64_t* round
     return ZK_OK;
 }
 
-static int ensure_scratch(zk_ctx* ctx, size_t bytes) {
+int ensure_scratch(zk_ctx* ctx, size_t bytes) {
     if (ctx->scratch_bytes >= bytes) return ZK_OK;
     if (ctx->scratch) {
         ZK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -225,6 +227,26 @@ ZK_HOST_BINARY(zk_fe_add, add)
 ZK_HOST_BINARY(zk_fe_sub, sub)
 ZK_HOST_BINARY(zk_fe_mul, mul)
 
+// DenseUnivariatePolynomial::lagrange_interpolate on the nodes 0..n-1 (dense_univariate.rs:74-98) and
+// ::evaluate (:57-68) -- the per-round host work of the product prover, exported for callers that keep
+// the round loop (and the transcript) on their side.
+extern "C" int zk_interpolate_evals(int fid, uint32_t n_evals, const uint64_t* evals, uint64_t* coeffs) {
+    if (fid < 0 || fid >= ZKF_NUM_FIELDS || n_evals < 1 || n_evals > 16) return ZK_ERR_ARG;
+    HostField f(fid);
+    Interpolator ip(f, (int)n_evals - 1);
+    ip.coefficients(reinterpret_cast<const HFe*>(evals), reinterpret_cast<HFe*>(coeffs));
+    return ZK_OK;
+}
+extern "C" int zk_univariate_evaluate(int fid, const uint64_t* coeffs, uint32_t n, const uint64_t x[4], uint64_t out[4]) {
+    if (fid < 0 || fid >= ZKF_NUM_FIELDS) return ZK_ERR_ARG;
+    HostField f(fid);
+    HFe xx;
+    memcpy(xx.l, x, 32);
+    HFe r = f.horner(reinterpret_cast<const HFe*>(coeffs), (int)n, xx);
+    memcpy(out, r.l, 32);
+    return ZK_OK;
+}
+
 // =================================================================================== transcript
 extern "C" zk_transcript* zk_transcript_new(void) { return new zk_transcript(); }
 extern "C" void zk_transcript_free(zk_transcript* t) { delete t; }
@@ -237,7 +259,7 @@ extern "C" void zk_transcript_challenge(zk_transcript* t, int fid, uint64_t out[
 }
 
 // =================================================================================== tables
-static int table_alloc(zk_ctx* ctx, uint64_t n, zk_table** out) {
+int table_alloc(zk_ctx* ctx, uint64_t n, zk_table** out) {
     std::unique_ptr<zk_table> t(new zk_table());
     t->len = n;
     t->cap = n;
@@ -289,6 +311,17 @@ extern "C" int zk_table_download(zk_ctx* ctx, const zk_table* t, uint64_t* out_l
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZK_OK;
 }
+// asynchronous refill of an existing table from (pinned) host memory -- the per-step input copy of an
+// end-to-end call; ordered on the context's stream, no synchronisation
+extern "C" int zk_table_upload_into(zk_ctx* ctx, zk_table* t, const uint64_t* limbs, uint64_t n) {
+    if (!is_pow2(n)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
+    if (n > t->cap) return fail(ctx, ZK_ERR_ARG, "upload_into: table capacity too small");
+    t->len = n;
+    ZK_CUDA(cudaMemcpyAsync(t->d, limbs, (size_t)n * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    return ZK_OK;
+}
+extern "C" int zk_pinned_alloc(size_t bytes, void** out) { return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? ZK_OK : ZK_ERR_CUDA; }
+extern "C" void zk_pinned_free(void* p) { cudaFreeHost(p); }
 extern "C" uint64_t zk_table_len(const zk_table* t) { return t->len; }
 extern "C" void* zk_table_device_ptr(const zk_table* t) { return t->d; }
 extern "C" void zk_table_free(zk_ctx* ctx, zk_table* t) {
@@ -476,17 +509,17 @@ extern "C" void zk_sumpoly_free(zk_ctx* ctx, zk_sumpoly* sp) {
 extern "C" uint64_t zk_sumpoly_len(const zk_sumpoly* sp) { return sp->tabs[0]->len; }
 extern "C" zk_table* zk_sumpoly_table(const zk_sumpoly* sp, uint32_t i) { return i < sp->tabs.size() ? sp->tabs[i] : nullptr; }
 
-static TablePtrs ptrs_of(const zk_sumpoly* sp) {
+TablePtrs ptrs_of(const zk_sumpoly* sp) {
     TablePtrs tp{};
     for (size_t i = 0; i < sp->tabs.size(); ++i) tp.t[i] = sp->tabs[i]->d;
     return tp;
 }
-static void set_len(zk_sumpoly* sp, uint64_t len) {
+void set_len(zk_sumpoly* sp, uint64_t len) {
     sp->len = len;
     for (zk_table* t : sp->tabs) t->len = len;
 }
 // the tables may have been refilled (zk_table_regenerate) since the last operation
-static int sync_len(zk_ctx* ctx, zk_sumpoly* sp) {
+int sync_len(zk_ctx* ctx, zk_sumpoly* sp) {
     for (zk_table* t : sp->tabs)
         if (t->len != sp->tabs[0]->len) return fail(ctx, ZK_ERR_ASSERT, "different number of variables");
     sp->len = sp->tabs[0]->len;
@@ -533,7 +566,7 @@ extern "C" int zk_sumcheck_fold_and_evals(zk_ctx* ctx, zk_sumpoly* sp, const uin
 }
 
 // =================================================================================== one-shot provers
-static const Interpolator& interp_for(zk_ctx* ctx, int degree) {
+const Interpolator& interp_for(zk_ctx* ctx, int degree) {
     auto it = ctx->interps.find(degree);
     if (it == ctx->interps.end()) it = ctx->interps.emplace(degree, Interpolator(ctx->field, degree)).first;
     return it->second;

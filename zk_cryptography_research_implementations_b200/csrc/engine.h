@@ -35,6 +35,12 @@ struct zk_ctx {
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
     std::string err;
+    // one-process-per-GPU sharding (comm.cu): NCCL communicator + exchange buffers
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    zk::Fe* xchg_send = nullptr;   // device, kMaxEvals elements
+    zk::Fe* xchg_recv = nullptr;   // device, world * kMaxEvals elements
+    zk::Fe* xchg_host = nullptr;   // pinned, world * kMaxEvals elements
 };
 
 struct zk_table {

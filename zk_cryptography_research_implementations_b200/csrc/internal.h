@@ -1,0 +1,20 @@
+// internal.h -- engine.cu entry points shared with comm.cu
+#pragma once
+#include "../../include/zk_sumcheck.h"
+#include "engine.h"
+#include "kernels.cuh"
+
+int fail(zk_ctx* ctx, int code, const char* msg);
+zk::FoldTable make_fold_table(const zk::HostField& f, const zk::HFe& r_mont);
+const zk::Interpolator& interp_for(zk_ctx* ctx, int degree);
+zk::TablePtrs ptrs_of(const zk_sumpoly* sp);
+void set_len(zk_sumpoly* sp, uint64_t len);
+int sync_len(zk_ctx* ctx, zk_sumpoly* sp);
+int table_alloc(zk_ctx* ctx, uint64_t n, zk_table** out);
+int ensure_scratch(zk_ctx* ctx, size_t bytes);
+namespace zk {
+int fetch_result(zk_ctx* ctx, HFe* out, int ne);
+int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len);
+int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1);
+int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, const FoldTable& ft);
+}
