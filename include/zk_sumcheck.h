@@ -139,6 +139,26 @@ int  zk_prove_product_host(zk_ctx *, const uint64_t *host_tables, uint32_t P, ui
                            const uint64_t claimed_sum[4], zk_transcript *, uint64_t *coeffs, uint64_t *challenges,
                            uint64_t *final_values, uint32_t flags);
 
+/* ---- circuit + GKR (circuit/src/arithmetic_circuit.rs, gkr/src/gkr_protocol.rs) ----
+ * Layers output-first as in the reference; gates of layer i are entries [layer_off[i], layer_off[i+1]) of
+ * left/right/out/op (op 0 = Add, 1 = Mul). */
+typedef struct {
+    uint32_t n_layers;
+    const uint64_t *layer_off;   /* n_layers + 1 */
+    const uint32_t *left, *right, *out;
+    const uint8_t *op;
+} zk_circuit_desc;
+/* Circuit::evaluate (arithmetic_circuit.rs:65-109), host: sizes[n_layers+1], values concatenated output-first */
+int  zk_circuit_evaluate(int field_id, const zk_circuit_desc *, const uint64_t *inputs, uint64_t n_inputs,
+                         uint64_t *sizes, uint64_t *values, uint64_t values_cap);
+uint64_t zk_gkr_total_rounds(uint32_t n_layers);   /* sum over layers of 2(i+1) */
+/* gkr_protocol::prove (gkr_protocol.rs:26-143) for reference-shaped circuits (layer i: i output bits -- one at
+ * layer 0 -- and i+1 bits per input index).  Proof{circuit_output, claimed_sum, sumcheck_proofs, wb/wc_evaluations}
+ * flattened: layer_claims[L], coeffs[rounds*3], challenges[rounds], wb[L-1], wc[L-1]. */
+int  zk_gkr_prove(zk_ctx *, const zk_circuit_desc *, const uint64_t *inputs, uint64_t n_inputs,
+                  uint64_t *output, uint64_t output_cap, uint64_t *n_output, uint64_t claimed_sum[4],
+                  uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges, uint64_t *wb, uint64_t *wc);
+
 /* ---- one process per GPU: tables sharded on the LOW index bits (rank q holds entries q, q+G, q+2G, ...) ----
  * NCCL over NVLink/NVSwitch carries one all-gather of (D+1) elements per round; folds stay local.
  * Rank 0 calls zk_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed, MPI, ...). */

@@ -1,0 +1,112 @@
+"""GKR prover on the GPU against the oracle's dense restatement of gkr_protocol::prove, bit for bit, and
+verified by the restated reference verifier."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import FIELDS
+
+pytestmark = pytest.mark.gpu
+
+
+def make_circuit(zk, fid, layers):
+    from zk_cryptography_research_implementations_b200.circuit import Circuit, Gate, Layer
+    return Circuit.new(fid, [Layer.new([Gate.new(*g) for g in l]) for l in layers])
+
+
+def check_against_oracle(zk, co, ctx, fid, layers, inputs_ints, verify=True):
+    from zk_cryptography_research_implementations_b200 import gkr
+    circuit = make_circuit(zk, fid, layers)
+    I = zk.fe_from_ints(fid, inputs_ints)
+    proof = gkr.prove(ctx, circuit, I)
+    oc = co.Circuit(layers)
+    want = co.gkr_prove(fid, oc, I)
+    assert np.array_equal(proof.circuit_output, want.circuit_output)
+    assert np.array_equal(proof.claimed_sum, want.claimed_sum)
+    got_coeffs = np.concatenate([np.stack([p.coefficients for p in sp.round_univariate_polynomials]) for sp in proof.sumcheck_proofs])
+    assert np.array_equal(got_coeffs, want.coeffs)
+    assert np.array_equal(np.concatenate([sp.random_challenges for sp in proof.sumcheck_proofs]), want.challenges)
+    assert np.array_equal(np.stack([sp.claimed_sum for sp in proof.sumcheck_proofs]), want.layer_claims)
+    L = len(layers)
+    assert np.array_equal(proof.wb_evaluations, want.wb[: L - 1]) and np.array_equal(proof.wc_evaluations, want.wc[: L - 1])
+    if verify:
+        assert co.gkr_verify(fid, oc, want, I)      # the reference verifier accepts the (identical) proof
+    return proof
+
+
+def test_gkr_reference_circuits_and_golden(zk, co, ctx_for, golden):
+    # gkr_protocol.rs:246-299, the reference's own two circuits
+    for e in golden["reference_kats"]["gkr_round_trips"]:
+        fid = FIELDS[e["field"]]
+        check_against_oracle(zk, co, ctx_for(fid), fid, e["layers"], e["inputs"])
+    # SURVEY appendix B vector
+    g = golden["appendix_b"]["gkr"]
+    fid = FIELDS[g["field"]]
+    proof = check_against_oracle(zk, co, ctx_for(fid), fid, g["layers"], g["inputs"])
+    assert zk.fe_to_ints(fid, proof.circuit_output) == g["output"]
+    assert [zk.fe_to_ints(fid, p.coefficients) for p in proof.sumcheck_proofs[0].round_univariate_polynomials] == g["layer0_coeffs"]
+    assert zk.fe_to_ints(fid, proof.wb_evaluations) == g["wb"] and zk.fe_to_ints(fid, proof.wc_evaluations) == g["wc"]
+    assert zk.fe_to_ints(fid, proof.claimed_sum) == [g["claimed_sum"]]
+    for e in golden["generated"]["gkr"]:
+        fid = FIELDS[e["field"]]
+        proof = check_against_oracle(zk, co, ctx_for(fid), fid, e["layers"], e["inputs"])
+        assert zk.fe_to_ints(fid, proof.claimed_sum) == [e["claimed_sum"]]
+        assert zk.fe_to_ints(fid, proof.wb_evaluations) == e["wb"]
+
+
+@pytest.mark.parametrize("fid", [0, 2])
+@pytest.mark.parametrize("depth", [1, 2, 4, 6])
+def test_gkr_random_reference_shaped_circuits(zk, co, ctx_for, fid, depth):
+    """layer i: 2^i outputs (2 at layer 0 for depth 1 variants), inputs of 2^(i+1) wires; several gates may feed one
+    output, one (b,c) pair may feed several outputs, both operators; edge inputs 0 / p-1."""
+    import pyoracle as po
+    p = po.P[{v: k for k, v in FIELDS.items()}[fid]]
+    rng = random.Random(100 * fid + depth)
+    layers = []
+    for i in range(depth):
+        n_out = 1 << i
+        gates, seen = [], set()
+        for o in range(n_out):
+            for _ in range(rng.choice([1, 1, 2, 3])):
+                g = (rng.randrange(1 << (i + 1)), rng.randrange(1 << (i + 1)), o, rng.randrange(2))
+                if g not in seen:
+                    seen.add(g)
+                    gates.append(g)
+        # make sure the widest wire index is used so the layer below has full width
+        layers.append(gates)
+    # every layer must produce exactly 2^i values: guaranteed since each output index 0..2^i-1 has a gate
+    inputs = [rng.randrange(p) for _ in range(1 << depth)]
+    inputs[0] = 0
+    inputs[-1] = p - 1
+    check_against_oracle(zk, co, ctx_for(fid), fid, layers, inputs)
+
+
+def test_gkr_two_outputs_and_duplicate_gates(zk, co, ctx_for):
+    # layer 0 with two outputs; a duplicated gate (the reference's dense indicator stores `= one`, the evaluation `+=`)
+    layers = [[(0, 1, 0, 1), (1, 0, 1, 0)], [(0, 1, 0, 0), (2, 3, 1, 1)]]
+    check_against_oracle(zk, co, ctx_for(0), 0, layers, [2, 3, 4, 5])
+    # with a duplicated gate the reference is unsound (its own verifier rejects its own proof); the prover output must
+    # still be the reference's, limb for limb
+    layers = [[(0, 1, 0, 1), (1, 0, 1, 0)], [(0, 1, 0, 0), (2, 3, 1, 1), (2, 3, 1, 1)]]
+    check_against_oracle(zk, co, ctx_for(0), 0, layers, [2, 3, 4, 5], verify=False)
+
+
+def test_circuit_kats_through_the_mirror_api(zk, co, ctx_for, golden):
+    from zk_cryptography_research_implementations_b200.circuit import num_of_layer_variables
+    k = golden["reference_kats"]
+    ctx = ctx_for(0)
+    for e in k["circuit_evaluate"]:
+        c = make_circuit(zk, 0, e["layers"])
+        res = c.evaluate(zk.fe_from_ints(0, e["inputs"]))
+        if "layer_evaluations" in e:
+            assert [zk.fe_to_ints(0, x) for x in res.layer_evaluations] == e["layer_evaluations"]
+        else:
+            assert zk.fe_to_ints(0, res.output) == e["output"]
+    for i, v in k["num_of_layer_variables"]["values"]:
+        assert num_of_layer_variables(i) == v
+    for e in k["add_i_mul_i"]:
+        c = make_circuit(zk, 0, e["layers"])
+        a, m = c.add_i_and_mul_i_mle(ctx, e["layer"])
+        av, mv = zk.fe_to_ints(0, a.evaluated_values), zk.fe_to_ints(0, m.evaluated_values)
+        assert len(av) == e["size"] and [i for i, v in enumerate(av) if v] == e["add_ones"] and [i for i, v in enumerate(mv) if v] == e["mul_ones"]
