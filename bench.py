@@ -40,6 +40,9 @@ WORKLOADS = {
     "product30": (0, "BN254_FQ", 1, 2, 30, "degree-2 product sumcheck f*g (BASELINE.json configs[2])"),
     "plain24": (2, "BLS12_381_FR", 1, 1, 24, "plain sumcheck of one MLE (BASELINE.json configs[1])"),
     "gkr22": (0, "BN254_FQ", 2, 2, 22, "GKR-shaped 2x2 sumcheck add*(Wb+Wc)+mul*(Wb*Wc) tables"),
+    # --log2 is the circuit depth L here: reference-shaped layered circuit, layer i has 2^i gates over 2^(i+1) wires,
+    # 2^L inputs; the layer-i sumcheck runs over 4^(i+1) entries x 4 tables
+    "gkr": (0, "BN254_FQ", 2, 2, 12, "GKR prove of a reference-shaped layered add/mul circuit (gkr_protocol::prove)"),
 }
 
 
@@ -74,6 +77,108 @@ def cpu_prove_once(field: int, P: int, D: int, log2: int):
     t0 = time.perf_counter()
     co.product_prove(field, tabs, claimed, co.Transcript())
     return time.perf_counter() - t0
+
+
+def synthetic_circuit(depth: int, seed: int = SEED):
+    """reference-shaped circuit: layer i has one gate per output index 0..2^i-1 reading two seeded wires of the
+    2^(i+1)-wide layer below, operator from the seed; duplicate-free by construction (distinct outputs)."""
+    rng = np.random.default_rng(seed)
+    layers = []
+    for i in range(depth):
+        n = 1 << i
+        left = rng.integers(0, 2 << i, size=n)
+        right = rng.integers(0, 2 << i, size=n)
+        op = rng.integers(0, 2, size=n)
+        layers.append([(int(left[o]), int(right[o]), o, int(op[o])) for o in range(n)])
+    return layers
+
+
+def gkr_inputs(field: int, depth: int):
+    rng = np.random.default_rng(SEED + 1)
+    tab = rng.integers(0, 1 << 62, size=(1 << depth, 4), dtype=np.uint64)
+    tab[:, 3] &= np.uint64((1 << 58) - 1)
+    return tab
+
+
+def cpu_gkr_once(field: int, depth: int):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import coracle as co
+    c = co.Circuit(synthetic_circuit(depth))
+    I = gkr_inputs(field, depth)
+    t0 = time.perf_counter()
+    co.gkr_prove(field, c, I)
+    return time.perf_counter() - t0
+
+
+def run_gkr(args, wl):
+    """GKR prove ms (BASELINE metric, second half).  Single GPU: the dense (b,c) formulation of the reference."""
+    field, fname, P, D, depth_default, desc = wl
+    depth = args.log2 or depth_default
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.impl == "reference":
+        d = min(depth, args.cpu_depth)
+        times = [cpu_gkr_once(field, d) for _ in range(max(args.steps, 1))]
+        t = statistics.mean(times)
+        line = {"impl": "reference", "metric": "gkr_prove_ms", "value": t * 1e3, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u256 (4x u64 Montgomery limbs)", "data": "synthetic",
+                "config": {"workload": "gkr: " + desc, "field": fname, "depth": d, "requested_depth": depth},
+                "cpu_baseline": {"value": t * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+                                 "sample": "depth-%d circuit (dense 2^(3i+2) wiring tables like the reference), oracle C restatement, 1 thread" % d},
+                "e2e": {"value": t * 1e3, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    import zk_cryptography_research_implementations_b200 as zk
+    from zk_cryptography_research_implementations_b200 import gkr
+    from zk_cryptography_research_implementations_b200.circuit import Circuit, Gate, Layer
+    torch.cuda.set_device(0)
+    ctx = zk.Context(field, 0, stream=torch.cuda.current_stream().cuda_stream)
+    layers = synthetic_circuit(depth)
+    circuit = Circuit.new(field, [Layer.new([Gate.new(*g) for g in l]) for l in layers])
+    I = gkr_inputs(field, depth)
+    for _ in range(args.warmup):
+        gkr.prove(ctx, circuit, I)
+    ctx.set_profiling(True)
+    ctx.reset_stats()
+    sampler = ClockSampler(0)
+    times = []
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        proof = gkr.prove(ctx, circuit, I)     # host inputs -> proof on the host: this IS the end-to-end call
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop()
+    st = ctx.stats()
+    ms = statistics.mean(times)
+    hbm_peak, peak_src = peaks()
+    achieved = st["round_bytes"] / (st["round_ms"] * 1e-3) / 1e9 if st["round_ms"] > 0 else 0.0
+    cpu = None
+    if not args.no_cpu:
+        d = min(depth, args.cpu_depth)
+        t = cpu_gkr_once(field, d)
+        cpu = {"value": t * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+               "sample": "depth-%d circuit (the GPU ran depth %d; the reference's dense 2^(3i+2) wiring tables make deeper ones "
+                         "infeasible on the CPU), oracle C restatement, 1 thread" % (d, depth)}
+    rounds = depth * (depth + 1)
+    line = {"metric": "gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
+            "config": {"workload": "gkr: " + desc, "field": fname, "depth": depth, "inputs": 1 << depth, "sumcheck_rounds": rounds,
+                       "largest_layer_entries": 4 ** depth, "tables_per_layer": 4, "l2": "largest layer 4 x %d MiB" % ((4 ** depth * 32) >> 20)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "fold_evals_kernel / round_evals_kernel <%s,P=2,D=2> (%d launches)" % (fname, st["round_launches"]),
+                         "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": int(I.nbytes), "d2h_bytes_per_step": int(rounds * 4 * 32),
+                    "note": "value already is the host-to-host zk_gkr_prove call (circuit + inputs on the host, proof on the host)"},
+            "gpu_launches": st["launches"], "clocks": clocks,
+            "proof_digest": int(np.bitwise_xor.reduce(np.stack([p.coefficients for sp in proof.sumcheck_proofs for p in sp.round_univariate_polynomials]).reshape(-1))) & 0xFFFFFFFF}
+    print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 def run_reference(args, wl):
@@ -340,13 +445,16 @@ def main():
     ap.add_argument("--log2", type=int, default=0, help="override log2(entries per table)")
     ap.add_argument("--collapse-len", type=int, default=1 << 12, dest="collapse_len")
     ap.add_argument("--cpu-log2", type=int, default=21, dest="cpu_log2", help="size of the CPU baseline sample")
+    ap.add_argument("--cpu-depth", type=int, default=7, dest="cpu_depth", help="circuit depth of the CPU GKR baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.workload == "gkr":
+        run_gkr(args, wl)
+    elif args.impl == "reference":
         run_reference(args, wl)
     else:
         run_ours(args, wl)

@@ -37,6 +37,8 @@ __device__ __forceinline__ void st256(Fe* p, const Fe& r) {
                  "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
                  : "memory");
 }
+// pull one 32-byte sector into L2 ahead of use (no register cost)
+__device__ __forceinline__ void prefetch_l2(const Fe* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // coherent (L2) read of data another block published
 __device__ __forceinline__ Fe ld256_cg(const Fe* p) {
     Fe r;
@@ -190,6 +192,13 @@ __global__ void __launch_bounds__(kThreads) round_evals_kernel(TablePtrs tp, uin
     ra.init();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
+        if (j + stride < half) {   // next iteration's sectors start their trip from HBM now
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                prefetch_l2(tp.t[t] + j + stride);
+                prefetch_l2(tp.t[t] + j + stride + half);
+            }
+        }
         Fe lo[T], hi[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -214,6 +223,13 @@ __global__ void __launch_bounds__(kThreads)
     ra.init();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < q; j += stride) {
+        if (j + stride < q) {   // next iteration's sectors start their trip from HBM now
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) prefetch_l2(tp.t[t] + j + stride + s * q);
+            }
+        }
         Fe lo[T], hi[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) {
