@@ -29,7 +29,9 @@ enum { ZK_OK = 0, ZK_ERR_ASSERT = -1, ZK_ERR_CUDA = -2, ZK_ERR_ARG = -3 };
 /* flags for the one-shot provers */
 enum {
     ZK_FLAG_DIRECT_S1 = 1,   /* compute s(1) in the kernel every round instead of claim - s(0) */
-    ZK_FLAG_SKIP_ABSORB = 2  /* zk_prove_basic*: the caller already absorbed the table bytes */
+    ZK_FLAG_SKIP_ABSORB = 2,   /* zk_prove_basic*: the caller already absorbed the table bytes */
+    ZK_FLAG_NCCL_EXCHANGE = 4  /* sharded provers: exchange the per-round partials with ncclAllGather even if the
+                                  shared mailboxes are attached (for comparison) */
 };
 
 typedef struct zk_ctx zk_ctx;
@@ -164,6 +166,11 @@ int  zk_gkr_prove(zk_ctx *, const zk_circuit_desc *, const uint64_t *inputs, uin
  * Rank 0 calls zk_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed, MPI, ...). */
 int  zk_comm_unique_id(uint8_t out[128]);
 int  zk_comm_init(zk_ctx *, int rank, int world, const uint8_t id[128]);   /* world: power of two */
+/* optional, same node only: round mailboxes in a POSIX shared-memory segment (Mailbox[2][world]); every rank's round
+ * kernel then publishes its partial evaluations straight into host memory all rank processes poll -- no collective
+ * on the per-round path.  Rank 0: create = 1 before the others attach; unlink after all have attached. */
+int  zk_comm_attach_mailboxes(zk_ctx *, const char *shm_name, int create);
+int  zk_comm_unlink_mailboxes(const char *shm_name);
 int  zk_comm_destroy(zk_ctx *);
 int  zk_comm_rank(const zk_ctx *);
 int  zk_comm_world(const zk_ctx *);

@@ -16,7 +16,7 @@ u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
 ZK_OK, ZK_ERR_ASSERT, ZK_ERR_CUDA, ZK_ERR_ARG = 0, -1, -2, -3
-FLAG_DIRECT_S1, FLAG_SKIP_ABSORB = 1, 2
+FLAG_DIRECT_S1, FLAG_SKIP_ABSORB, FLAG_NCCL_EXCHANGE = 1, 2, 4
 
 # name -> (restype, argtypes); every symbol include/zk_sumcheck.h declares
 SIGNATURES = {
@@ -79,6 +79,8 @@ SIGNATURES = {
     "zk_gkr_prove": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p]),
     "zk_comm_unique_id": (C.c_int, [C.c_char_p]),
     "zk_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
+    "zk_comm_attach_mailboxes": (C.c_int, [vp, C.c_char_p, C.c_int]),
+    "zk_comm_unlink_mailboxes": (C.c_int, [C.c_char_p]),
     "zk_comm_destroy": (C.c_int, [vp]),
     "zk_comm_rank": (C.c_int, [vp]),
     "zk_comm_world": (C.c_int, [vp]),

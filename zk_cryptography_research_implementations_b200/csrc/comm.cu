@@ -11,7 +11,11 @@
 // NCCL is resolved with dlopen (the copy torch already loaded), so the library still loads on a
 // CPU-only box; nothing here runs without a GPU.
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -118,6 +122,11 @@ extern "C" int zk_comm_destroy(zk_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
+    if (ctx->xmail_host) {
+        cudaHostUnregister(ctx->xmail_host);
+        munmap(ctx->xmail_host, ctx->xmail_bytes);
+        ctx->xmail_host = ctx->xmail_dev = nullptr;
+    }
     cudaFree(ctx->xchg_send);
     cudaFree(ctx->xchg_recv);
     cudaFreeHost(ctx->xchg_host);
@@ -130,23 +139,61 @@ extern "C" int zk_comm_destroy(zk_ctx* ctx) {
 extern "C" int zk_comm_rank(const zk_ctx* ctx) { return ctx->rank; }
 extern "C" int zk_comm_world(const zk_ctx* ctx) { return ctx->world; }
 
-// all ranks: sum over ranks of the `ne` elements the last round kernel published (field addition is
-// not an NCCL reduction, so: all-gather the raw elements, add mod p on the host)
+// Attach the shared round mailboxes: a POSIX shared-memory segment holding Mailbox[2][world], mapped by every
+// rank process and registered with CUDA so each rank's round kernel can publish straight into it.  Rank 0
+// passes create = 1 (and may shm_unlink the name once every rank has attached).
+extern "C" int zk_comm_attach_mailboxes(zk_ctx* ctx, const char* shm_name, int create) {
+    if (ctx->world < 2) return fail(ctx, ZK_ERR_ARG, "zk_comm_init first");
+    if (ctx->xmail_host) return fail(ctx, ZK_ERR_ARG, "mailboxes already attached");
+    size_t bytes = sizeof(Mailbox) * 2 * (size_t)ctx->world;
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    int fd = shm_open(shm_name, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return fail(ctx, ZK_ERR_ARG, "shm_open failed");
+    if (create && ftruncate(fd, (off_t)bytes) != 0) { close(fd); return fail(ctx, ZK_ERR_ARG, "ftruncate failed"); }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(ctx, ZK_ERR_ARG, "mmap failed");
+    if (create) memset(p, 0, bytes);
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess) { munmap(p, bytes); ctx->err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return ZK_ERR_CUDA; }
+    ctx->xmail_host = (Mailbox*)p;
+    ctx->xmail_bytes = bytes;
+    ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->xmail_dev, p, 0));
+    ctx->xmail_seq = 0;
+    return ZK_OK;
+}
+extern "C" int zk_comm_unlink_mailboxes(const char* shm_name) { return shm_unlink(shm_name) == 0 ? ZK_OK : ZK_ERR_ARG; }
+
+// All ranks: sum over ranks of the `ne` elements the last round kernel published.  Field addition is not an
+// NCCL reduction op, so the raw elements are exchanged and added mod p on the host by every rank.
+//  * shared mailboxes attached (default): every rank's kernel wrote into its slot of the shared segment; spin
+//    until all G slots carry this round's sequence number -- no collective, no copy, no stream sync;
+//  * otherwise: ncclAllGather of the (d+1) x 32 bytes over NVLink + D2H.
 static int exchange_sum(zk_ctx* ctx, HFe* vals, int ne) {
     const HostField& f = ctx->field;
     const int G = ctx->world;
     const size_t bytes = (size_t)ne * sizeof(Fe);
-    // the kernel published into mapped host memory; stage a device copy for NCCL on the same stream
-    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_send, ctx->result_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    for (int e = 0; e < ne; ++e) vals[e] = f.zero();
+    if (ctx->exchange_pending) {
+        const unsigned seq = ctx->xmail_seq;
+        const Mailbox* row = ctx->xmail_host + (size_t)(seq & 1u) * G;
+        for (int q = 0; q < G; ++q) {
+            int rc = wait_mailbox(ctx, row + q, seq, q == ctx->rank);
+            if (rc) return rc;
+            const HFe* v = reinterpret_cast<const HFe*>(const_cast<const Fe*>(row[q].vals));
+            for (int e = 0; e < ne; ++e) vals[e] = f.add(vals[e], v[e]);
+        }
+        return ZK_OK;
+    }
+    // the kernel published into this context's own mailbox; stage a device copy for NCCL on the same stream
+    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_send, ctx->mail_dev->vals, bytes, cudaMemcpyDefault, ctx->stream));
     ZK_NCCL(g_nccl.AllGather(ctx->xchg_send, ctx->xchg_recv, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     ZK_CUDA(cudaMemcpyAsync(ctx->xchg_host, ctx->xchg_recv, bytes * G, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     const HFe* all = reinterpret_cast<const HFe*>(ctx->xchg_host);
-    for (int e = 0; e < ne; ++e) {
-        HFe acc = f.zero();
-        for (int q = 0; q < G; ++q) acc = f.add(acc, all[(size_t)q * ne + e]);
-        vals[e] = acc;
-    }
+    for (int e = 0; e < ne; ++e)
+        for (int q = 0; q < G; ++q) vals[e] = f.add(vals[e], all[(size_t)q * ne + e]);
     return ZK_OK;
 }
 
@@ -215,10 +262,11 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
             sharded = false;
         }
         TablePtrs tp = ptrs_of(sp);
+        const bool shared = sharded && ctx->xmail_host != nullptr && !(flags & ZK_FLAG_NCCL_EXCHANGE);
         if (need_plain_evals) {
-            rc = launch_round_evals(ctx, tp, P, D, sp->len);
+            rc = launch_round_evals(ctx, tp, P, D, sp->len, shared);
         } else {
-            rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1);
+            rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1, shared);
             set_len(sp, sp->len / 2);
         }
         if (rc) return rc;

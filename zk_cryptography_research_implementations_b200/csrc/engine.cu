@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <string>
@@ -16,6 +18,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "round_launch.cuh"
+#include "internal.h"
 
 using namespace zk;
 
@@ -131,8 +134,9 @@ static int ctx_create(zk_ctx** out, int fid, int device, void* stream, bool own_
     ZK_CUDA(cudaMalloc(&ctx->partials, (size_t)ctx->max_grid * kMaxEvals * sizeof(Fe)));
     ZK_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
     ZK_CUDA(cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream));
-    ZK_CUDA(cudaHostAlloc(&ctx->result_host, kMaxEvals * sizeof(Fe), cudaHostAllocMapped));
-    ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->result_dev, ctx->result_host, 0));
+    ZK_CUDA(cudaHostAlloc(&ctx->mail_host, sizeof(Mailbox), cudaHostAllocMapped));
+    memset(ctx->mail_host, 0, sizeof(Mailbox));
+    ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->mail_dev, ctx->mail_host, 0));
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = c.release();
     return ZK_OK;
@@ -153,7 +157,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
-    cudaFreeHost(ctx->result_host);
+    cudaFreeHost(ctx->mail_host);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -337,25 +341,49 @@ extern "C" void zk_table_free(zk_ctx* ctx, zk_table* t) {
 // =================================================================================== kernel launchers
 namespace zk {
 
-// wait for the round kernel and copy its NE published elements out of the mapped result buffer
-int fetch_result(zk_ctx* ctx, HFe* out, int ne) {
-    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(out, ctx->result_host, (size_t)ne * sizeof(Fe));
+int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own) {
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t spins = 0;; ++spins) {
+        if (box->seq == seq) break;
+        if ((spins & 0x3ff) == 0x3ff) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) {
+                ctx->err = std::string("round kernel failed: ") + cudaGetErrorString(q);
+                return ZK_ERR_CUDA;
+            }
+            if (q == cudaSuccess && own && box->seq != seq) {
+                // the stream drained: the write must have landed; re-read once before giving up
+                if (box->seq == seq) break;
+                return fail(ctx, ZK_ERR_CUDA, "round kernel finished without publishing its result");
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+                return fail(ctx, ZK_ERR_CUDA, "timed out waiting for a round result (peer rank lost?)");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     return ZK_OK;
 }
 
-int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len) {
+// wait for the round kernel (spin on the mailbox sequence number) and copy its NE published elements out
+int fetch_result(zk_ctx* ctx, HFe* out, int ne) {
+    int rc = wait_mailbox(ctx, ctx->mail_host, ctx->mail_seq, true);
+    if (rc) return rc;
+    memcpy(out, const_cast<const Fe*>(ctx->mail_host->vals), (size_t)ne * sizeof(Fe));
+    return ZK_OK;
+}
+
+int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared) {
     prof_begin(ctx);
     int rc;
-    ZK_DISPATCH_FID(ctx, rc = launch_round_evals_pd<FID>(ctx, tp, P, D, len / 2));
+    ZK_DISPATCH_FID(ctx, rc = launch_round_evals_pd<FID>(ctx, tp, P, D, len / 2, shared));
     prof_end(ctx, 32.0 * P * D * (double)len);
     return rc;
 }
 // old length `len` (>= 4): folds to len/2 and evaluates the next round
-int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1) {
+int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1, bool shared) {
     prof_begin(ctx);
     int rc;
-    ZK_DISPATCH_FID(ctx, rc = launch_fold_evals_pd<FID>(ctx, tp, P, D, len / 4, ft, skip1));
+    ZK_DISPATCH_FID(ctx, rc = launch_fold_evals_pd<FID>(ctx, tp, P, D, len / 4, ft, skip1, shared));
     prof_end(ctx, 32.0 * P * D * 1.5 * (double)len);
     return rc;
 }

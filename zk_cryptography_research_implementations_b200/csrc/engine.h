@@ -6,7 +6,7 @@
 #include <vector>
 #include "host_field.h"
 
-namespace zk { struct Fe; }
+namespace zk { struct Fe; struct Mailbox; }
 
 struct zk_ctx {
     explicit zk_ctx(int field_id) : fid(field_id), field(field_id) {}
@@ -22,8 +22,15 @@ struct zk_ctx {
     // grid-wide reduction scratch + the published round evaluations (mapped pinned host memory)
     zk::Fe* partials = nullptr;
     unsigned* ticket = nullptr;
-    zk::Fe* result_host = nullptr;
-    zk::Fe* result_dev = nullptr;
+    zk::Mailbox* mail_host = nullptr;   // this context's own mailbox (unsharded operations)
+    zk::Mailbox* mail_dev = nullptr;
+    unsigned mail_seq = 0;
+    // sharded runs: mailboxes [2][world] in a POSIX shared-memory segment mapped by every rank process
+    zk::Mailbox* xmail_host = nullptr;
+    zk::Mailbox* xmail_dev = nullptr;
+    size_t xmail_bytes = 0;
+    unsigned xmail_seq = 0;
+    bool exchange_pending = false;      // the last round kernel published into the shared mailbox
     // general scratch (evaluate / convert_to_bytes / out-of-place folds)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

@@ -14,7 +14,9 @@ int table_alloc(zk_ctx* ctx, uint64_t n, zk_table** out);
 int ensure_scratch(zk_ctx* ctx, size_t bytes);
 namespace zk {
 int fetch_result(zk_ctx* ctx, HFe* out, int ne);
-int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len);
-int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1);
+int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared = false);
+int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1, bool shared = false);
+// spin until `box` carries sequence number `seq` (watchdog: stream errors, 120 s wall clock)
+int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own);
 int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, const FoldTable& ft);
 }

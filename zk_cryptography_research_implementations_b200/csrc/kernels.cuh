@@ -50,10 +50,20 @@ __device__ __forceinline__ Fe ld256_cg(const Fe* p) {
 }
 
 // ---------------------------------------------------------------- grid-wide reduction of NE field elements
+// The published result of a round kernel: the d+1 field elements plus a sequence number written LAST
+// (after a system-scope fence).  The mailbox lives in mapped pinned host memory -- for sharded runs in a
+// segment shared by all rank processes -- so the host sees the round's result a PCIe write after the
+// last block finishes, without a stream synchronisation or a D2H copy.
+struct Mailbox {
+    Fe vals[kMaxEvals];
+    unsigned seq;
+    unsigned pad[7];
+};
 struct ReduceScratch {
     Fe* partials;        // [gridDim.x][NE]
     unsigned* ticket;    // zero before the launch; reset by the last block
-    Fe* out;             // [NE]; device memory or mapped pinned host memory
+    Mailbox* out;        // mapped pinned host memory (device address)
+    unsigned seq;        // value to publish in out->seq
 };
 
 template <int FID> __device__ __forceinline__ Fe warp_sum(Fe v) {
@@ -120,9 +130,10 @@ template <int FID, int NE> __device__ __forceinline__ void grid_sum_publish(Fe (
     block_sum<FID, NE>(vals);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int e = 0; e < NE; ++e) rs.out[e] = vals[e];
+        for (int e = 0; e < NE; ++e) rs.out->vals[e] = vals[e];
         *rs.ticket = 0;
         __threadfence_system();
+        *reinterpret_cast<volatile unsigned*>(&rs.out->seq) = rs.seq;
     }
 }
 

@@ -24,7 +24,18 @@ inline int launch_check(zk_ctx* ctx) {
     }
     return ZK_OK;
 }
-inline ReduceScratch reduce_scratch(zk_ctx* ctx) { return ReduceScratch{ctx->partials, ctx->ticket, ctx->result_dev}; }
+// where the next round kernel publishes: the shared mailbox slot of this rank (sharded round, double-buffered by
+// sequence parity) or the context's own mailbox
+inline ReduceScratch reduce_scratch(zk_ctx* ctx, bool shared) {
+    if (shared) {
+        unsigned seq = ++ctx->xmail_seq;
+        ctx->exchange_pending = true;
+        return ReduceScratch{ctx->partials, ctx->ticket, ctx->xmail_dev + (size_t)(seq & 1u) * ctx->world + ctx->rank, seq};
+    }
+    unsigned seq = ++ctx->mail_seq;
+    ctx->exchange_pending = false;
+    return ReduceScratch{ctx->partials, ctx->ticket, ctx->mail_dev, seq};
+}
 inline int unsupported_pd(zk_ctx* ctx) {
     ctx->err = "unsupported (P, D): supported are (1,1) (1,2) (2,2) (3,2) (4,2) (1,3) (2,3)";
     return ZK_ERR_ARG;
@@ -34,12 +45,12 @@ inline int round_blocks_per_sm(int P, int D) { return (P * D >= 4) ? 1 : 2; }
 
 #define ZK_PD_CASES ZK_CASE(1, 1) ZK_CASE(1, 2) ZK_CASE(2, 2) ZK_CASE(1, 3) ZK_CASE(2, 3) ZK_CASE(3, 2) ZK_CASE(4, 2)
 
-template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t half);
-template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t q, const FoldTable& ft, bool skip1);
+template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t half, bool shared);
+template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t q, const FoldTable& ft, bool skip1, bool shared);
 
 #ifdef ZK_INSTANTIATE_ROUND_EVALS
-template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t half) {
-    ReduceScratch rs = reduce_scratch(ctx);
+template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t half, bool shared) {
+    ReduceScratch rs = reduce_scratch(ctx, shared);
     int grid = launch_grid(ctx, half, round_blocks_per_sm(P, D));
 #define ZK_CASE(PP, DD)                                                                    \
     if (P == PP && D == DD) {                                                              \
@@ -50,12 +61,12 @@ template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, i
 #undef ZK_CASE
     return unsupported_pd(ctx);
 }
-template int launch_round_evals_pd<ZK_INSTANTIATE_ROUND_EVALS>(zk_ctx*, const TablePtrs&, int, int, uint64_t);
+template int launch_round_evals_pd<ZK_INSTANTIATE_ROUND_EVALS>(zk_ctx*, const TablePtrs&, int, int, uint64_t, bool);
 #endif
 
 #ifdef ZK_INSTANTIATE_FOLD_EVALS
-template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t q, const FoldTable& ft, bool skip1) {
-    ReduceScratch rs = reduce_scratch(ctx);
+template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t q, const FoldTable& ft, bool skip1, bool shared) {
+    ReduceScratch rs = reduce_scratch(ctx, shared);
     int grid = launch_grid(ctx, q, round_blocks_per_sm(P, D));
 #define ZK_CASE(PP, DD)                                                                                     \
     if (P == PP && D == DD) {                                                                               \
@@ -67,7 +78,7 @@ template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, in
 #undef ZK_CASE
     return unsupported_pd(ctx);
 }
-template int launch_fold_evals_pd<ZK_INSTANTIATE_FOLD_EVALS>(zk_ctx*, const TablePtrs&, int, int, uint64_t, const FoldTable&, bool);
+template int launch_fold_evals_pd<ZK_INSTANTIATE_FOLD_EVALS>(zk_ctx*, const TablePtrs&, int, int, uint64_t, const FoldTable&, bool, bool);
 #endif
 
 }  // namespace zk

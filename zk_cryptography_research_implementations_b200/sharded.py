@@ -13,6 +13,7 @@ Two drivers over the same layout:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -39,7 +40,7 @@ def interleave(shards: Sequence[np.ndarray]) -> np.ndarray:
 
 
 # ------------------------------------------------------------------ communicator bootstrap
-def init_comm(ctx: Context, group=None) -> None:
+def init_comm(ctx: Context, group=None, shared_mailboxes: bool = True) -> None:
     """create the library's NCCL communicator for this process group (id broadcast through torch)"""
     import torch
     import torch.distributed as dist
@@ -53,6 +54,18 @@ def init_comm(ctx: Context, group=None) -> None:
     dist.broadcast(t, 0, group=group)
     ident = bytes(t.cpu().tolist())
     ctx.check(ctx.lib.zk_comm_init(ctx.h, rank, world, ident))
+    if world > 1 and shared_mailboxes:
+        # per-round exchange through a shared-memory segment all rank processes (one node) map
+        name = [("/zkb200_%d_%s" % (os.getpid(), os.urandom(4).hex())) if rank == 0 else None]
+        dist.broadcast_object_list(name, 0, group=group)
+        if rank == 0:
+            ctx.check(ctx.lib.zk_comm_attach_mailboxes(ctx.h, name[0].encode(), 1))
+        dist.barrier(group=group)
+        if rank != 0:
+            ctx.check(ctx.lib.zk_comm_attach_mailboxes(ctx.h, name[0].encode(), 0))
+        dist.barrier(group=group)
+        if rank == 0:
+            ctx.lib.zk_comm_unlink_mailboxes(name[0].encode())
 
 
 def prove_product_native(ctx: Context, sp_handle, P: int, D: int, n_global: int, claimed_sum, transcript: Transcript,
