@@ -40,6 +40,7 @@ WORKLOADS = {
     "product30": (0, "BN254_FQ", 1, 2, 30, "degree-2 product sumcheck f*g (BASELINE.json configs[2])"),
     "plain24": (2, "BLS12_381_FR", 1, 1, 24, "plain sumcheck of one MLE (BASELINE.json configs[1])"),
     "gkr22": (0, "BN254_FQ", 2, 2, 22, "GKR-shaped 2x2 sumcheck add*(Wb+Wc)+mul*(Wb*Wc) tables"),
+    "mle": (0, "BN254_FQ", 1, 1, 28, "MultilinearPolynomial::evaluate / partial_evaluate sweep point (BASELINE.json configs[4])"),
     # --log2 is the circuit depth L here: reference-shaped layered circuit, layer i has 2^i gates over 2^(i+1) wires,
     # 2^L inputs; the layer-i sumcheck runs over 4^(i+1) entries x 4 tables
     "gkr": (0, "BN254_FQ", 2, 2, 12, "GKR prove of a reference-shaped layered add/mul circuit (gkr_protocol::prove)"),
@@ -179,6 +180,125 @@ def run_gkr(args, wl):
             "proof_digest": int(np.bitwise_xor.reduce(np.stack([p.coefficients for sp in proof.sumcheck_proofs for p in sp.round_univariate_polynomials]).reshape(-1))) & 0xFFFFFFFF}
     print(json.dumps(line), flush=True)
     ctx.close()
+
+
+def run_mle(args, wl):
+    """configs[4]: MLE evaluate (all n challenges, one read of the table per 3 variables) and one partial_evaluate,
+    against the HBM roofline.  N > 1: table sharded on the low index bits, zk_mle_evaluate_sharded."""
+    field, fname, P, D, log2_default, desc = wl
+    log2 = args.log2 or log2_default
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import coracle as co
+        sl = min(log2, args.cpu_log2)
+        rng = np.random.default_rng(SEED)
+        tab = rng.integers(0, 1 << 62, size=(1 << sl, 4), dtype=np.uint64)
+        tab[:, 3] &= np.uint64((1 << 58) - 1)
+        rs = tab[:sl].copy()
+        times = []
+        for _ in range(max(args.steps, 1)):
+            t0 = time.perf_counter()
+            co.mle_evaluate(field, tab, rs)
+            times.append(time.perf_counter() - t0)
+        t = statistics.mean(times)
+        v = (1 << sl) / t
+        print(json.dumps({"impl": "reference", "metric": "mle_evaluate_field_elements_per_s", "value": v, "unit": "elements/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery limbs)", "data": "synthetic",
+                          "config": {"workload": "mle: " + desc, "field": fname, "log2_entries": log2},
+                          "cpu_baseline": {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
+                                           "sample": "evaluate of a 2^%d-entry sample, oracle C restatement (n folds with fresh vectors), 1 thread" % sl},
+                          "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    import zk_cryptography_research_implementations_b200 as zk
+    from zk_cryptography_research_implementations_b200 import sharded
+    from zk_cryptography_research_implementations_b200.core import _ptr
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = zk.Context(field, local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        sharded.init_comm(ctx)
+    lib = ctx.lib
+    N = 1 << log2
+    m = N // world
+    table = ctx.generate(SEED, 0, m, first=rank, step=world)
+    rs = np.ascontiguousarray(ctx.generate(SEED, 99, max(log2, 1)).download()[:log2])
+    out = np.zeros(4, dtype=np.uint64)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def ev():
+        ctx.check(lib.zk_mle_evaluate_sharded(ctx.h, table.h, _ptr(rs), log2, _ptr(out)))
+
+    def timed(fn, prep):
+        for _ in range(args.warmup):
+            prep(); barrier(); fn(); barrier()
+        ctx.reset_stats()
+        ts = []
+        for _ in range(args.steps):
+            prep(); barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); barrier()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([statistics.mean(ts)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_eval = timed(ev, lambda: None)
+    launches = ctx.stats()["launches"]
+    # one partial_evaluate of variable 0 (in place: read N, write N/2), table refilled between steps
+    r0 = np.ascontiguousarray(rs[0])
+    ms_fold = timed(lambda: ctx.check(lib.zk_mle_partial_evaluate(ctx.h, table.h, 0, _ptr(r0))),
+                    lambda: table.regenerate(SEED, 0, m, rank, world))
+    clocks = sampler.stop() if sampler else None
+    hbm_peak, peak_src = peaks()
+    if rank == 0:
+        ach_eval = 32.0 * m / (ms_eval * 1e-3) / 1e9          # algorithmic: ONE read of the table
+        ach_fold = 48.0 * m / (ms_fold * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import coracle as co
+            sl = min(log2, args.cpu_log2)
+            rng = np.random.default_rng(SEED)
+            tab = rng.integers(0, 1 << 62, size=(1 << sl, 4), dtype=np.uint64)
+            tab[:, 3] &= np.uint64((1 << 58) - 1)
+            t0 = time.perf_counter()
+            co.mle_evaluate(field, tab, tab[:sl].copy())
+            t = time.perf_counter() - t0
+            cpu = {"value": (1 << sl) / t, "unit": "elements/s", "cores": 1, "kind": "port",
+                   "sample": "evaluate of a 2^%d-entry sample (%.2f s), oracle C restatement, 1 thread" % (sl, t)}
+        print(json.dumps({
+            "metric": "mle_evaluate_field_elements_per_s", "value": N / (ms_eval * 1e-3), "unit": "elements/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_eval, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
+            "config": {"workload": "mle: " + desc, "field": fname, "log2_entries": log2, "table_bytes_total": N * 32,
+                       "sharding": "low index bits across %d rank(s)" % world, "l2": "table larger than L2" if m * 32 > 126e6 else "table fits L2"},
+            "roofline": {"bound": "hbm", "achieved": ach_eval, "peak": hbm_peak, "unit": "GB/s", "frac": ach_eval / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "fold_multi_kernel<%s,3> passes (algorithmic bytes = 32 N: one read)" % fname,
+                         "note": "timed around the whole evaluate call (n/3 passes + host fold tables)"},
+            "partial_evaluate": {"ms": ms_fold, "elements_per_s": N / (ms_fold * 1e-3), "achieved_GBps": ach_fold, "frac": ach_fold / hbm_peak,
+                                 "kernel": "fold0_kernel (read N, write N/2: 48 N bytes)"},
+            "cpu_baseline": cpu, "e2e": None, "gpu_launches": launches, "clocks": clocks,
+            "result_digest": int(np.bitwise_xor.reduce(out)) & 0xFFFFFFFF}), flush=True)
+    barrier()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_reference(args, wl):
@@ -454,6 +574,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.workload == "gkr":
         run_gkr(args, wl)
+    elif args.workload == "mle":
+        run_mle(args, wl)
     elif args.impl == "reference":
         run_reference(args, wl)
     else:

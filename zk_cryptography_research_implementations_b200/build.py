@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
+# kernel-variant experiments: ZKB200_DEFINES="-DZK_PIPE_VARIANT=1" python -m ...build --force
+NVCC_FLAGS += os.environ.get("ZKB200_DEFINES", "").split()
 
 
 def sources():
