@@ -30,6 +30,8 @@ enum { ZK_OK = 0, ZK_ERR_ASSERT = -1, ZK_ERR_CUDA = -2, ZK_ERR_ARG = -3 };
 enum {
     ZK_FLAG_DIRECT_S1 = 1,   /* compute s(1) in the kernel every round instead of claim - s(0) */
     ZK_FLAG_SKIP_ABSORB = 2,   /* zk_prove_basic*: the caller already absorbed the table bytes */
+    ZK_FLAG_NO_CLAIM_ABSORB = 8, /* zk_prove_product: do not absorb claimed_sum first (continuation of a sumcheck whose
+                                  earlier rounds ran in a previous call -- the two phases of a sparse GKR layer) */
     ZK_FLAG_NCCL_EXCHANGE = 4  /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
 };
@@ -38,6 +40,7 @@ typedef struct zk_ctx zk_ctx;
 typedef struct zk_table zk_table;
 typedef struct zk_sumpoly zk_sumpoly;
 typedef struct zk_transcript zk_transcript;
+typedef struct zk_wide_circuit zk_wide_circuit;
 
 /* ---- library / context ---- */
 const char *zk_version(void);
@@ -160,6 +163,22 @@ uint64_t zk_gkr_total_rounds(uint32_t n_layers);   /* sum over layers of 2(i+1) 
 int  zk_gkr_prove(zk_ctx *, const zk_circuit_desc *, const uint64_t *inputs, uint64_t n_inputs,
                   uint64_t *output, uint64_t output_cap, uint64_t *n_output, uint64_t claimed_sum[4],
                   uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges, uint64_t *wb, uint64_t *wc);
+
+/* ---- GKR for wide layers: sparse two-phase layer sumcheck over 2^m-entry tables (m = log2 width of the layer below)
+ * instead of the reference's dense 2^(3i+2) / 4^(i+1) tables; identical round polynomials on reference-shaped
+ * circuits.  layer_bits[li] = log2(#values of layer li), li = 0..n_layers (last = inputs); gates as in
+ * zk_circuit_desc, duplicate-free.  The circuit (three CSR orderings per layer) lives on the GPU. */
+int  zk_wide_circuit_create(zk_ctx *, uint32_t n_layers, const uint32_t *layer_bits, const uint64_t *layer_off,
+                            const uint32_t *left, const uint32_t *right, const uint32_t *out, const uint8_t *op,
+                            zk_wide_circuit **result);
+void zk_wide_circuit_free(zk_ctx *, zk_wide_circuit *);
+uint64_t zk_wide_circuit_total_rounds(const zk_wide_circuit *);   /* sum over layers of 2 * layer_bits[li+1] */
+/* gkr_protocol::prove (gkr_protocol.rs:26-143).  output (may be NULL): 2^layer_bits[0] elements; the rest as
+ * zk_gkr_prove.  The output claim binds layer_bits[0] successive challenges (one in the reference's shape).
+ * ZK_FLAG_SKIP_ABSORB: do not absorb the output layer into the transcript. */
+int  zk_gkr_prove_wide(zk_ctx *, const zk_wide_circuit *, const uint64_t *inputs, uint64_t n_inputs, uint64_t *output,
+                       uint64_t *claimed_sum, uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges,
+                       uint64_t *wb, uint64_t *wc, uint32_t flags);
 
 /* ---- one process per GPU: tables sharded on the LOW index bits (rank q holds entries q, q+G, q+2G, ...) ----
  * NCCL over NVLink/NVSwitch carries one all-gather of (D+1) elements per round; folds stay local.

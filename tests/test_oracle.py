@@ -197,3 +197,19 @@ def test_random_cross_check_python_vs_c(co):
         # a wrong claimed sum is caught by the verifier in round 0
         ok, _, _ = co.product_verify(fid, co.from_ints(fid, [(claimed + 1) % p])[0], coeffs, co.Transcript())
         assert not ok
+
+
+def test_generalised_python_gkr_model_reduces_to_the_reference_shape():
+    """pyoracle.gkr_prove_general (extension oracle for wide layers) == pyoracle.gkr_prove on reference shapes"""
+    rng = random.Random(11)
+    p = po.P["BN254_FQ"]
+    for depth in (1, 2, 3, 4):
+        layers = []
+        for i in range(depth):
+            layers.append([po.Gate(rng.randrange(2 << i), rng.randrange(2 << i), o, rng.randrange(2)) for o in range(1 << i)])
+        inputs = [rng.randrange(p) for _ in range(1 << depth)]
+        a = po.gkr_prove(layers, inputs, p)
+        b = po.gkr_prove_general(layers, [1] + list(range(1, depth + 1)), inputs, p)
+        assert a.sumcheck_proofs == b.sumcheck_proofs and a.claimed_sum == b.claimed_sum
+        assert a.wb_evaluations == b.wb_evaluations and a.wc_evaluations == b.wc_evaluations
+        assert po.gkr_verify(layers, a, inputs, p)

@@ -16,7 +16,7 @@ u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
 ZK_OK, ZK_ERR_ASSERT, ZK_ERR_CUDA, ZK_ERR_ARG = 0, -1, -2, -3
-FLAG_DIRECT_S1, FLAG_SKIP_ABSORB, FLAG_NCCL_EXCHANGE = 1, 2, 4
+FLAG_DIRECT_S1, FLAG_SKIP_ABSORB, FLAG_NCCL_EXCHANGE, FLAG_NO_CLAIM_ABSORB = 1, 2, 4, 8
 
 # name -> (restype, argtypes); every symbol include/zk_sumcheck.h declares
 SIGNATURES = {
@@ -77,6 +77,11 @@ SIGNATURES = {
     "zk_circuit_evaluate": (C.c_int, [C.c_int, vp, u64p, C.c_uint64, u64p, u64p, C.c_uint64]),
     "zk_gkr_total_rounds": (C.c_uint64, [C.c_uint32]),
     "zk_gkr_prove": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p]),
+    "zk_wide_circuit_create": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32), u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_uint32), u8p, C.POINTER(vp)]),
+    "zk_wide_circuit_free": (None, [vp, vp]),
+    "zk_wide_circuit_total_rounds": (C.c_uint64, [vp]),
+    "zk_gkr_prove_wide": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint32]),
     "zk_comm_unique_id": (C.c_int, [C.c_char_p]),
     "zk_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
     "zk_comm_attach_mailboxes": (C.c_int, [vp, C.c_char_p, C.c_int]),

@@ -611,7 +611,7 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
     const Interpolator& ip = interp_for(ctx, D);
     HFe claim;
     memcpy(claim.l, claimed_sum, 32);
-    tr->t.append_be(f, claim);                                                   // :35
+    if (!(flags & ZK_FLAG_NO_CLAIM_ABSORB)) tr->t.append_be(f, claim);           // :35
     TablePtrs tp = ptrs_of(sp);
     HFe evals[kMaxEvals], coeffs[kMaxEvals], r = f.zero();
     HFe running = claim;  // s_{k-1}(r_{k-1}); only trusted from round 1 on

@@ -46,3 +46,76 @@ def prove(ctx: Context, circuit: Circuit, inputs) -> Proof:      # gkr_protocol.
         proofs.append(SumcheckProverProof(claims[i].copy(), polys, chal[o:o + r].copy()))
         o += r
     return Proof(output[: n_out.value].copy(), claimed, proofs, wb[: L - 1].copy(), wc[: L - 1].copy())
+
+
+class WideCircuit:
+    """A layered circuit with explicit layer widths, resident on the GPU (three CSR orderings of every layer's
+    gates) for the sparse two-phase layer prover (csrc/gkr_wide.cu).  layer_bits[li] = log2(#values of layer li),
+    li = 0..L (last entry = inputs).  `layers` as for `Circuit`: lists of (left, right, out, op)."""
+
+    def __init__(self, ctx: Context, layer_bits, layers):
+        self.ctx = ctx
+        self.layer_bits = [int(b) for b in layer_bits]
+        self.n_layers = len(layers)
+        assert len(self.layer_bits) == self.n_layers + 1
+        off = [0]
+        for l in layers:
+            off.append(off[-1] + len(l))
+        def col(k, dt):
+            if isinstance(layers[0], np.ndarray):
+                return np.ascontiguousarray(np.concatenate([l[:, k] for l in layers]).astype(dt))
+            return np.array([g[k] for l in layers for g in l], dtype=dt)
+        self._off = np.array(off, dtype=np.uint64)
+        left, right, out, op = col(0, np.uint32), col(1, np.uint32), col(2, np.uint32), col(3, np.uint8)
+        bits = np.array(self.layer_bits, dtype=np.uint32)
+        h = C.c_void_p()
+        u32p = C.POINTER(C.c_uint32)
+        ctx.check(ctx.lib.zk_wide_circuit_create(ctx.h, self.n_layers, bits.ctypes.data_as(u32p), _ptr(self._off),
+                                                 left.ctypes.data_as(u32p), right.ctypes.data_as(u32p), out.ctypes.data_as(u32p),
+                                                 op.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def reference_shaped(cls, ctx: Context, layers):
+        """the reference's rigid shape: layer 0 has one output bit, layer i >= 1 has i, inputs have L bits"""
+        L = len(layers)
+        return cls(ctx, [1] + list(range(1, L + 1)), layers)
+
+    def total_rounds(self) -> int:
+        return int(self.ctx.lib.zk_wide_circuit_total_rounds(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zk_wide_circuit_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def prove_wide(ctx: Context, circuit: WideCircuit, inputs, flags: int = 0, want_output: bool = True) -> Proof:
+    """gkr_protocol::prove with the sparse two-phase layer sumcheck (same proof as `prove` on reference shapes)."""
+    lib = ctx.lib
+    inputs = as_elems(inputs).reshape(-1, 4)
+    L = circuit.n_layers
+    R = circuit.total_rounds()
+    n_out = 1 << circuit.layer_bits[0]
+    output = np.zeros((n_out, 4), dtype=np.uint64) if want_output else None
+    claimed = np.zeros(4, dtype=np.uint64)
+    claims = np.zeros((L, 4), dtype=np.uint64)
+    coeffs = np.zeros((R, 3, 4), dtype=np.uint64)
+    chal = np.zeros((R, 4), dtype=np.uint64)
+    wb = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
+    wc = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
+    ctx.check(lib.zk_gkr_prove_wide(ctx.h, circuit.h, _ptr(inputs), inputs.shape[0], _ptr(output) if want_output else None,
+                                    _ptr(claimed), _ptr(claims), _ptr(coeffs), _ptr(chal), _ptr(wb), _ptr(wc), flags))
+    proofs, o = [], 0
+    for i in range(L):
+        r = 2 * circuit.layer_bits[i + 1]
+        polys = [DenseUnivariatePolynomial(ctx.field, coeffs[o + k]) for k in range(r)]
+        proofs.append(SumcheckProverProof(claims[i].copy(), polys, chal[o:o + r].copy()))
+        o += r
+    return Proof(output, claimed, proofs, wb[: L - 1].copy(), wc[: L - 1].copy())
