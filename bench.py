@@ -40,6 +40,8 @@ WORKLOADS = {
     "product30": (0, "BN254_FQ", 1, 2, 30, "degree-2 product sumcheck f*g (BASELINE.json configs[2])"),
     "plain24": (2, "BLS12_381_FR", 1, 1, 24, "plain sumcheck of one MLE (BASELINE.json configs[1])"),
     "gkr22": (0, "BN254_FQ", 2, 2, 22, "GKR-shaped 2x2 sumcheck add*(Wb+Wc)+mul*(Wb*Wc) tables"),
+    # --log2 = log2 of the layer width; 16 layers of 2^log2 gates, sparse two-phase layer prover
+    "gkr_wide": (0, "BN254_FQ", 2, 2, 22, "GKR prove of a synthetic layered add/mul circuit, depth 16, width 2^22 gates (BASELINE.json configs[3])"),
     "mle": (0, "BN254_FQ", 1, 1, 28, "MultilinearPolynomial::evaluate / partial_evaluate sweep point (BASELINE.json configs[4])"),
     # --log2 is the circuit depth L here: reference-shaped layered circuit, layer i has 2^i gates over 2^(i+1) wires,
     # 2^L inputs; the layer-i sumcheck runs over 4^(i+1) entries x 4 tables
@@ -109,6 +111,95 @@ def cpu_gkr_once(field: int, depth: int):
     t0 = time.perf_counter()
     co.gkr_prove(field, c, I)
     return time.perf_counter() - t0
+
+
+def wide_circuit_arrays(width_log2: int, depth: int = 16, seed: int = SEED):
+    """depth layers of 2^w gates each.  Layers 1..depth-1: gate g drives output g from two seeded wires of the layer below;
+    layer 0 reduces the 2^w wires below it into TWO outputs (gate g reads wire g and a seeded wire, output g mod 2), so the
+    circuit keeps the reference's output shape (one output bit -> one challenge r_a, 64 bytes absorbed).  Duplicate-free."""
+    rng = np.random.default_rng(seed)
+    n = 1 << width_log2
+    layers = []
+    for li in range(depth):
+        g = np.arange(n, dtype=np.int64)
+        arr = np.zeros((n, 4), dtype=np.int64)
+        arr[:, 1] = rng.integers(0, n, size=n)
+        arr[:, 3] = rng.integers(0, 2, size=n)
+        if li == 0:
+            arr[:, 0] = g
+            arr[:, 2] = g & 1
+        else:
+            arr[:, 0] = rng.integers(0, n, size=n)
+            arr[:, 2] = g
+        layers.append(arr)
+    bits = [1] + [width_log2] * depth
+    return bits, layers
+
+
+def run_gkr_wide(args, wl):
+    field, fname, P, D, w_default, desc = wl
+    w = args.log2 or w_default
+    depth = 16
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return          # single-GPU workload: 704 latency-bound rounds over 128 MiB tables do not shard usefully (DESIGN.md)
+    if args.impl == "reference":
+        args.workload = "gkr"
+        return run_gkr(args, WORKLOADS["gkr"])
+    import torch
+    import zk_cryptography_research_implementations_b200 as zk
+    from zk_cryptography_research_implementations_b200 import gkr
+    torch.cuda.set_device(0)
+    ctx = zk.Context(field, 0, stream=torch.cuda.current_stream().cuda_stream)
+    bits, layers = wide_circuit_arrays(w, depth)
+    t0 = time.perf_counter()
+    circuit = gkr.WideCircuit(ctx, bits, layers)
+    setup_s = time.perf_counter() - t0
+    I = gkr_inputs(field, w)
+    proof = None
+    for _ in range(args.warmup):
+        proof = gkr.prove_wide(ctx, circuit, I)
+    ctx.set_profiling(True)
+    ctx.reset_stats()
+    sampler = ClockSampler(0)
+    times = []
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        proof = gkr.prove_wide(ctx, circuit, I)      # inputs on the host -> proof on the host
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop()
+    st = ctx.stats()
+    ms = statistics.mean(times)
+    hbm_peak, peak_src = peaks()
+    achieved = st["round_bytes"] / (st["round_ms"] * 1e-3) / 1e9 if st["round_ms"] > 0 else 0.0
+    cpu = None
+    if not args.no_cpu:
+        d = args.cpu_depth
+        t = cpu_gkr_once(field, d)
+        cpu = {"value": t * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+               "sample": "reference-shaped depth-%d circuit (2^%d inputs, %d gates): the reference's dense 2^(3i+2) wiring tables cannot "
+                         "express or hold a 2^%d-wide layer; oracle C restatement, 1 thread" % (d, d, (1 << d) - 1, w)}
+    rounds = circuit.total_rounds()
+    coeffs = np.stack([p.coefficients for sp in proof.sumcheck_proofs for p in sp.round_univariate_polynomials])
+    line = {"metric": "gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
+            "config": {"workload": "gkr_wide: " + desc, "field": fname, "depth": depth, "width_log2": w, "gates": depth << w,
+                       "layer_bits": bits, "sumcheck_rounds": rounds, "prover": "sparse two-phase (csrc/gkr_wide.cu)",
+                       "circuit_setup_s": setup_s, "l2": "per phase 4 tables x %d MiB" % ((32 << w) >> 20)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "fold_evals_kernel / round_evals_kernel <%s,P=2,D=2> (%d launches)" % (fname, st["round_launches"]),
+                         "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": int(I.nbytes), "d2h_bytes_per_step": int(rounds * 4 * 32),
+                    "note": "value already is the host-to-host zk_gkr_prove_wide call (inputs on the host, proof on the host; the circuit's CSR lives on the GPU)"},
+            "gpu_launches": st["launches"], "clocks": clocks,
+            "proof_digest": int(np.bitwise_xor.reduce(coeffs.reshape(-1))) & 0xFFFFFFFF}
+    print(json.dumps(line), flush=True)
+    circuit.close()
+    ctx.close()
 
 
 def run_gkr(args, wl):
@@ -230,7 +321,7 @@ def run_mle(args, wl):
     N = 1 << log2
     m = N // world
     table = ctx.generate(SEED, 0, m, first=rank, step=world)
-    rs = np.ascontiguousarray(ctx.generate(SEED, 99, max(log2, 1)).download()[:log2])
+    rs = np.ascontiguousarray(ctx.generate(SEED, 99, 64).download()[:log2])
     out = np.zeros(4, dtype=np.uint64)
 
     def barrier():
@@ -574,6 +665,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.workload == "gkr":
         run_gkr(args, wl)
+    elif args.workload == "gkr_wide":
+        run_gkr_wide(args, wl)
     elif args.workload == "mle":
         run_mle(args, wl)
     elif args.impl == "reference":

@@ -488,16 +488,21 @@ extern "C" int zk_mle_add(zk_ctx* ctx, const zk_table* a, const zk_table* b, zk_
     ZK_DISPATCH_FID(ctx, (ew_kernel<FID, EW_ADD><<<grid_for(ctx, a->len, 4), kThreads, 0, ctx->stream>>>(a->d, b->d, (*out)->d, a->len)));
     return post_launch(ctx);
 }
+// out[b * n + c] = wb[b] (op) wc[c] into caller-provided memory (n * n elements)
+int tensor_into(zk_ctx* ctx, const Fe* wb, const Fe* wc, uint64_t n, Fe* out, int op) {
+    if (ilog2(n) > 31) return fail(ctx, ZK_ERR_ARG, "tensor too large");
+    int grid = grid_for(ctx, n * n, 4);
+    if (op == EW_ADD) { ZK_DISPATCH_FID(ctx, (tensor_kernel<FID, EW_ADD><<<grid, kThreads, 0, ctx->stream>>>(wb, wc, out, n, ilog2(n)))); }
+    else { ZK_DISPATCH_FID(ctx, (tensor_kernel<FID, EW_MUL><<<grid, kThreads, 0, ctx->stream>>>(wb, wc, out, n, ilog2(n)))); }
+    return post_launch(ctx);
+}
 static int tensor_op(zk_ctx* ctx, const zk_table* wb, const zk_table* wc, zk_table** out, int op) {
     if (wb->len != wc->len) return fail(ctx, ZK_ERR_ASSERT, "Different polynomial length");
     uint64_t n = wb->len;
     if (ilog2(n) > 31) return fail(ctx, ZK_ERR_ARG, "tensor too large");
     int rc = table_alloc(ctx, n * n, out);
     if (rc) return rc;
-    int grid = grid_for(ctx, n * n, 4);
-    if (op == EW_ADD) { ZK_DISPATCH_FID(ctx, (tensor_kernel<FID, EW_ADD><<<grid, kThreads, 0, ctx->stream>>>(wb->d, wc->d, (*out)->d, n, ilog2(n)))); }
-    else { ZK_DISPATCH_FID(ctx, (tensor_kernel<FID, EW_MUL><<<grid, kThreads, 0, ctx->stream>>>(wb->d, wc->d, (*out)->d, n, ilog2(n)))); }
-    return post_launch(ctx);
+    return tensor_into(ctx, wb->d, wc->d, n, (*out)->d, op);
 }
 extern "C" int zk_mle_tensor_add(zk_ctx* ctx, const zk_table* wb, const zk_table* wc, zk_table** out) { return tensor_op(ctx, wb, wc, out, EW_ADD); }
 extern "C" int zk_mle_tensor_mul(zk_ctx* ctx, const zk_table* wb, const zk_table* wc, zk_table** out) { return tensor_op(ctx, wb, wc, out, EW_MUL); }

@@ -58,6 +58,11 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Fe* table, const uint
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st256(table + pos[i], val[i]);
 }
 
+struct DevPool {   // one allocation for all per-layer tables of a prove (cudaMalloc/cudaFree per layer cost more than the kernels)
+    Fe* p = nullptr;
+    ~DevPool() { if (p) cudaFree(p); }
+};
+
 // zero a table and scatter (position -> value) pairs with unique positions
 int fill_sparse(zk_ctx* ctx, zk_table* t, const std::map<uint64_t, HFe>& entries) {
     ZK_CUDA(cudaMemsetAsync(t->d, 0, (size_t)t->len * sizeof(Fe), ctx->stream));
@@ -165,6 +170,17 @@ extern "C" int zk_gkr_prove(zk_ctx* ctx, const zk_circuit_desc* c, const uint64_
     if (w0.size() != 2) return fail(ctx, ZK_ERR_ARG, "reference-shaped circuits have at most two outputs (layer 0 has one output bit)");
     HFe claim = f.add(w0[0], f.mul(ra, f.sub(w0[1], w0[0])));                  // :51 W_0(r_a)
 
+    // one pool for the four 4^(i+1)-entry tables and W of the widest layer
+    const uint64_t nbc_max = 1ull << (2 * bc_bits(L - 1)), w_max = 1ull << bc_bits(L - 1);
+    DevPool pool;
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaMalloc(&pool.p, (size_t)(4 * nbc_max + w_max) * sizeof(Fe)));
+    zk_table view[5];
+    for (int i = 0; i < 5; ++i) {
+        view[i].d = pool.p + (size_t)i * nbc_max;
+        view[i].owned = false;
+    }
+
     HFe alpha = f.zero(), beta = f.zero();
     std::vector<HFe> rb, rcv;
     uint64_t round_off = 0;
@@ -201,17 +217,20 @@ extern "C" int zk_gkr_prove(zk_ctx* ctx, const zk_circuit_desc* c, const uint64_
             }
         }
         // ---- the four tables of compute_fbc_polynomial (utils.rs:8-21)
-        zk_table *t_add = nullptr, *t_wadd = nullptr, *t_mul = nullptr, *t_wmul = nullptr, *t_w = nullptr;
-        if ((rc = table_alloc(ctx, nbc, &t_add))) return rc;
-        if ((rc = table_alloc(ctx, nbc, &t_mul))) return rc;
+        zk_table *t_add = &view[0], *t_wadd = &view[1], *t_mul = &view[2], *t_wmul = &view[3], *t_w = &view[4];
+        for (int i = 0; i < 4; ++i) view[i].len = view[i].cap = nbc;
+        t_w->len = t_w->cap = wlen;
         if ((rc = fill_sparse(ctx, t_add, add_e))) return rc;
         if ((rc = fill_sparse(ctx, t_mul, mul_e))) return rc;
-        if ((rc = zk_table_upload(ctx, values.data() + 4 * off[li + 1], wlen, &t_w))) return rc;       // :88-89 W_b = W_c
-        if ((rc = zk_mle_tensor_add(ctx, t_w, t_w, &t_wadd))) return rc;
-        if ((rc = zk_mle_tensor_mul(ctx, t_w, t_w, &t_wmul))) return rc;
-        zk_table* tabs[4] = {t_add, t_wadd, t_mul, t_wmul};
-        zk_sumpoly* sp = nullptr;
-        if ((rc = zk_sumpoly_create(ctx, tabs, 2, 2, &sp))) return rc;
+        ZK_CUDA(cudaMemcpyAsync(t_w->d, values.data() + 4 * off[li + 1], wlen * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));   // :88-89 W_b = W_c
+        if ((rc = tensor_into(ctx, t_w->d, t_w->d, wlen, t_wadd->d, EW_ADD))) return rc;
+        if ((rc = tensor_into(ctx, t_w->d, t_w->d, wlen, t_wmul->d, EW_MUL))) return rc;
+        zk_sumpoly sp_obj;
+        sp_obj.P = 2;
+        sp_obj.D = 2;
+        sp_obj.len = nbc;
+        sp_obj.tabs = {t_add, t_wadd, t_mul, t_wmul};
+        zk_sumpoly* sp = &sp_obj;
         // ---- sumcheck_prove(f_bc, claimed_sum, &mut transcript) :99
         memcpy(layer_claims + 4 * li, claim.l, 32);
         zk_transcript wrap;
@@ -219,12 +238,11 @@ extern "C" int zk_gkr_prove(zk_ctx* ctx, const zk_circuit_desc* c, const uint64_
         uint64_t* chal = challenges_out + 4 * round_off;
         rc = zk_prove_product(ctx, sp, claim.l, &wrap, coeffs_out + 12 * round_off, chal, nullptr, 0);
         tr = wrap.t;
-        zk_sumpoly_free(ctx, sp);
-        if (rc) { zk_table_free(ctx, t_w); return rc; }
+        if (rc) return rc;
         if (li + 1 < L) {                                                      // :109
             HFe wbv, wcv;
-            if ((rc = zk_mle_evaluate(ctx, t_w, chal, bcb, wbv.l))) { zk_table_free(ctx, t_w); return rc; }             // utils.rs:70-82
-            if ((rc = zk_mle_evaluate(ctx, t_w, chal + 4 * bcb, bcb, wcv.l))) { zk_table_free(ctx, t_w); return rc; }
+            if ((rc = zk_mle_evaluate(ctx, t_w, chal, bcb, wbv.l))) return rc;                                           // utils.rs:70-82
+            if ((rc = zk_mle_evaluate(ctx, t_w, chal + 4 * bcb, bcb, wcv.l))) return rc;
             memcpy(wb_out + 4 * li, wbv.l, 32);
             memcpy(wc_out + 4 * li, wcv.l, 32);
             rb.assign(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + bcb);                                 // :120-123
@@ -235,7 +253,6 @@ extern "C" int zk_gkr_prove(zk_ctx* ctx, const zk_circuit_desc* c, const uint64_
             beta = tr.challenge(f);                                            // :128-129
             claim = f.add(f.mul(alpha, wbv), f.mul(beta, wcv));                // :132
         }
-        zk_table_free(ctx, t_w);
         round_off += rounds;
     }
     memcpy(claimed_sum, claim.l, 32);

@@ -59,11 +59,24 @@ struct WideLayer {
     GateCsr by_right;   // x = out,  y = left
     GateCsr by_out;     // x = left, y = right
 };
+struct DevBuf {   // RAII device allocation
+    Fe* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p) { o.p = nullptr; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(uint64_t n) { return cudaMalloc(&p, (size_t)(n ? n : 1) * sizeof(Fe)); }
+};
 struct zk_wide_circuit {
     uint32_t L = 0;
     std::vector<uint32_t> bits;   // bits[li] = log2(#values of layer li), li = 0..L (L = inputs)
     std::vector<WideLayer> layers;
     int device = 0;
+    // prover workspace, allocated with the circuit so a prove never calls cudaMalloc/cudaFree:
+    std::vector<DevBuf> W;        // all layer values (Circuit::evaluate result), resident
+    DevBuf wtab, eqa, eqb, h1, h2, Wc, ones, factors, half_hi, half_lo;
+    bool ones_ready = false;
 };
 
 namespace {
@@ -102,6 +115,18 @@ template <int FID> __global__ void __launch_bounds__(kThreads) eq_kernel(Fe* out
     }
 }
 
+// out[a] = hi[a >> lo_bits] * lo[a & (2^lo_bits - 1)]: eq over k variables from two half-width eq tables, one
+// multiply per entry (the direct product above costs k multiplies per entry)
+template <int FID>
+__global__ void __launch_bounds__(kThreads) eq_outer_kernel(Fe* out, const Fe* hi, const Fe* lo, uint32_t lo_bits, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = (1ull << lo_bits) - 1;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride) {
+        Fe h = hi[a >> lo_bits], l = lo[a & mask], o;
+        Fp<FID>::mont_mul(o, h, l);
+        st256(out + a, o);
+    }
+}
+
 // Circuit::evaluate for one layer (arithmetic_circuit.rs:82-97): out[o] = sum over gates with output o of op(in[l], in[r])
 template <int FID>
 __global__ void __launch_bounds__(kThreads) eval_layer_kernel(GateCsr g, const Fe* in, Fe* out, uint64_t n_out) {
@@ -117,6 +142,24 @@ __global__ void __launch_bounds__(kThreads) eval_layer_kernel(GateCsr g, const F
             Fp<FID>::add(acc, acc, v);
         }
         st256(out + o, acc);
+    }
+}
+
+// same, one BLOCK per output: for reduction layers where a few outputs collect very many gates
+template <int FID>
+__global__ void __launch_bounds__(kThreads) eval_layer_block_kernel(GateCsr g, const Fe* in, Fe* out, uint64_t n_out) {
+    for (uint64_t o = blockIdx.x; o < n_out; o += gridDim.x) {
+        Fe acc[1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[0].v[k] = 0;
+        for (uint64_t i = g.off[o] + threadIdx.x; i < g.off[o + 1]; i += blockDim.x) {
+            Fe l = ld256(in + g.x[i]), r = ld256(in + g.y[i]), v;
+            if (g.op[i] == 0) Fp<FID>::add(v, l, r);
+            else Fp<FID>::mont_mul(v, l, r);
+            Fp<FID>::add(acc[0], acc[0], v);
+        }
+        block_sum<FID, 1>(acc);
+        if (threadIdx.x == 0) st256(out + o, acc[0]);
     }
 }
 
@@ -200,12 +243,6 @@ void free_csr(GateCsr* g) {
     *g = GateCsr();
 }
 
-struct DevBuf {   // RAII device allocation
-    Fe* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(uint64_t n) { return cudaMalloc(&p, (size_t)(n ? n : 1) * sizeof(Fe)); }
-};
-
 // factors for eq_kernel from host challenges
 int upload_factors(zk_ctx* ctx, const std::vector<HFe>& r, Fe* dst) {
     const HostField& f = ctx->field;
@@ -215,6 +252,29 @@ int upload_factors(zk_ctx* ctx, const std::vector<HFe>& r, Fe* dst) {
         fac[2 * v + 1] = r[v];
     }
     ZK_CUDA(cudaMemcpyAsync(dst, fac.data(), fac.size() * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+// out[a] = scale * eq(r, a) for all a in {0,1}^k (variable 0 = most significant bit)
+int build_eq(zk_ctx* ctx, zk_wide_circuit* wc, const std::vector<HFe>& r, const HFe& scale, Fe* out) {
+    const uint32_t k = (uint32_t)r.size(), kh = k / 2, kl = k - kh;
+    int rc = upload_factors(ctx, r, wc->factors.p);
+    if (rc) return rc;
+    Fe scale_fe, one_fe;
+    HFe one = ctx->field.one();
+    memcpy(scale_fe.v, scale.l, 32);
+    memcpy(one_fe.v, one.l, 32);
+    if (k <= 8) {
+        ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(out, k, wc->factors.p, scale_fe)));
+        ctx->launches++;
+    } else {
+        ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, 1ull << kh, 4), kThreads, 0, ctx->stream>>>(wc->half_hi.p, kh, wc->factors.p, scale_fe)));
+        ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, 1ull << kl, 4), kThreads, 0, ctx->stream>>>(wc->half_lo.p, kl, wc->factors.p + 2 * kh, one_fe)));
+        ZK_FID_SWITCH(ctx, (eq_outer_kernel<FID><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(out, wc->half_hi.p, wc->half_lo.p, kl, 1ull << k)));
+        ctx->launches += 3;
+    }
+    ZK_CUDA(cudaGetLastError());
+    // `factors` is reused by the next build_eq: make sure the kernels above have consumed it
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZK_OK;
 }
@@ -246,6 +306,25 @@ extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint
         }
         if (rc) { zk_wide_circuit_free(ctx, wc); return rc; }
     }
+    {   // workspace
+        uint32_t maxbits = 0;
+        for (uint32_t b : wc->bits) maxbits = std::max(maxbits, b);
+        const uint64_t maxn = 1ull << maxbits;
+        wc->W.resize(n_layers + 1);
+        cudaError_t e = cudaSuccess;
+        for (uint32_t li = 0; li <= n_layers && e == cudaSuccess; ++li) e = wc->W[li].alloc(1ull << wc->bits[li]);
+        DevBuf* bufs[] = {&wc->wtab, &wc->eqa, &wc->eqb, &wc->h1, &wc->h2, &wc->Wc, &wc->ones};
+        for (DevBuf* b : bufs)
+            if (e == cudaSuccess) e = b->alloc(maxn);
+        if (e == cudaSuccess) e = wc->factors.alloc(2 * 32);
+        if (e == cudaSuccess) e = wc->half_hi.alloc(1ull << 16);
+        if (e == cudaSuccess) e = wc->half_lo.alloc(1ull << 16);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("cudaMalloc (GKR workspace): ") + cudaGetErrorString(e);
+            zk_wide_circuit_free(ctx, wc);
+            return ZK_ERR_CUDA;
+        }
+    }
     *result = wc;
     return ZK_OK;
 }
@@ -267,9 +346,10 @@ extern "C" uint64_t zk_wide_circuit_total_rounds(const zk_wide_circuit* wc) {
 // gkr_protocol::prove (gkr_protocol.rs:26-143), sparse two-phase layers.  Outputs as zk_gkr_prove; `output` may be
 // NULL (wide output layers).  flags: ZK_FLAG_SKIP_ABSORB leaves the output layer out of the transcript (its absorb
 // is a serial host Keccak over 32 * 2^bits[0] bytes).
-extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const uint64_t* inputs, uint64_t n_inputs,
+extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* inputs, uint64_t n_inputs,
                                  uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
                                  uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags) {
+    zk_wide_circuit* wc = const_cast<zk_wide_circuit*>(wc_);   // the workspace inside the circuit object is mutable
     const HostField& f = ctx->field;
     const uint32_t L = wc->L;
     if (n_inputs != (1ull << wc->bits[L])) return fail(ctx, ZK_ERR_ASSERT, "different number of variables");
@@ -278,12 +358,16 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const u
     const uint64_t maxn = 1ull << maxbits;
 
     // ---- circuit.evaluate on the device: all layer values stay resident (gkr_protocol.rs:27)
-    std::vector<DevBuf> W(L + 1);
-    for (uint32_t li = 0; li <= L; ++li) ZK_CUDA(W[li].alloc(1ull << wc->bits[li]));
+    std::vector<DevBuf>& W = wc->W;
     ZK_CUDA(cudaMemcpyAsync(W[L].p, inputs, n_inputs * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
     for (uint32_t li = L; li-- > 0;) {
         const uint64_t n_out = 1ull << wc->bits[li];
-        ZK_FID_SWITCH(ctx, (eval_layer_kernel<FID><<<grid_of(ctx, n_out, 4), kThreads, 0, ctx->stream>>>(wc->layers[li].by_out, W[li + 1].p, W[li].p, n_out)));
+        if (wc->layers[li].n_gates / n_out >= 64) {   // heavy fan-in: a block per output
+            int blocks = (int)std::min<uint64_t>(n_out, (uint64_t)ctx->sm_count * 4);
+            ZK_FID_SWITCH(ctx, (eval_layer_block_kernel<FID><<<blocks, kThreads, 0, ctx->stream>>>(wc->layers[li].by_out, W[li + 1].p, W[li].p, n_out)));
+        } else {
+            ZK_FID_SWITCH(ctx, (eval_layer_kernel<FID><<<grid_of(ctx, n_out, 4), kThreads, 0, ctx->stream>>>(wc->layers[li].by_out, W[li + 1].p, W[li].p, n_out)));
+        }
         ctx->launches++;
     }
     ZK_CUDA(cudaGetLastError());
@@ -311,12 +395,12 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const u
     HFe claim = w0[0];
 
     // ---- scratch tables
-    DevBuf wtab, eqa, eqb, h1, h2, Wc, ones, factors;
-    ZK_CUDA(wtab.alloc(maxn)); ZK_CUDA(eqa.alloc(maxn)); ZK_CUDA(eqb.alloc(maxn));
-    ZK_CUDA(h1.alloc(maxn)); ZK_CUDA(h2.alloc(maxn)); ZK_CUDA(Wc.alloc(maxn)); ZK_CUDA(ones.alloc(maxn));
-    ZK_CUDA(factors.alloc(2 * 32));
-    ZK_FID_SWITCH(ctx, (fill_one_kernel<FID><<<grid_of(ctx, maxn, 4), kThreads, 0, ctx->stream>>>(ones.p, maxn)));
-    ctx->launches++;
+    DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &eqb = wc->eqb, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc, &ones = wc->ones;
+    if (!wc->ones_ready) {   // folding an all-ones table in place leaves it all ones: filled once
+        ZK_FID_SWITCH(ctx, (fill_one_kernel<FID><<<grid_of(ctx, maxn, 4), kThreads, 0, ctx->stream>>>(ones.p, maxn)));
+        ctx->launches++;
+        wc->ones_ready = true;
+    }
 
     HFe alpha = f.zero(), beta = f.zero();
     std::vector<HFe> rb, rcv;
@@ -335,20 +419,12 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const u
         int rc;
         // ---- w(a): eq(r_a, .) at the output layer, alpha eq(r_b, .) + beta eq(r_c, .) below
         if (li == 0) {
-            if ((rc = upload_factors(ctx, ra, factors.p))) return rc;
-            ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, na, 4), kThreads, 0, ctx->stream>>>(wtab.p, ab, factors.p, one_fe)));
-            ctx->launches++;
+            if ((rc = build_eq(ctx, wc, ra, f.one(), wtab.p))) return rc;
         } else {
-            Fe a_fe, b_fe;
-            memcpy(a_fe.v, alpha.l, 32);
-            memcpy(b_fe.v, beta.l, 32);
-            if ((rc = upload_factors(ctx, rb, factors.p))) return rc;
-            ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, na, 4), kThreads, 0, ctx->stream>>>(eqa.p, ab, factors.p, a_fe)));
-            ZK_CUDA(cudaStreamSynchronize(ctx->stream));
-            if ((rc = upload_factors(ctx, rcv, factors.p))) return rc;
-            ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, na, 4), kThreads, 0, ctx->stream>>>(eqb.p, ab, factors.p, b_fe)));
+            if ((rc = build_eq(ctx, wc, rb, alpha, eqa.p))) return rc;
+            if ((rc = build_eq(ctx, wc, rcv, beta, eqb.p))) return rc;
             ZK_FID_SWITCH(ctx, (ew_kernel<FID, EW_ADD><<<grid_of(ctx, na, 4), kThreads, 0, ctx->stream>>>(eqa.p, eqb.p, wtab.p, na)));
-            ctx->launches += 3;
+            ctx->launches++;
         }
         // ---- phase 1 tables and sumcheck over b
         ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nm)));
@@ -373,12 +449,11 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const u
         const HFe Wu = fin1[1];                                                                           // W(r_b)
         std::vector<HFe> u(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + m);
         // ---- phase 2 tables and sumcheck over c
-        if ((rc = upload_factors(ctx, u, factors.p))) return rc;
-        ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(eqa.p, m, factors.p, one_fe)));
+        if ((rc = build_eq(ctx, wc, u, f.one(), eqa.p))) return rc;
         Fe Wu_fe;
         memcpy(Wu_fe.v, Wu.l, 32);
         ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_fe, h1.p, h2.p, nm)));
-        ctx->launches += 2;
+        ctx->launches += 1;
         ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_CUDA(cudaGetLastError());
         for (int i = 0; i < 4; ++i) { tabs1[i]->len = nm; }

@@ -12,6 +12,7 @@ void set_len(zk_sumpoly* sp, uint64_t len);
 int sync_len(zk_ctx* ctx, zk_sumpoly* sp);
 int table_alloc(zk_ctx* ctx, uint64_t n, zk_table** out);
 int ensure_scratch(zk_ctx* ctx, size_t bytes);
+int tensor_into(zk_ctx* ctx, const zk::Fe* wb, const zk::Fe* wc, uint64_t n, zk::Fe* out, int op);
 namespace zk {
 int fetch_result(zk_ctx* ctx, HFe* out, int ne);
 int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared = false);
