@@ -190,7 +190,8 @@ def run_gkr_wide(args, wl):
                        "layer_bits": bits, "sumcheck_rounds": rounds, "prover": "sparse two-phase (csrc/gkr_wide.cu)",
                        "circuit_setup_s": setup_s, "l2": "per phase 4 tables x %d MiB" % ((32 << w) >> 20)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "fold_evals_kernel / round_evals_kernel <%s,P=2,D=2> (%d launches)" % (fname, st["round_launches"]),
+                         "peak_source": peak_src, "kernel": "fold_evals_kernel / round_evals_kernel <%s,P=1,D=2,+1 linear table> (%d launches; most are on tables far smaller than L2: "
+                                   "latency-bound, the fraction is not a bandwidth statement)" % (fname, st["round_launches"]),
                          "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)},
             "cpu_baseline": cpu,
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": int(I.nbytes), "d2h_bytes_per_step": int(rounds * 4 * 32),

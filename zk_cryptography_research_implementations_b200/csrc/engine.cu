@@ -372,19 +372,19 @@ int fetch_result(zk_ctx* ctx, HFe* out, int ne) {
     return ZK_OK;
 }
 
-int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared) {
+int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared, int nlin) {
     prof_begin(ctx);
     int rc;
-    ZK_DISPATCH_FID(ctx, rc = launch_round_evals_pd<FID>(ctx, tp, P, D, len / 2, shared));
-    prof_end(ctx, 32.0 * P * D * (double)len);
+    ZK_DISPATCH_FID(ctx, rc = launch_round_evals_pd<FID>(ctx, tp, P, D, nlin, len / 2, shared));
+    prof_end(ctx, 32.0 * (P * D + nlin) * (double)len);
     return rc;
 }
 // old length `len` (>= 4): folds to len/2 and evaluates the next round
-int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1, bool shared) {
+int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1, bool shared, int nlin) {
     prof_begin(ctx);
     int rc;
-    ZK_DISPATCH_FID(ctx, rc = launch_fold_evals_pd<FID>(ctx, tp, P, D, len / 4, ft, skip1, shared));
-    prof_end(ctx, 32.0 * P * D * 1.5 * (double)len);
+    ZK_DISPATCH_FID(ctx, rc = launch_fold_evals_pd<FID>(ctx, tp, P, D, nlin, len / 4, ft, skip1, shared));
+    prof_end(ctx, 32.0 * (P * D + nlin) * 1.5 * (double)len);
     return rc;
 }
 int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, const FoldTable& ft) {
@@ -611,7 +611,7 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
     if (int rc0 = sync_len(ctx, sp)) return rc0;
     if (!is_pow2(sp->len)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
     const HostField& f = ctx->field;
-    const int D = sp->D, P = sp->P, NE = D + 1;
+    const int D = sp->D, P = sp->P, NE = D + 1, NL = (int)sp->nlin, T = P * D + NL;
     const uint32_t n = ilog2(sp->len);
     const Interpolator& ip = interp_for(ctx, D);
     HFe claim;
@@ -624,9 +624,9 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
         const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
         int rc;
         if (k == 0) {
-            rc = launch_round_evals(ctx, tp, P, D, sp->len);                     // :41 generate_round_univariate
+            rc = launch_round_evals(ctx, tp, P, D, sp->len, false, NL);          // :41 generate_round_univariate
         } else {
-            rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1);   // :57 fused with :41
+            rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1, false, NL);   // :57 fused with :41
             set_len(sp, sp->len / 2);
         }
         if (rc) return rc;
@@ -643,12 +643,12 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
         memcpy(challenges_out + (size_t)k * 4, r.l, 32);                         // :59
     }
     if (n > 0) {                                                                 // :57 last partial_evaluate
-        int rc = launch_fold0(ctx, tp, P * D, sp->len, make_fold_table(f, r));
+        int rc = launch_fold0(ctx, tp, T, sp->len, make_fold_table(f, r));
         if (rc) return rc;
         set_len(sp, sp->len / 2);
     }
     if (final_values) {
-        for (int t = 0; t < P * D; ++t)
+        for (int t = 0; t < T; ++t)
             ZK_CUDA(cudaMemcpyAsync(final_values + 4 * t, sp->tabs[t]->d, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
     }
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -59,6 +59,7 @@ struct zk_table {
 struct zk_sumpoly {
     std::vector<zk_table*> tabs;   // [p * D + d]
     uint32_t P = 0, D = 0;
+    uint32_t nlin = 0;             // trailing tables that enter the sum linearly (internal: sparse GKR phases)
     uint64_t len = 0;
 };
 

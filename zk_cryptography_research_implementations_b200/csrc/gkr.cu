@@ -31,7 +31,6 @@ using namespace zk;
 
 namespace {
 inline bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
-inline uint32_t ilog2(uint64_t n) { uint32_t k = 0; while (n >>= 1) ++k; return k; }
 
 // num_of_layer_variables split into (a bits, b/c bits) -- arithmetic_circuit.rs:166-178 (layer 0 prints
 // a as the single digit "0": one a-bit)

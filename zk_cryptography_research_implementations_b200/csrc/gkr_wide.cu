@@ -23,6 +23,9 @@
 // challenges; parity with the reference is defined (and tested) on reference-shaped circuits.
 // Gate lists must be duplicate-free (the reference's dense indicator stores `= one`, its evaluation `+=`).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -75,8 +78,7 @@ struct zk_wide_circuit {
     int device = 0;
     // prover workspace, allocated with the circuit so a prove never calls cudaMalloc/cudaFree:
     std::vector<DevBuf> W;        // all layer values (Circuit::evaluate result), resident
-    DevBuf wtab, eqa, eqb, h1, h2, Wc, ones, factors, half_hi, half_lo;
-    bool ones_ready = false;
+    DevBuf wtab, eqa, eqb, h1, h2, Wc, factors, half_hi, half_lo;
 };
 
 namespace {
@@ -85,19 +87,6 @@ inline int grid_of(const zk_ctx* ctx, uint64_t work, int bps) {
     if (blocks > cap) blocks = cap;
     if (ctx->grid_cap > 0 && blocks > (uint64_t)ctx->grid_cap) blocks = ctx->grid_cap;
     return (int)(blocks < 1 ? 1 : blocks);
-}
-
-template <int FID> __global__ void __launch_bounds__(kThreads) fill_one_kernel(Fe* out, uint64_t n) {
-    Fe one;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) one.v[k] = 0;
-    // Montgomery one = R mod p = 2^256 - p reduced once more if needed; computed as mont(1) via R^2
-    Fe r2, plain;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { r2.v[k] = FieldParams<FID>::r2(k); plain.v[k] = (k == 0); }
-    Fp<FID>::mont_mul(one, plain, r2);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st256(out + i, one);
 }
 
 // out[a] = prod_v (bit_v(a) ? r_v : 1 - r_v), variable 0 = most significant bit of a.
@@ -313,7 +302,7 @@ extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint
         wc->W.resize(n_layers + 1);
         cudaError_t e = cudaSuccess;
         for (uint32_t li = 0; li <= n_layers && e == cudaSuccess; ++li) e = wc->W[li].alloc(1ull << wc->bits[li]);
-        DevBuf* bufs[] = {&wc->wtab, &wc->eqa, &wc->eqb, &wc->h1, &wc->h2, &wc->Wc, &wc->ones};
+        DevBuf* bufs[] = {&wc->wtab, &wc->eqa, &wc->eqb, &wc->h1, &wc->h2, &wc->Wc};
         for (DevBuf* b : bufs)
             if (e == cudaSuccess) e = b->alloc(maxn);
         if (e == cudaSuccess) e = wc->factors.alloc(2 * 32);
@@ -350,13 +339,20 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
                                  uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
                                  uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags) {
     zk_wide_circuit* wc = const_cast<zk_wide_circuit*>(wc_);   // the workspace inside the circuit object is mutable
+    // ZKB200_TRACE=1: coarse host-side timeline of one prove (stream synchronised at each mark)
+    const bool trace = getenv("ZKB200_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    double t_acc[6] = {0, 0, 0, 0, 0, 0};
+    auto mark = [&](int slot) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto now = std::chrono::steady_clock::now();
+        t_acc[slot] += std::chrono::duration<double, std::milli>(now - t_prev).count();
+        t_prev = now;
+    };
     const HostField& f = ctx->field;
     const uint32_t L = wc->L;
     if (n_inputs != (1ull << wc->bits[L])) return fail(ctx, ZK_ERR_ASSERT, "different number of variables");
-    uint32_t maxbits = 0;
-    for (uint32_t b : wc->bits) maxbits = std::max(maxbits, b);
-    const uint64_t maxn = 1ull << maxbits;
-
     // ---- circuit.evaluate on the device: all layer values stay resident (gkr_protocol.rs:27)
     std::vector<DevBuf>& W = wc->W;
     ZK_CUDA(cudaMemcpyAsync(W[L].p, inputs, n_inputs * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
@@ -371,6 +367,7 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
         ctx->launches++;
     }
     ZK_CUDA(cudaGetLastError());
+    mark(0);
 
     // ---- output layer: absorb W_0, bind its variables (gkr_protocol.rs:39-51; one challenge in the reference shape)
     HostTranscript tr;
@@ -395,21 +392,12 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
     HFe claim = w0[0];
 
     // ---- scratch tables
-    DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &eqb = wc->eqb, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc, &ones = wc->ones;
-    if (!wc->ones_ready) {   // folding an all-ones table in place leaves it all ones: filled once
-        ZK_FID_SWITCH(ctx, (fill_one_kernel<FID><<<grid_of(ctx, maxn, 4), kThreads, 0, ctx->stream>>>(ones.p, maxn)));
-        ctx->launches++;
-        wc->ones_ready = true;
-    }
+    DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &eqb = wc->eqb, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
+
 
     HFe alpha = f.zero(), beta = f.zero();
     std::vector<HFe> rb, rcv;
     uint64_t round_off = 0;
-    Fe one_fe;
-    {
-        HFe o = f.one();
-        memcpy(one_fe.v, o.l, 32);
-    }
     for (uint32_t li = 0; li < L; ++li)
         if (wc->bits[li + 1] == 0) return fail(ctx, ZK_ERR_ARG, "every layer must read at least two wires");
     for (uint32_t li = 0; li < L; ++li) {
@@ -426,18 +414,21 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
             ZK_FID_SWITCH(ctx, (ew_kernel<FID, EW_ADD><<<grid_of(ctx, na, 4), kThreads, 0, ctx->stream>>>(eqa.p, eqb.p, wtab.p, na)));
             ctx->launches++;
         }
+        mark(1);
         // ---- phase 1 tables and sumcheck over b
         ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nm)));
         ctx->launches++;
         ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_CUDA(cudaGetLastError());
-        zk_table t_h1, t_W, t_h2, t_one;
-        zk_table* tabs1[4] = {&t_h1, &t_W, &t_h2, &t_one};
-        Fe* ptr1[4] = {h1.p, Wc.p, h2.p, ones.p};
-        for (int i = 0; i < 4; ++i) { tabs1[i]->d = ptr1[i]; tabs1[i]->len = tabs1[i]->cap = nm; tabs1[i]->owned = false; }
+        // h1*W + h2*1: one product plus one LINEAR table -- the all-ones factor is never materialised
+        zk_table t_h1, t_W, t_h2;
+        zk_table* tabs1[3] = {&t_h1, &t_W, &t_h2};
+        Fe* ptr1[3] = {h1.p, Wc.p, h2.p};
+        for (int i = 0; i < 3; ++i) { tabs1[i]->d = ptr1[i]; tabs1[i]->len = tabs1[i]->cap = nm; tabs1[i]->owned = false; }
+        mark(2);
         zk_sumpoly sp1;
-        sp1.P = 2; sp1.D = 2; sp1.len = nm;
-        sp1.tabs.assign(tabs1, tabs1 + 4);
+        sp1.P = 1; sp1.D = 2; sp1.nlin = 1; sp1.len = nm;
+        sp1.tabs.assign(tabs1, tabs1 + 3);
         memcpy(layer_claims + 4 * li, claim.l, 32);
         zk_transcript wrap;
         wrap.t = tr;
@@ -446,6 +437,7 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
         HFe fin1[4], fin2[4];
         rc = zk_prove_product(ctx, &sp1, claim.l, &wrap, coef, chal, fin1[0].l, 0);                      // rounds 0..m-1
         if (rc) return rc;
+        mark(3);
         const HFe Wu = fin1[1];                                                                           // W(r_b)
         std::vector<HFe> u(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + m);
         // ---- phase 2 tables and sumcheck over c
@@ -456,17 +448,19 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
         ctx->launches += 1;
         ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_CUDA(cudaGetLastError());
-        for (int i = 0; i < 4; ++i) { tabs1[i]->len = nm; }
-        zk_table* tabs2[4] = {&t_h1, &t_one, &t_h2, &t_W};                                               // A*1 + B*W
+        mark(4);
+        for (int i = 0; i < 3; ++i) { tabs1[i]->len = nm; }
+        zk_table* tabs2[3] = {&t_h2, &t_W, &t_h1};                                                       // B*W + A*1 (A in h1, B in h2)
         zk_sumpoly sp2;
-        sp2.P = 2; sp2.D = 2; sp2.len = nm;
-        sp2.tabs.assign(tabs2, tabs2 + 4);
+        sp2.P = 1; sp2.D = 2; sp2.nlin = 1; sp2.len = nm;
+        sp2.tabs.assign(tabs2, tabs2 + 3);
         // the running claim entering round m is s_{m-1}(r_{m-1}); it is not absorbed again (one 2m-round sumcheck)
         HFe mid = f.horner(reinterpret_cast<HFe*>(coef + 12 * (m - 1)), 3, u[m - 1]);
         rc = zk_prove_product(ctx, &sp2, mid.l, &wrap, coef + 12 * m, chal + 4 * m, fin2[0].l, ZK_FLAG_NO_CLAIM_ABSORB);   // rounds m..2m-1
         if (rc) return rc;
         tr = wrap.t;
-        const HFe Wv = fin2[3];                                                                           // W(r_c)
+        mark(5);
+        const HFe Wv = fin2[1];                                                                           // W(r_c)
         if (li + 1 < L) {                                                                                 // gkr_protocol.rs:109-132
             memcpy(wb_out + 4 * li, Wu.l, 32);
             memcpy(wc_out + 4 * li, Wv.l, 32);
@@ -482,5 +476,8 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
     }
     memcpy(claimed_sum, claim.l, 32);
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace)
+        fprintf(stderr, "zk_gkr_prove_wide ms: upload+evaluate %.2f | w tables %.2f | phase-1 build %.2f | phase-1 sumcheck %.2f | eq(u)+phase-2 build %.2f | phase-2 sumcheck %.2f\n",
+                t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4], t_acc[5]);
     return ZK_OK;
 }

@@ -15,8 +15,8 @@ int ensure_scratch(zk_ctx* ctx, size_t bytes);
 int tensor_into(zk_ctx* ctx, const zk::Fe* wb, const zk::Fe* wc, uint64_t n, zk::Fe* out, int op);
 namespace zk {
 int fetch_result(zk_ctx* ctx, HFe* out, int ne);
-int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared = false);
-int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1, bool shared = false);
+int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared = false, int nlin = 0);
+int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1, bool shared = false, int nlin = 0);
 // spin until `box` carries sequence number `seq` (watchdog: stream errors, 120 s wall clock)
 int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own);
 int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, const FoldTable& ft);

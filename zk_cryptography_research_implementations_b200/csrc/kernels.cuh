@@ -143,17 +143,26 @@ template <int FID, int NE> __device__ __forceinline__ void grid_sum_publish(Fe (
 // (sumcheck_gkr_protocol.rs:127-137 evaluates the same sums with D+1 full folds of every table.)
 // D == 1 (plain sumcheck, prover.rs:74-89) accumulates 9-limb sums; D >= 2 accumulates 17-limb
 // unreduced products.  SKIP1 leaves s(1) out (the host derives it from the running claim).
-template <int FID, int P, int D, bool SKIP1> struct RoundAcc {
+// NLIN extra tables enter the sum LINEARLY (a product with the all-ones table, which is then neither stored, folded
+// nor multiplied): s(X) += sum_l (lo_l + X (hi_l - lo_l)).  The sparse GKR layer prover's phases have exactly that
+// shape, h1*W + h2*1 (gkr_wide.cu).  Only the two half sums are accumulated; finish() spreads them over the s(X).
+template <int FID, int P, int D, bool SKIP1, int NLIN = 0> struct RoundAcc {
     static constexpr int NE = D + 1;
     static constexpr int W = (D == 1) ? 9 : 17;
+    static constexpr int T = P * D + NLIN;
     uint32_t acc[NE][W];
+    uint32_t lin[NLIN > 0 ? 2 : 1][9];
     __device__ __forceinline__ void init() {
 #pragma unroll
         for (int e = 0; e < NE; ++e)
 #pragma unroll
             for (int k = 0; k < W; ++k) acc[e][k] = 0;
+#pragma unroll
+        for (int e = 0; e < (NLIN > 0 ? 2 : 1); ++e)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) lin[e][k] = 0;
     }
-    __device__ __forceinline__ void add_point(int e, const Fe (&v)[P * D]) {
+    __device__ __forceinline__ void add_point(int e, const Fe (&v)[T]) {
         if (D == 1) {
 #pragma unroll
             for (int p = 0; p < P; ++p) Fp<FID>::acc9_add(acc[e], v[p]);
@@ -167,11 +176,16 @@ template <int FID, int P, int D, bool SKIP1> struct RoundAcc {
             }
         }
     }
-    __device__ __forceinline__ void add_pair(const Fe (&lo)[P * D], const Fe (&hi)[P * D]) {
+    __device__ __forceinline__ void add_pair(const Fe (&lo)[T], const Fe (&hi)[T]) {
         add_point(0, lo);
         if (!SKIP1) add_point(1, hi);
+#pragma unroll
+        for (int l = 0; l < NLIN; ++l) {
+            Fp<FID>::acc9_add(lin[0], lo[P * D + l]);
+            Fp<FID>::acc9_add(lin[1], hi[P * D + l]);
+        }
         if (D >= 2) {
-            Fe cur[P * D], diff[P * D];
+            Fe cur[T], diff[T];
 #pragma unroll
             for (int t = 0; t < P * D; ++t) {
                 Fp<FID>::sub(diff[t], hi[t], lo[t]);
@@ -192,14 +206,28 @@ template <int FID, int P, int D, bool SKIP1> struct RoundAcc {
             if (D == 1) Fp<FID>::reduce9(out[e], acc[e]);
             else Fp<FID>::redc_wide(out[e], acc[e]);
         }
+        if (NLIN > 0) {   // linear part at X = 0, 1, 2, ...: S_lo, S_hi, 2 S_hi - S_lo, ...
+            Fe slo, shi, cur, diff;
+            Fp<FID>::reduce9(slo, lin[0]);
+            Fp<FID>::reduce9(shi, lin[1]);
+            Fp<FID>::add(out[0], out[0], slo);
+            if (!SKIP1) Fp<FID>::add(out[1], out[1], shi);
+            Fp<FID>::sub(diff, shi, slo);
+            cur = shi;
+#pragma unroll
+            for (int x = 2; x <= D; ++x) {
+                Fp<FID>::add(cur, cur, diff);
+                Fp<FID>::add(out[x], out[x], cur);
+            }
+        }
     }
 };
 
 // Round 0: evaluations only.  half = N/2 pairs (j, j + half).
-template <int FID, int P, int D>
+template <int FID, int P, int D, int NLIN = 0>
 __global__ void __launch_bounds__(kThreads) round_evals_kernel(TablePtrs tp, uint64_t half, ReduceScratch rs) {
-    constexpr int T = P * D;
-    RoundAcc<FID, P, D, false> ra;
+    constexpr int T = P * D + NLIN;
+    RoundAcc<FID, P, D, false, NLIN> ra;
     ra.init();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
@@ -226,19 +254,25 @@ __global__ void __launch_bounds__(kThreads) round_evals_kernel(TablePtrs tp, uin
 // Rounds k >= 1: fold table_{k-1} (4q entries per table) by r in place into table_k (2q entries) and
 // evaluate round k on the folded values.  Thread j owns old entries j, j+q, j+2q, j+3q and new
 // entries j, j+q -- it never touches another thread's data, so the in-place update is race free.
-template <int FID, int P, int D, bool SKIP1>
-__global__ void __launch_bounds__(kThreads)
+#ifndef ZK_FOLD_MIN_BLOCKS
+#define ZK_FOLD_MIN_BLOCKS 2   // register cap so that two 256-thread blocks stay resident per SM for up to 3 tables
+#endif
+#ifndef ZK_PREFETCH_DIST
+#define ZK_PREFETCH_DIST 1
+#endif
+template <int FID, int P, int D, bool SKIP1, int NLIN = 0>
+__global__ void __launch_bounds__(kThreads, (P * D + NLIN <= 3 && D <= 2) ? ZK_FOLD_MIN_BLOCKS : 1)
     fold_evals_kernel(TablePtrs tp, uint64_t q, const __grid_constant__ FoldTable ft, ReduceScratch rs) {
-    constexpr int T = P * D;
-    RoundAcc<FID, P, D, SKIP1> ra;
+    constexpr int T = P * D + NLIN;
+    RoundAcc<FID, P, D, SKIP1, NLIN> ra;
     ra.init();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < q; j += stride) {
-        if (j + stride < q) {   // next iteration's sectors start their trip from HBM now
+        if (j + ZK_PREFETCH_DIST * stride < q) {   // a later iteration's sectors start their trip from HBM now
 #pragma unroll
             for (int t = 0; t < T; ++t) {
 #pragma unroll
-                for (int s = 0; s < 4; ++s) prefetch_l2(tp.t[t] + j + stride + s * q);
+                for (int s = 0; s < 4; ++s) prefetch_l2(tp.t[t] + j + ZK_PREFETCH_DIST * stride + s * q);
             }
         }
         Fe lo[T], hi[T];

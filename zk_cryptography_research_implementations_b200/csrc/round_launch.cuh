@@ -37,21 +37,29 @@ inline ReduceScratch reduce_scratch(zk_ctx* ctx, bool shared) {
     return ReduceScratch{ctx->partials, ctx->ticket, ctx->mail_dev, seq};
 }
 inline int unsupported_pd(zk_ctx* ctx) {
-    ctx->err = "unsupported (P, D): supported are (1,1) (1,2) (2,2) (3,2) (4,2) (1,3) (2,3)";
+    ctx->err = "unsupported (P, D): supported are (1,1) (1,2) (2,2) (3,2) (4,2) (1,3) (2,3), and (1,2) with one linear table";
     return ZK_ERR_ARG;
 }
 // resident blocks per SM for the round kernels (register-limited; see profiles/)
-inline int round_blocks_per_sm(int P, int D) { return (P * D >= 4) ? 1 : 2; }
+#ifndef ZK_ROUND_BPS
+#define ZK_ROUND_BPS 4
+#endif
+inline int round_blocks_per_sm(int tables) { return (tables >= 4) ? 2 : ZK_ROUND_BPS; }
 
 #define ZK_PD_CASES ZK_CASE(1, 1) ZK_CASE(1, 2) ZK_CASE(2, 2) ZK_CASE(1, 3) ZK_CASE(2, 3) ZK_CASE(3, 2) ZK_CASE(4, 2)
 
-template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t half, bool shared);
-template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t q, const FoldTable& ft, bool skip1, bool shared);
+template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t half, bool shared);
+template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t q, const FoldTable& ft, bool skip1, bool shared);
 
 #ifdef ZK_INSTANTIATE_ROUND_EVALS
-template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t half, bool shared) {
+template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t half, bool shared) {
+    if (nlin != 0 && !(P == 1 && D == 2 && nlin == 1)) return unsupported_pd(ctx);
     ReduceScratch rs = reduce_scratch(ctx, shared);
-    int grid = launch_grid(ctx, half, round_blocks_per_sm(P, D));
+    int grid = launch_grid(ctx, half, round_blocks_per_sm(P * D + nlin));
+    if (nlin == 1) {
+        round_evals_kernel<FID, 1, 2, 1><<<grid, kThreads, 0, ctx->stream>>>(tp, half, rs);
+        return launch_check(ctx);
+    }
 #define ZK_CASE(PP, DD)                                                                    \
     if (P == PP && D == DD) {                                                              \
         round_evals_kernel<FID, PP, DD><<<grid, kThreads, 0, ctx->stream>>>(tp, half, rs); \
@@ -61,13 +69,19 @@ template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, i
 #undef ZK_CASE
     return unsupported_pd(ctx);
 }
-template int launch_round_evals_pd<ZK_INSTANTIATE_ROUND_EVALS>(zk_ctx*, const TablePtrs&, int, int, uint64_t, bool);
+template int launch_round_evals_pd<ZK_INSTANTIATE_ROUND_EVALS>(zk_ctx*, const TablePtrs&, int, int, int, uint64_t, bool);
 #endif
 
 #ifdef ZK_INSTANTIATE_FOLD_EVALS
-template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t q, const FoldTable& ft, bool skip1, bool shared) {
+template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t q, const FoldTable& ft, bool skip1, bool shared) {
+    if (nlin != 0 && !(P == 1 && D == 2 && nlin == 1)) return unsupported_pd(ctx);
     ReduceScratch rs = reduce_scratch(ctx, shared);
-    int grid = launch_grid(ctx, q, round_blocks_per_sm(P, D));
+    int grid = launch_grid(ctx, q, round_blocks_per_sm(P * D + nlin));
+    if (nlin == 1) {
+        if (skip1) fold_evals_kernel<FID, 1, 2, true, 1><<<grid, kThreads, 0, ctx->stream>>>(tp, q, ft, rs);
+        else fold_evals_kernel<FID, 1, 2, false, 1><<<grid, kThreads, 0, ctx->stream>>>(tp, q, ft, rs);
+        return launch_check(ctx);
+    }
 #define ZK_CASE(PP, DD)                                                                                     \
     if (P == PP && D == DD) {                                                                               \
         if (skip1) fold_evals_kernel<FID, PP, DD, true><<<grid, kThreads, 0, ctx->stream>>>(tp, q, ft, rs); \
@@ -78,7 +92,7 @@ template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, in
 #undef ZK_CASE
     return unsupported_pd(ctx);
 }
-template int launch_fold_evals_pd<ZK_INSTANTIATE_FOLD_EVALS>(zk_ctx*, const TablePtrs&, int, int, uint64_t, const FoldTable&, bool, bool);
+template int launch_fold_evals_pd<ZK_INSTANTIATE_FOLD_EVALS>(zk_ctx*, const TablePtrs&, int, int, int, uint64_t, const FoldTable&, bool, bool);
 #endif
 
 }  // namespace zk
