@@ -579,10 +579,20 @@ def run_ours(args, wl):
     # ---- integer-multiply ceiling (register-resident probe, same clocks)
     integer = {}
     if rank == 0 and not args.no_probe:
-        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced")):
+        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced"), (3, "fp64_fma")):
             ops, pms = C.c_double(), C.c_double()
             ctx.check(lib.zk_arith_probe(ctx.h, kind, 1500, 2, C.byref(ops), C.byref(pms)))
             integer[name + "_Gops"] = ops.value / 1e9
+        # IMAD.WIDE budget of one prove (per rank): round 0 evaluates (D+1) P products per pair (64 IMAD.WIDE each, D = 2)
+        # or none (D = 1); each later round folds 2T entries per new pair (84 each) and evaluates D P products (s(1) is
+        # derived) -- summed over the rounds: N/2 pairs in round 0, N/2 new pairs in all later rounds together.
+        prod0 = (D + 1) * P * 64 if D >= 2 else 0
+        prodk = D * P * 64 if D >= 2 else 0
+        imad = (m / 2.0) * prod0 + (m / 2.0) * (2 * T * 84 + prodk)
+        pipe = integer["mont_mul_Gops"] * 1e9 * 137          # IMAD.WIDE/s the probe sustains (137 per Montgomery product)
+        integer.update({"imad_wide_per_prove_per_rank": imad, "imad_wide_per_s_measured": pipe, "imad_floor_ms": imad / pipe * 1e3,
+                        "hbm_floor_ms": st["round_bytes"] / max(args.steps, 1) / (hbm_peak * 1e9) * 1e3,
+                        "note": "frac is reported against the slower (larger-time) of the two floors: HBM here"})
 
     # ---- e2e: the same prove through the C-ABI from pinned HOST tables (H2D of the inputs every step)
     e2e = None

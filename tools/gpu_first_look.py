@@ -1,4 +1,5 @@
-"""Quick look on the GPU box: arithmetic probes and round-kernel timings (not a benchmark of record)."""
+"""Quick look on the GPU box: arithmetic probes (mont_mul / fold / mul_acc at 1, 2, 4 blocks per SM) and round-kernel
+timings for a few (P, D, n).  Developer tool, not a benchmark of record: `gpurun -- python tools/gpu_first_look.py`."""
 import ctypes as C
 import json
 import sys

@@ -498,4 +498,22 @@ __global__ void __launch_bounds__(kThreads) arith_probe_kernel(Fe* out, uint32_t
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// FP64 pipe probe: 8 independent DFMA chains per thread (kind 3 of zk_arith_probe).  Not used by any kernel;
+// it answers whether a double-precision limb product (Emmart-style 52-bit limbs, 2 DFMA per product) could
+// relieve the half-rate IMAD.WIDE pipe in a later round.
+template <int UNUSED = 0> __global__ void __launch_bounds__(kThreads) dfma_probe_kernel(double* out, uint32_t iters) {
+    double x[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = 1.0 + 1e-9 * (threadIdx.x + 13 * c + blockIdx.x);
+    const double a = 1.0000001, b = 1e-12;
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = fma(x[c], a, b);
+    }
+    double r = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r += x[c];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 }  // namespace zk
