@@ -144,6 +144,15 @@ int  zk_prove_product_host(zk_ctx *, const uint64_t *host_tables, uint32_t P, ui
                            const uint64_t claimed_sum[4], zk_transcript *, uint64_t *coeffs, uint64_t *challenges,
                            uint64_t *final_values, uint32_t flags);
 
+/* ---- verifiers: same kernels, transcript replay on the host ----
+ * gkr_sumcheck::verify (sumcheck_gkr_protocol.rs:69-106); host only.  challenges (may be NULL): n_rounds elements. */
+int  zk_verify_product(int field_id, const uint64_t claimed_sum[4], const uint64_t *coeffs, uint32_t n_rounds, uint32_t D,
+                       zk_transcript *, uint64_t *challenges, uint64_t last_claimed_sum[4], int *is_proof_valid);
+/* basic_sumcheck Verifier::verify (verifier.rs:23-71): the final `initial_polynomial.evaluate(&challenges)` and the table
+ * absorb run on the GPU.  *ok = 1 iff the reference would return true. */
+int  zk_verify_basic(zk_ctx *, const zk_table *initial_polynomial, const uint64_t claimed_sum[4], const uint64_t *round_polys,
+                     uint32_t n_rounds, int *ok);
+
 /* ---- circuit + GKR (circuit/src/arithmetic_circuit.rs, gkr/src/gkr_protocol.rs) ----
  * Layers output-first as in the reference; gates of layer i are entries [layer_off[i], layer_off[i+1]) of
  * left/right/out/op (op 0 = Add, 1 = Mul). */
@@ -163,6 +172,11 @@ uint64_t zk_gkr_total_rounds(uint32_t n_layers);   /* sum over layers of 2(i+1) 
 int  zk_gkr_prove(zk_ctx *, const zk_circuit_desc *, const uint64_t *inputs, uint64_t n_inputs,
                   uint64_t *output, uint64_t output_cap, uint64_t *n_output, uint64_t claimed_sum[4],
                   uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges, uint64_t *wb, uint64_t *wc);
+
+/* gkr_protocol::verify (gkr_protocol.rs:146-236) of a proof laid out as zk_gkr_prove writes it */
+int  zk_gkr_verify(zk_ctx *, const zk_circuit_desc *, const uint64_t *output, uint64_t n_output, const uint64_t *layer_claims,
+                   const uint64_t *coeffs, const uint64_t *wb, const uint64_t *wc, const uint64_t *inputs, uint64_t n_inputs,
+                   int *ok);
 
 /* ---- GKR for wide layers: sparse two-phase layer sumcheck over 2^m-entry tables (m = log2 width of the layer below)
  * instead of the reference's dense 2^(3i+2) / 4^(i+1) tables; identical round polynomials on reference-shaped

@@ -74,6 +74,9 @@ SIGNATURES = {
     "zk_prove_basic": (C.c_int, [vp, u64p, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint32]),
     "zk_prove_product_host": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, C.c_uint64, u64p, vp, u64p, u64p, u64p,
                                         C.c_uint32]),
+    "zk_verify_product": (C.c_int, [C.c_int, u64p, u64p, C.c_uint32, C.c_uint32, vp, u64p, u64p, C.POINTER(C.c_int)]),
+    "zk_verify_basic": (C.c_int, [vp, vp, u64p, u64p, C.c_uint32, C.POINTER(C.c_int)]),
+    "zk_gkr_verify": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, u64p, u64p, u64p, u64p, C.c_uint64, C.POINTER(C.c_int)]),
     "zk_circuit_evaluate": (C.c_int, [C.c_int, vp, u64p, C.c_uint64, u64p, u64p, C.c_uint64]),
     "zk_gkr_total_rounds": (C.c_uint64, [C.c_uint32]),
     "zk_gkr_prove": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p]),

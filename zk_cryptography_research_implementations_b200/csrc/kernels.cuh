@@ -17,7 +17,10 @@ namespace zk {
 
 constexpr int kMaxTables = 8;   // P * D
 constexpr int kMaxEvals = 5;    // D + 1
-constexpr int kThreads = 256;
+#ifndef ZK_THREADS
+#define ZK_THREADS 256
+#endif
+constexpr int kThreads = ZK_THREADS;   // threads per block of every kernel
 
 struct TablePtrs {
     Fe* t[kMaxTables];

@@ -48,6 +48,22 @@ def prove(ctx: Context, circuit: Circuit, inputs) -> Proof:      # gkr_protocol.
     return Proof(output[: n_out.value].copy(), claimed, proofs, wb[: L - 1].copy(), wc[: L - 1].copy())
 
 
+def verify(ctx: Context, circuit: Circuit, proof: Proof, inputs) -> bool:      # gkr_protocol.rs:146-236
+    lib = ctx.lib
+    inputs = as_elems(inputs).reshape(-1, 4)
+    L = len(circuit.layers)
+    out = np.ascontiguousarray(as_elems(proof.circuit_output).reshape(-1, 4))
+    claims = np.ascontiguousarray(np.stack([sp.claimed_sum for sp in proof.sumcheck_proofs]))
+    coeffs = np.ascontiguousarray(np.concatenate([np.stack([p.coefficients for p in sp.round_univariate_polynomials])
+                                                  for sp in proof.sumcheck_proofs]))
+    wb = np.ascontiguousarray(np.concatenate([as_elems(proof.wb_evaluations).reshape(-1, 4), np.zeros((1, 4), dtype=np.uint64)]))
+    wc = np.ascontiguousarray(np.concatenate([as_elems(proof.wc_evaluations).reshape(-1, 4), np.zeros((1, 4), dtype=np.uint64)]))
+    ok = C.c_int(0)
+    ctx.check(lib.zk_gkr_verify(ctx.h, C.byref(circuit.desc), _ptr(out), out.shape[0], _ptr(claims), _ptr(coeffs), _ptr(wb), _ptr(wc),
+                                _ptr(inputs), inputs.shape[0], C.byref(ok)))
+    return bool(ok.value)
+
+
 class WideCircuit:
     """A layered circuit with explicit layer widths, resident on the GPU (three CSR orderings of every layer's
     gates) for the sparse two-phase layer prover (csrc/gkr_wide.cu).  layer_bits[li] = log2(#values of layer li),

@@ -1,10 +1,8 @@
 """`sumcheck_protocol` crate mirror: the two provers, running on the GPU.
 
   basic_sumcheck.prover      sumcheck_protocol/src/basic_sumcheck/prover.rs
-  gkr_sumcheck               sumcheck_protocol/src/gkr_sumcheck/sumcheck_gkr_protocol.rs
-
-The verifiers are out of scope; tests verify our proofs with the oracle's
-restatement of the reference verifier.
+  basic_sumcheck.verifier    sumcheck_protocol/src/basic_sumcheck/verifier.rs
+  gkr_sumcheck               sumcheck_protocol/src/gkr_sumcheck/sumcheck_gkr_protocol.rs (prove and verify)
 """
 from __future__ import annotations
 
@@ -65,6 +63,31 @@ class Prover:
         return SumcheckProof(self.initial_polynomial.copy(), claimed, rounds[:n], chal[:n], fin)
 
 
+class Verifier:
+    """`Verifier<F>` (verifier.rs:8-12)."""
+
+    def __init__(self):
+        self.is_initialized = False
+
+    @classmethod
+    def init(cls, ctx: Context) -> "Verifier":                              # verifier.rs:15-21
+        self = cls()
+        self.ctx = ctx
+        self.is_initialized = True
+        return self
+
+    def verify(self, proof: SumcheckProof) -> bool:                         # verifier.rs:23-71
+        if not self.is_initialized:
+            raise ReferencePanic("Can't verify without init")
+        ctx = self.ctx
+        table = ctx.upload(as_elems(proof.initial_polynomial).reshape(-1, 4))
+        rp = np.ascontiguousarray(as_elems(proof.round_univariate_polynomials).reshape(-1, 2, 4))
+        ok = C.c_int(0)
+        ctx.check(ctx.lib.zk_verify_basic(ctx.h, table.h, _ptr(as_elems(proof.initial_claimed_sum)),
+                                          _ptr(rp) if rp.size else None, rp.shape[0], C.byref(ok)))
+        return bool(ok.value)
+
+
 def split_polynomial_and_sum_each(ctx: Context, polynomial_evaluated_values) -> np.ndarray:   # prover.rs:74-89
     t = ctx.upload(as_elems(polynomial_evaluated_values).reshape(-1, 4))
     out = np.zeros((2, 4), dtype=np.uint64)
@@ -115,6 +138,33 @@ def prove(sum_polynomial: SumPolynomial, claimed_sum, transcript: Transcript, fl
         ctx.lib.zk_sumpoly_free(ctx.h, sp)
     polys = [DenseUnivariatePolynomial(ctx.field, coeffs[k]) for k in range(n)]
     return SumcheckProverProof(claimed, polys, chal[:n], fin)
+
+
+@dataclass
+class SumcheckVerifierProof:
+    """`SumcheckVerifierProof<F>` (sumcheck_gkr_protocol.rs:15-20)."""
+    is_proof_valid: bool
+    random_challenges: np.ndarray
+    last_claimed_sum: np.ndarray
+
+
+def verify(field: int, proof: SumcheckProverProof, transcript: Transcript) -> SumcheckVerifierProof:
+    """`verify` (sumcheck_gkr_protocol.rs:69-106)"""
+    lib = _lib.load()
+    polys = proof.round_univariate_polynomials
+    n = len(polys)
+    D = (polys[0].coefficients.shape[0] - 1) if n else 2
+    coeffs = np.ascontiguousarray(np.stack([p.coefficients for p in polys])) if n else np.zeros((1, D + 1, 4), dtype=np.uint64)
+    chal = np.zeros((max(n, 1), 4), dtype=np.uint64)
+    last = np.zeros(4, dtype=np.uint64)
+    ok = C.c_int(0)
+    rc = lib.zk_verify_product(field, _ptr(as_elems(proof.claimed_sum)), _ptr(coeffs), n, D, transcript.h, _ptr(chal), _ptr(last),
+                               C.byref(ok))
+    if rc:
+        raise ValueError("zk_verify_product failed (%d)" % rc)
+    if not ok.value:
+        return SumcheckVerifierProof(False, np.zeros((0, 4), dtype=np.uint64), last)     # :85-89 `random_challenges: vec![]`
+    return SumcheckVerifierProof(True, chal[:n], last)
 
 
 def univariate_to_bytes(field: int, univariate_poly) -> bytes:      # sumcheck_gkr_protocol.rs:145-150 (little-endian)
