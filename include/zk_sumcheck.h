@@ -216,7 +216,8 @@ int  zk_prove_product_sharded(zk_ctx *, zk_sumpoly *sp, const uint64_t claimed_s
 int  zk_mle_evaluate_sharded(zk_ctx *, const zk_table *local, const uint64_t *values, uint32_t n_values, uint64_t out[4]);
 
 /* ---- measurement: register-resident field arithmetic, no memory traffic (the IMAD-pipe ceiling) ----
- * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate, 3: FP64 FMA. */
+ * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate, 3: FP64 FMA,
+ * 4: IMAD.WIDE.U32, 5: 32-bit IMAD, 6: carry-chained IMAD.WIDE.U32.X (raw pipe rates). */
 int  zk_arith_probe(zk_ctx *, int kind, uint32_t iters, int blocks_per_sm, double *ops_per_s, double *ms);
 
 #ifdef __cplusplus

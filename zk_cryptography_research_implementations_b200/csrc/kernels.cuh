@@ -26,6 +26,10 @@ struct TablePtrs {
     Fe* t[kMaxTables];
 };
 
+template <int FID> __device__ __forceinline__ void fold_by_scalar(Fe& out, const Fe& lo, const Fe& hi, const FoldTable& ft) {
+    FoldScalar<FID>::fold(out, lo, hi, ft);
+}
+
 // ---------------------------------------------------------------- 256-bit global access
 __device__ __forceinline__ Fe ld256(const Fe* p) {
     Fe r;
@@ -283,8 +287,8 @@ __global__ void __launch_bounds__(kThreads, (P * D + NLIN <= 3 && D <= 2) ? ZK_F
         for (int t = 0; t < T; ++t) {
             Fe a0 = ld256(tp.t[t] + j), a1 = ld256(tp.t[t] + j + q);
             Fe a2 = ld256(tp.t[t] + j + 2 * q), a3 = ld256(tp.t[t] + j + 3 * q);
-            FoldScalar<FID>::fold(lo[t], a0, a2, ft);
-            FoldScalar<FID>::fold(hi[t], a1, a3, ft);
+            fold_by_scalar<FID>(lo[t], a0, a2, ft);
+            fold_by_scalar<FID>(hi[t], a1, a3, ft);
             st256(tp.t[t] + j, lo[t]);
             st256(tp.t[t] + j + q, hi[t]);
         }
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(kThreads)
         Fe* tab = tp.t[t];
         for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
             Fe a0 = ld256(tab + j), a1 = ld256(tab + j + half), o;
-            FoldScalar<FID>::fold(o, a0, a1, ft);
+            fold_by_scalar<FID>(o, a0, a1, ft);
             st256(tab + j, o);
         }
     }
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(kThreads)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
         uint64_t j = ((i & ~low_mask) << 1) | (i & low_mask);
         Fe a0 = ld256(in + j), a1 = ld256(in + (j | (1ull << power))), o;
-        FoldScalar<FID>::fold(o, a0, a1, ft);
+        fold_by_scalar<FID>(o, a0, a1, ft);
         st256(out + i, o);
     }
 }
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(kThreads)
         for (int lvl = 0; lvl < K; ++lvl) {
             const int h = 1 << (K - 1 - lvl);
 #pragma unroll
-            for (int c = 0; c < h; ++c) FoldScalar<FID>::fold(v[c], v[c], v[c + h], fts.t[lvl]);
+            for (int c = 0; c < h; ++c) fold_by_scalar<FID>(v[c], v[c], v[c + h], fts.t[lvl]);
         }
         st256(out + j, v[0]);
     }
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(kThreads) arith_probe_kernel(Fe* out, uint32_t
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (KIND == 0) Fp<FID>::mont_mul(x[c], x[c], y[c]);
-            else if (KIND == 1) FoldScalar<FID>::fold(x[c], x[c], y[c], ft);
+            else if (KIND == 1) fold_by_scalar<FID>(x[c], x[c], y[c], ft);
             else { Fp<FID>::mul_acc(acc[c], x[c], y[c]); x[c].v[0] ^= acc[c][16]; }
         }
     }
@@ -516,6 +520,38 @@ template <int UNUSED = 0> __global__ void __launch_bounds__(kThreads) dfma_probe
     double r = 0;
 #pragma unroll
     for (int c = 0; c < 8; ++c) r += x[c];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// integer-multiply pipe probes (kinds 4, 5, 6 of zk_arith_probe): 8 independent chains per thread of
+//   4: mad.wide.u32 (IMAD.WIDE.U32, 64-bit accumulate, no carry flag)
+//   5: mad.lo.u32   (IMAD, 32-bit)
+//   6: mad.lo.cc / madc.hi.cc pairs (IMAD.WIDE.U32.X, carry chained) -- what fp.cuh emits
+template <int KIND> __global__ void __launch_bounds__(kThreads) imad_probe_kernel(uint64_t* out, uint32_t iters) {
+    uint64_t acc[8];
+    uint32_t a[8], b = threadIdx.x * 2654435761u + 12345u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { acc[c] = blockIdx.x + c; a[c] = threadIdx.x * 40503u + 977u * c + 1u; }
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (KIND == 4) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a[c]), "r"(b));
+            } else if (KIND == 5) {
+                uint32_t lo = (uint32_t)acc[c];
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a[c]), "r"(b));
+                acc[c] = lo;
+            } else {
+                uint32_t lo = (uint32_t)acc[c], hi = (uint32_t)(acc[c] >> 32);
+                if (c == 0) ptx::mad_wide_cc(lo, hi, a[c], b);
+                else ptx::madc_wide_cc(lo, hi, a[c], b);
+                acc[c] = ((uint64_t)hi << 32) | lo;
+            }
+        }
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r += acc[c] * (2 * c + 1);
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
