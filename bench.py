@@ -531,8 +531,8 @@ def run_ours(args, wl):
                                                 _ptr(fin), 2))
         else:
             tr = Transcript()
-            ctx.check(lib.zk_prove_product_sharded(ctx.h, sp, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(chal), _ptr(fin), 0,
-                                                   args.collapse_len))
+            ctx.check(lib.zk_prove_product_sharded(ctx.h, sp, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(chal), _ptr(fin),
+                                                   4 if args.nccl_exchange else 0, args.collapse_len))
 
     if D == 1 and world > 1:
         raise SystemExit("plain24 is a single-GPU workload (its transcript absorbs the whole table on the host)")
@@ -644,6 +644,8 @@ def run_ours(args, wl):
             "vs_baseline": None, "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
             "config": config_dict(args.workload, wl, log2, world),
             "roofline": roofline, "integer_roofline": integer, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "exchange": (None if world == 1 else ("ncclAllGather per round" if args.nccl_exchange else
+                                                   "shared-memory mailboxes written by the round kernels (no per-round collective)")),
             "clocks": clocks, "proof_digest": proof_digest,
         }
         if D == 1:
@@ -669,6 +671,8 @@ def main():
     ap.add_argument("--cpu-log2", type=int, default=21, dest="cpu_log2", help="size of the CPU baseline sample")
     ap.add_argument("--cpu-depth", type=int, default=7, dest="cpu_depth", help="circuit depth of the CPU GKR baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
+    ap.add_argument("--nccl-exchange", action="store_true", dest="nccl_exchange",
+                    help="per-round partial exchange with ncclAllGather instead of the shared-memory mailboxes")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-probe", action="store_true")

@@ -15,6 +15,9 @@
 
 namespace zk {
 
+#ifndef ZK_TWO_BLOCK_TABLES
+#define ZK_TWO_BLOCK_TABLES 4   // up to this many tables the round kernels are compiled for two resident blocks per SM
+#endif
 constexpr int kMaxTables = 8;   // P * D
 constexpr int kMaxEvals = 5;    // D + 1
 #ifndef ZK_THREADS
@@ -232,7 +235,7 @@ template <int FID, int P, int D, bool SKIP1, int NLIN = 0> struct RoundAcc {
 
 // Round 0: evaluations only.  half = N/2 pairs (j, j + half).
 template <int FID, int P, int D, int NLIN = 0>
-__global__ void __launch_bounds__(kThreads) round_evals_kernel(TablePtrs tp, uint64_t half, ReduceScratch rs) {
+__global__ void __launch_bounds__(kThreads, (P * D + NLIN <= ZK_TWO_BLOCK_TABLES && D <= 2) ? 2 : 1) round_evals_kernel(TablePtrs tp, uint64_t half, ReduceScratch rs) {
     constexpr int T = P * D + NLIN;
     RoundAcc<FID, P, D, false, NLIN> ra;
     ra.init();
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) round_evals_kernel(TablePtrs tp, uin
 #define ZK_PREFETCH_DIST 1
 #endif
 template <int FID, int P, int D, bool SKIP1, int NLIN = 0>
-__global__ void __launch_bounds__(kThreads, (P * D + NLIN <= 3 && D <= 2) ? ZK_FOLD_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(kThreads, (P * D + NLIN <= ZK_TWO_BLOCK_TABLES && D <= 2) ? ZK_FOLD_MIN_BLOCKS : 1)
     fold_evals_kernel(TablePtrs tp, uint64_t q, const __grid_constant__ FoldTable ft, ReduceScratch rs) {
     constexpr int T = P * D + NLIN;
     RoundAcc<FID, P, D, SKIP1, NLIN> ra;
