@@ -39,6 +39,7 @@ WORKLOADS = {
     # name: (field id, field name, P, D, default log2 N, description)
     "product30": (0, "BN254_FQ", 1, 2, 30, "degree-2 product sumcheck f*g (BASELINE.json configs[2])"),
     "plain24": (2, "BLS12_381_FR", 1, 1, 24, "plain sumcheck of one MLE (BASELINE.json configs[1])"),
+    "plain32": (2, "BLS12_381_FR", 1, 1, 32, "plain sumcheck of one 2^32-entry MLE (128 GiB), rounds only -- the upper end of BASELINE's 2^24-2^32 range"),
     "gkr22": (0, "BN254_FQ", 2, 2, 22, "GKR-shaped 2x2 sumcheck add*(Wb+Wc)+mul*(Wb*Wc) tables"),
     # --log2 = log2 of the layer width; 16 layers of 2^log2 gates, sparse two-phase layer prover
     "gkr_wide": (0, "BN254_FQ", 2, 2, 22, "GKR prove of a synthetic layered add/mul circuit, depth 16, width 2^22 gates (BASELINE.json configs[3])"),
@@ -383,6 +384,10 @@ def run_mle(args, wl):
             "roofline": {"bound": "hbm", "achieved": ach_eval, "peak": hbm_peak, "unit": "GB/s", "frac": ach_eval / hbm_peak, "traffic": None,
                          "peak_source": peak_src, "kernel": "fold_multi_kernel<%s,3> passes (algorithmic bytes = 32 N: one read)" % fname,
                          "note": "timed around the whole evaluate call (n/3 passes + host fold tables)"},
+            "integer_roofline": {"folds_per_evaluate": N - 1, "imad_wide_per_fold": 84,
+                                 "note": "evaluate is bound by the integer-multiply pipe, not HBM: (N-1) folds x 84 IMAD.WIDE against 32 N bytes; "
+                                         "at the probe's 8.86e12 IMAD.WIDE/s per GPU the floor is %.2f ms (HBM floor %.2f ms) -> %.2f of the slower roofline"
+                                         % ((m - 1) * 84 / 8.86e12 * 1e3, 32.0 * m / (hbm_peak * 1e9) * 1e3, ((m - 1) * 84 / 8.86e12 * 1e3) / ms_eval)},
             "partial_evaluate": {"ms": ms_fold, "elements_per_s": N / (ms_fold * 1e-3), "achieved_GBps": ach_fold, "frac": ach_fold / hbm_peak,
                                  "kernel": "fold0_kernel (read N, write N/2: 48 N bytes)"},
             "cpu_baseline": cpu, "e2e": None, "gpu_launches": launches, "clocks": clocks,
@@ -527,15 +532,20 @@ def run_ours(args, wl):
         if D == 1:
             # plain sumcheck rounds; the 32*N-byte Keccak absorb of the table is host transcript work,
             # reported separately (absorb_ms) and included in e2e
-            ctx.check(lib.zk_prove_basic_device(ctx.h, lib.zk_sumpoly_table(sp, 0), _ptr(claimed), _ptr(rpolys), _ptr(chal),
-                                                _ptr(fin), 2))
+            if world > 1:
+                tr = Transcript()
+                ctx.check(lib.zk_prove_basic_sharded(ctx.h, lib.zk_sumpoly_table(sp, 0), tr.h, _ptr(claimed), _ptr(rpolys), _ptr(chal),
+                                                     _ptr(fin), 4 if args.nccl_exchange else 0, args.collapse_len))
+            else:
+                ctx.check(lib.zk_prove_basic_device(ctx.h, lib.zk_sumpoly_table(sp, 0), _ptr(claimed), _ptr(rpolys), _ptr(chal),
+                                                    _ptr(fin), 2))
         else:
             tr = Transcript()
             ctx.check(lib.zk_prove_product_sharded(ctx.h, sp, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(chal), _ptr(fin),
                                                    4 if args.nccl_exchange else 0, args.collapse_len))
 
     if D == 1 and world > 1:
-        raise SystemExit("plain24 is a single-GPU workload (its transcript absorbs the whole table on the host)")
+        args.no_e2e = True   # the end-to-end plain prove absorbs the whole table through one host sponge: single-GPU only
 
     def timed_steps(fn, prep, steps, warmup, profile):
         for _ in range(warmup):

@@ -212,6 +212,10 @@ int  zk_comm_world(const zk_ctx *);
 int  zk_prove_product_sharded(zk_ctx *, zk_sumpoly *sp, const uint64_t claimed_sum[4], zk_transcript *,
                               uint64_t *coeffs, uint64_t *challenges, uint64_t *final_values, uint32_t flags,
                               uint64_t collapse_len);
+/* basic_sumcheck Prover::prove over a sharded table (any world size).  The whole-table absorb of prover.rs:38-39 is the
+ * caller's: every rank passes an identical transcript that has already absorbed it (or deliberately has not). */
+int  zk_prove_basic_sharded(zk_ctx *, zk_table *local, zk_transcript *, uint64_t claimed_sum[4], uint64_t *round_polys,
+                            uint64_t *challenges, uint64_t final_value[4], uint32_t flags, uint64_t collapse_len);
 /* MultilinearPolynomial::evaluate over a sharded table (values: all log2(global length) challenges) */
 int  zk_mle_evaluate_sharded(zk_ctx *, const zk_table *local, const uint64_t *values, uint32_t n_values, uint64_t out[4]);
 

@@ -1,0 +1,40 @@
+"""bench.py's reference arm runs on the CPU (it times the oracle's restatement of the reference prover): check the JSON
+contract of that line here; the GPU arm's line is checked on the B200 (tests/test_gpu_bench_contract.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config"}
+
+
+def run_bench(*args, timeout=600):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("workload,extra", [("product30", ["--cpu-log2", "10"]), ("plain24", ["--cpu-log2", "10"]),
+                                            ("gkr", ["--cpu-depth", "3"]), ("mle", ["--cpu-log2", "10"])])
+def test_reference_arm_line(workload, extra):
+    d = run_bench("--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0", *extra)
+    assert BASE_KEYS <= set(d)
+    assert d["impl"] == "reference" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                          "--cpu-log2", "8"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""

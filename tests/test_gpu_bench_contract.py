@@ -1,0 +1,29 @@
+"""The GPU arm of bench.py at a small size: one JSON line with every key of the contract."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_arm_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--log2", "20", "--steps", "2", "--warmup", "3", "--cpu-log2", "12",
+                          "--e2e-steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["vs_baseline"] is None
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * (1 << 20) * 32 and d["e2e"]["value"] > 0 and d["e2e"]["value"] != d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["gpu_launches"] > 0

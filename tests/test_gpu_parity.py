@@ -365,3 +365,21 @@ def test_large_basic_sumcheck_properties(zk, co, ctx_for, fid, n):
     # spot-check convert_to_bytes against the oracle on a slice
     sl = orig.evaluated_values[:1024]
     assert orig.convert_to_bytes()[:32 * 1024] == co.mle_to_bytes(fid, sl)
+
+
+def test_basic_sharded_entry_point_world_1(zk, co, ctx_for):
+    """zk_prove_basic_sharded with a single rank == the reference proof when the caller absorbs the table"""
+    from zk_cryptography_research_implementations_b200.core import _ptr
+    from zk_cryptography_research_implementations_b200.transcripts import Transcript
+    fid = 2
+    ctx = ctx_for(fid)
+    for n in (0, 1, 5, 12):
+        T = rand_table(co, fid, 1 << n, 900 + n)
+        claimed_w, rp_w, ch_w, fin_w = co.basic_prove(fid, T)
+        t = ctx.upload(T)
+        tr = Transcript()
+        tr.append(co.mle_to_bytes(fid, T))
+        claimed = np.zeros(4, dtype=np.uint64); rp = np.zeros((max(n, 1), 2, 4), dtype=np.uint64)
+        ch = np.zeros((max(n, 1), 4), dtype=np.uint64); fin = np.zeros(4, dtype=np.uint64)
+        ctx.check(ctx.lib.zk_prove_basic_sharded(ctx.h, t.h, tr.h, _ptr(claimed), _ptr(rp), _ptr(ch), _ptr(fin), 0, 1))
+        assert np.array_equal(claimed, claimed_w) and np.array_equal(rp[:n], rp_w) and np.array_equal(ch[:n], ch_w) and np.array_equal(fin, fin_w)

@@ -68,6 +68,18 @@ def _worker(rank, world, port, q):
             out = np.zeros(4, dtype=np.uint64)
             ctx.check(ctx.lib.zk_mle_evaluate_sharded(ctx.h, local.h, _ptr(np.ascontiguousarray(want[1])), n, _ptr(out)))
             ok &= np.array_equal(out, co.mle_evaluate(fid, full[0, 0], want[1]))
+        # plain sumcheck over a sharded table: the caller absorbs the table, the rest must equal the reference proof
+        for (n, collapse) in [(11, 1), (13, 128)]:
+            N = 1 << n
+            full = np.array(zk.fe_from_ints(fid, zk.synthetic_table_ints(fid, 6, 0, N)))
+            claimed_w, rp_w, ch_w, fin_w = co.basic_prove(fid, full)
+            local = ctx.generate(6, 0, N // world, first=rank, step=world)
+            tr = Transcript()
+            tr.append(co.mle_to_bytes(fid, full))
+            claimed = np.zeros(4, dtype=np.uint64); rp = np.zeros((n, 2, 4), dtype=np.uint64)
+            ch = np.zeros((n, 4), dtype=np.uint64); fin = np.zeros(4, dtype=np.uint64)
+            ctx.check(ctx.lib.zk_prove_basic_sharded(ctx.h, local.h, tr.h, _ptr(claimed), _ptr(rp), _ptr(ch), _ptr(fin), 0, collapse))
+            ok &= np.array_equal(claimed, claimed_w) and np.array_equal(rp, rp_w) and np.array_equal(ch, ch_w) and np.array_equal(fin, fin_w)
         q.put((rank, bool(ok)))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

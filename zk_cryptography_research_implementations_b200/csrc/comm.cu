@@ -295,6 +295,84 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
     return ZK_OK;
 }
 
+// basic_sumcheck Prover::prove (prover.rs:35-71) over a table sharded across the ranks (world 1: the whole table).
+// The reference first absorbs the whole polynomial (prover.rs:38-39); with the table spread over several GPUs that
+// absorb is the caller's: `tr` arrives with the table bytes already absorbed (every rank must pass an identical
+// transcript).  From there on: claimed sum, n rounds of [sum left, sum right] -> absorb (big-endian) -> challenge ->
+// fold, exactly as the single-GPU prover; identical outputs on every rank.
+extern "C" int zk_prove_basic_sharded(zk_ctx* ctx, zk_table* local, zk_transcript* tr, uint64_t claimed_sum[4],
+                                      uint64_t* round_polys, uint64_t* challenges, uint64_t final_value[4], uint32_t flags,
+                                      uint64_t collapse_len) {
+    if (ctx->world > 1 && !ctx->nccl_comm) return fail(ctx, ZK_ERR_ARG, "zk_comm_init has not been called");
+    if (!is_pow2(local->len)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
+    if (collapse_len < 1) collapse_len = 1;
+    const HostField& f = ctx->field;
+    const int G = ctx->world;
+    const uint32_t n = ilog2(local->len) + ilog2((uint64_t)G);
+    zk_sumpoly sp;   // a one-table view so that the shared helpers (collapse, set_len) apply
+    sp.P = 1;
+    sp.D = 1;
+    sp.len = local->len;
+    sp.tabs.assign(1, local);
+    HFe evals[2], r = f.zero();
+    bool sharded = G > 1;
+    if (n == 0) {
+        ZK_CUDA(cudaMemcpyAsync(claimed_sum, local->d, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        HFe c;
+        memcpy(c.l, claimed_sum, 32);
+        tr->t.append_be(f, c);
+        if (final_value) memcpy(final_value, claimed_sum, 32);
+        return ZK_OK;
+    }
+    for (uint32_t k = 0; k < n; ++k) {
+        int rc;
+        bool plain = (k == 0);
+        if (k > 0 && sharded && sp.len / 2 <= collapse_len) {
+            rc = launch_fold0(ctx, ptrs_of(&sp), 1, sp.len, make_fold_table(f, r));
+            if (rc) return rc;
+            set_len(&sp, sp.len / 2);
+            if ((rc = collapse(ctx, &sp))) return rc;
+            sharded = false;
+            plain = true;
+        }
+        if (k == 0 && sharded && sp.len <= collapse_len) {
+            if ((rc = collapse(ctx, &sp))) return rc;
+            sharded = false;
+        }
+        TablePtrs tp = ptrs_of(&sp);
+        const bool shared = sharded && ctx->xmail_host != nullptr && !(flags & ZK_FLAG_NCCL_EXCHANGE);
+        if (plain) {
+            rc = launch_round_evals(ctx, tp, 1, 1, sp.len, shared);                    // prover.rs:50
+        } else {
+            rc = launch_fold_evals(ctx, tp, 1, 1, sp.len, make_fold_table(f, r), false, shared);   // :61-63 fused with :50
+            set_len(&sp, sp.len / 2);
+        }
+        if (rc) return rc;
+        rc = sharded ? exchange_sum(ctx, evals, 2) : fetch_result(ctx, evals, 2);
+        if (rc) return rc;
+        if (k == 0) {                                                                  // init's claimed sum, prover.rs:28,40-41
+            HFe claimed = f.add(evals[0], evals[1]);
+            memcpy(claimed_sum, claimed.l, 32);
+            tr->t.append_be(f, claimed);
+        }
+        uint8_t bytes[64];
+        f.to_bytes_be(evals[0], bytes);
+        f.to_bytes_be(evals[1], bytes + 32);
+        tr->t.append(bytes, 64);                                                       // :51-55
+        r = tr->t.challenge(f);                                                        // :58
+        memcpy(round_polys + (size_t)k * 8, evals, 64);
+        if (challenges) memcpy(challenges + (size_t)k * 4, r.l, 32);
+    }
+    if (sharded) return fail(ctx, ZK_ERR_ARG, "internal: table still sharded after the last round");
+    int rc = launch_fold0(ctx, ptrs_of(&sp), 1, sp.len, make_fold_table(f, r));
+    if (rc) return rc;
+    set_len(&sp, sp.len / 2);
+    if (final_value) ZK_CUDA(cudaMemcpyAsync(final_value, local->d, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
 // MultilinearPolynomial::evaluate over a sharded table: each rank binds the leading n-g variables of
 // its shard (no communication), the G survivors are gathered and the last g variables are bound on
 // the host.  `values` holds all n challenges; every rank returns the same element.
