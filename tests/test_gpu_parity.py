@@ -383,3 +383,26 @@ def test_basic_sharded_entry_point_world_1(zk, co, ctx_for):
         ch = np.zeros((max(n, 1), 4), dtype=np.uint64); fin = np.zeros(4, dtype=np.uint64)
         ctx.check(ctx.lib.zk_prove_basic_sharded(ctx.h, t.h, tr.h, _ptr(claimed), _ptr(rp), _ptr(ch), _ptr(fin), 0, 1))
         assert np.array_equal(claimed, claimed_w) and np.array_equal(rp[:n], rp_w) and np.array_equal(ch[:n], ch_w) and np.array_equal(fin, fin_w)
+
+
+def test_degenerate_sizes(zk, co, ctx_for):
+    """one-entry tables: zero rounds (prove returns an empty proof and leaves the transcript with only the claim absorbed)"""
+    from zk_cryptography_research_implementations_b200 import sumcheck_protocol as scp
+    from zk_cryptography_research_implementations_b200.transcripts import Transcript
+    fid = 0
+    ctx = ctx_for(fid)
+    tabs = np.stack([np.stack([rand_table(co, fid, 1, 70 + 2 * p + d, edge=False) for d in range(2)]) for p in range(2)])
+    claimed = np.zeros(4, dtype=np.uint64)
+    co.lib().zko_fe_sum(fid, co._p(co.sumpoly_reduce(fid, tabs)), 1, co._p(claimed))
+    tr_o, tr_g = co.Transcript(), Transcript()
+    coeffs, ch, fin = co.product_prove(fid, tabs, claimed, tr_o)
+    proof = scp.prove(sumpoly_handle(zk, ctx, tabs), claimed, tr_g)
+    assert coeffs.shape[0] == 0 and len(proof.round_univariate_polynomials) == 0 and proof.random_challenges.shape[0] == 0
+    assert np.array_equal(proof.final_values.reshape(2, 2, 4), fin)
+    assert tr_o.sample_random_challenge() == tr_g.sample_random_challenge()
+    # evaluate with no values returns entry 0; partial_evaluate of a one-entry table is the reference's panic
+    from zk_cryptography_research_implementations_b200.polynomials import MultilinearPolynomial as MLE
+    one = MLE.new(ctx, tabs[0, 0])
+    assert np.array_equal(one.evaluate(np.zeros((0, 4), dtype=np.uint64)), tabs[0, 0, 0])
+    with pytest.raises(zk.ReferencePanic):
+        MLE.partial_evaluate(one, 0, tabs[0, 1, 0])

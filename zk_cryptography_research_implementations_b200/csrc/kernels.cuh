@@ -390,18 +390,6 @@ template <int FID> __global__ void __launch_bounds__(kThreads) scale_kernel(cons
         st256(out + i, o);
     }
 }
-// out[i] = alpha * a[i] + beta * b[i]           (gkr/src/utils.rs:59-66)
-template <int FID>
-__global__ void __launch_bounds__(kThreads) axpby_kernel(const Fe* a, const Fe* b, Fe* out, uint64_t n, Fe alpha, Fe beta) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Fe x = ld256(a + i), y = ld256(b + i), u, v, o;
-        Fp<FID>::mont_mul(u, x, alpha);
-        Fp<FID>::mont_mul(v, y, beta);
-        Fp<FID>::add(o, u, v);
-        st256(out + i, o);
-    }
-}
 // SumPolynomial::add_polynomials_element_wise (sum_polynomial.rs:57-76): out[i] = sum_p prod_d t[p][d][i]
 template <int FID> __global__ void __launch_bounds__(kThreads) sumpoly_reduce_kernel(TablePtrs tp, int P, int D, Fe* out, uint64_t n) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
