@@ -32,8 +32,13 @@ enum {
     ZK_FLAG_SKIP_ABSORB = 2,   /* zk_prove_basic*: the caller already absorbed the table bytes */
     ZK_FLAG_NO_CLAIM_ABSORB = 8, /* zk_prove_product: do not absorb claimed_sum first (continuation of a sumcheck whose
                                   earlier rounds ran in a previous call -- the two phases of a sparse GKR layer) */
-    ZK_FLAG_NCCL_EXCHANGE = 4  /* sharded provers: exchange the per-round partials with ncclAllGather even if the
+    ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
+    ZK_FLAG_HOST_ROUNDS = 16   /* keep every round on the host-driven path: one kernel + one host Fiat-Shamir step per
+                                  round.  Default: once the tables are down to 2^tail_log entries (zk_ctx_set_tail_log,
+                                  default 13) ONE single-block launch runs all remaining rounds with the transcript on the
+                                  device (transcripts/.../fiat_shamir_transcript.rs:12-43 restated in csrc/dev_transcript.cuh);
+                                  the proof is identical either way */
 };
 
 typedef struct zk_ctx zk_ctx;
@@ -55,6 +60,12 @@ int  zk_ctx_synchronize(zk_ctx *);
 int  zk_ctx_set_profiling(zk_ctx *, int on);
 int  zk_ctx_reset_stats(zk_ctx *);
 int  zk_ctx_get_stats(zk_ctx *, uint64_t *launches, uint64_t *round_launches, double *round_ms, double *round_bytes);
+/* Device tail: a sumcheck whose tables hold at most 2^tail_log entries finishes in ONE single-block launch that runs
+ * every remaining round -- sums, fold, Lagrange coefficients (dense_univariate.rs:74-127), transcript absorb and
+ * challenge (fiat_shamir_transcript.rs:22-43) -- on the GPU.  Default 13 (env ZKB200_TAIL_LOG); 0 keeps every round
+ * host-driven; at most 16.  Proofs are bit-identical for every setting. */
+int  zk_ctx_set_tail_log(zk_ctx *, int tail_log);
+int  zk_ctx_get_tail_log(const zk_ctx *);
 
 /* ---- field helpers on the host (ark-ff: F::from(u64), into_bigint, from_le_bytes_mod_order) ---- */
 int  zk_fe_from_u64(int field_id, uint64_t v, uint64_t out[4]);

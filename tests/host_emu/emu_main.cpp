@@ -5,6 +5,9 @@
 #include <cstring>
 #include <vector>
 #include "fp.cuh"
+#include "round_acc.cuh"
+#include "tail.cuh"
+#include "host_field.h"
 #include "../../oracle/zkoracle.h"
 
 static uint64_t rng_state = 0x1234567ull;
@@ -85,7 +88,277 @@ template <int FID> static int run() {
     return bad;
 }
 
+// RoundAcc (round_acc.cuh): several "threads" accumulate pairs, their 32-bit columns are summed as exact
+// 64-bit integers (what the kernels' REDUX / RED stages do) and finalize() must return the reference's
+// generate_round_univariate evaluations (oracle: zko_generate_round_univariate on the same tables).
+template <int FID, int P, int D, bool SKIP1, int NLIN> static int run_round_acc(int n_threads, int pairs_per_thread, int edge) {
+    typedef zk::RoundAcc<FID, P, D, SKIP1, NLIN> RA;
+    constexpr int T = P * D + NLIN;
+    const uint64_t half = (uint64_t)n_threads * pairs_per_thread, len = 2 * half;   // must be a power of two
+    // oracle layout: P' products of D factors; a linear table l enters as the product (l, ones, ones...)
+    constexpr int PO = P + NLIN;
+    std::vector<uint64_t> tabs((size_t)PO * D * len * 4);
+    uint64_t one[4]; zko_fe_from_u64(FID, 1, one);
+    for (int p = 0; p < PO; ++p)
+        for (int d = 0; d < D; ++d)
+            for (uint64_t i = 0; i < len; ++i) {
+                uint64_t* dst = &tabs[(((size_t)p * D + d) * len + i) * 4];
+                if (p >= P && d > 0) memcpy(dst, one, 32);
+                else rand_fe(FID, dst, edge ? (int)(rnd() % 6) : 0);
+            }
+    std::vector<unsigned long long> tot(RA::NC, 0);
+    for (int th = 0; th < n_threads; ++th) {
+        RA ra; ra.init();
+        for (int it = 0; it < pairs_per_thread; ++it) {
+            uint64_t j = (uint64_t)it * n_threads + th;
+            zk::Fe lo[T], hi[T];
+            for (int t = 0; t < T; ++t) {
+                // table t of the kernel: products first, then the linear tables
+                int p = t < P * D ? t / D : P + (t - P * D), d = t < P * D ? t % D : 0;
+                const uint64_t* base = &tabs[(((size_t)p * D + d) * len) * 4];
+                lo[t] = to_fe(base + j * 4); hi[t] = to_fe(base + (j + half) * 4);
+            }
+            ra.add_pair(lo, hi);
+        }
+        uint32_t col[RA::NC]; ra.columns(col);
+        for (int c = 0; c < RA::NC; ++c) tot[c] += col[c];
+    }
+    std::vector<uint64_t> want((D + 1) * 4);
+    zko_generate_round_univariate(FID, tabs.data(), PO, D, len, want.data());
+    int bad = 0;
+    for (int e = 0; e <= D; ++e) {
+        if (SKIP1 && e == 1) continue;
+        zk::Fe out; RA::finalize(out, e, tot.data());
+        if (!eq(out, &want[4 * e])) { ++bad; printf("RoundAcc<%d,%d,%d,%d,%d> eval %d mismatch\n", FID, P, D, (int)SKIP1, NLIN, e); }
+    }
+    return bad;
+}
+template <int FID> static int run_round_accs() {
+    int bad = 0;
+    for (int edge = 0; edge < 2; ++edge) {
+        bad += run_round_acc<FID, 1, 1, false, 0>(8, 4, edge);
+        bad += run_round_acc<FID, 1, 2, false, 0>(4, 4, edge);
+        bad += run_round_acc<FID, 1, 2, true, 0>(256, 2, edge);
+        bad += run_round_acc<FID, 2, 2, false, 0>(4, 4, edge);
+        bad += run_round_acc<FID, 1, 2, false, 1>(8, 2, edge);
+        bad += run_round_acc<FID, 1, 2, true, 1>(1, 1, edge);
+        bad += run_round_acc<FID, 2, 3, false, 0>(4, 2, edge);
+        bad += run_round_acc<FID, 4, 2, true, 0>(2, 2, edge);
+    }
+    printf("round_acc field %d: %s\n", FID, bad ? "FAIL" : "ok");
+    return bad;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The device transcript and the whole tail body (tail.cuh) under a one-thread host policy, against the oracle.
+struct HostExec {
+    int tid() const { return 0; }
+    int nthreads() const { return 1; }
+    void sync() const {}
+    template <int NC> void column_sums(const uint32_t (&col)[NC], unsigned long long* tot) const { for (int c = 0; c < NC; ++c) tot[c] = col[c]; }
+    zk::Fe load(const zk::Fe* p) const { return *p; }
+    void store(zk::Fe* p, const zk::Fe& v) const { *p = v; }
+    void publish(uint32_t* seq, uint32_t v) const { *seq = v; }
+};
+
+static int test_dev_sponge() {
+    int bad = 0;
+    // byte-wise and word-wise absorbs at every alignment against the oracle's Keccak / transcript
+    for (int prefix = 0; prefix < 300; prefix += (prefix < 20 ? 1 : 37)) {
+        std::vector<uint8_t> data(prefix + 8 * 40);
+        for (auto& b : data) b = (uint8_t)rnd();
+        zk::KeccakState st; memset(&st, 0, sizeof st);
+        zko_transcript* ot = zko_transcript_new();
+        for (int i = 0; i < prefix; ++i) zk::sponge_absorb_byte(&st, data[i]);
+        zko_transcript_append(ot, data.data(), prefix);
+        for (int rep = 0; rep < 5; ++rep) {
+            for (int w = 0; w < 8; ++w) { uint64_t word; memcpy(&word, &data[prefix + 8 * (8 * rep + w)], 8); zk::sponge_absorb_word(&st, word); }
+            zko_transcript_append(ot, &data[prefix + 64 * rep], 64);
+            uint64_t dg[4]; uint8_t want[32];
+            zk::sponge_sample(&st, dg);
+            zko_transcript_sample(ot, want);
+            if (memcmp(dg, want, 32)) { ++bad; printf("device sponge digest mismatch prefix=%d rep=%d\n", prefix, rep); }
+        }
+        // the host transcript of the library takes the state over and continues identically
+        zk::HostTranscript ht; ht.import_state(st.s, st.pos);
+        uint8_t a[32], b[32]; ht.sample(a); zko_transcript_sample(ot, b);
+        if (memcmp(a, b, 32)) { ++bad; printf("state handback mismatch prefix=%d\n", prefix); }
+        zko_transcript_free(ot);
+    }
+    printf("dev_sponge: %s\n", bad ? "FAIL" : "ok");
+    return bad;
+}
+
+static zk::FoldTable host_fold_table(const zk::HostField& f, const zk::HFe& r_mont) {
+    zk::FoldTable ft; zk::HFe cur = f.from_mont(r_mont), m232 = f.from_u64(1ull << 32);
+    for (int i = 0; i < 8; ++i) { memcpy(ft.w[i], cur.l, 32); cur = f.mul(cur, m232); }
+    return ft;
+}
+template <int FID> static void fill_tail_consts(zk::TailArgs& a, const zk::HostField& f, int D) {
+    zk::Interpolator ip(f, D);
+    memcpy(a.interp, ip.matrix(), (size_t)(D + 1) * (D + 1) * 32);
+    zk::HFe cur = f.one(), m232 = f.from_u64(1ull << 32);
+    for (int i = 0; i < 8; ++i) { memcpy(a.pow32[i].v, cur.l, 32); cur = f.mul(cur, m232); }
+}
+
+// product sumcheck: `host_rounds` rounds are run the way the host driver runs them, the rest by the tail body
+template <int FID, int P, int D, int NLIN> static int run_tail_product(int n, int host_rounds, int prefix_bytes) {
+    constexpr int T = P * D + NLIN, PO = P + NLIN + (P + NLIN < 2 ? 1 : 0), NE = D + 1;
+    const uint64_t len = 1ull << n;
+    zk::HostField f(FID);
+    // oracle tables: P products, NLIN products (l, 1, ..), and a 0*0 product when the oracle needs a second one
+    std::vector<uint64_t> ot((size_t)PO * D * len * 4, 0);
+    uint64_t one[4]; zko_fe_from_u64(FID, 1, one);
+    std::vector<std::vector<zk::Fe>> tabs(T, std::vector<zk::Fe>(len));
+    for (int t = 0; t < T; ++t) {
+        int p = t < P * D ? t / D : P + (t - P * D), d = t < P * D ? t % D : 0;
+        for (uint64_t i = 0; i < len; ++i) {
+            uint64_t* dst = &ot[(((size_t)p * D + d) * len + i) * 4];
+            rand_fe(FID, dst, (rnd() % 16 == 0) ? (int)(rnd() % 6) : 0);
+            tabs[t][i] = to_fe(dst);
+        }
+    }
+    for (int l = 0; l < NLIN; ++l)
+        for (int d = 1; d < D; ++d)
+            for (uint64_t i = 0; i < len; ++i) memcpy(&ot[(((size_t)(P + l) * D + d) * len + i) * 4], one, 32);
+    // claimed sum and the oracle proof (transcript pre-loaded with some bytes so the sponge position is odd)
+    std::vector<uint64_t> red(len * 4); uint64_t claim[4];
+    zko_sumpoly_reduce(FID, ot.data(), PO, D, len, red.data()); zko_fe_sum(FID, red.data(), len, claim);
+    std::vector<uint8_t> prefix(prefix_bytes); for (auto& b : prefix) b = (uint8_t)rnd();
+    zko_transcript* otr = zko_transcript_new(); zko_transcript_append(otr, prefix.data(), prefix.size());
+    std::vector<uint64_t> wc((size_t)n * NE * 4), wch((size_t)n * 4), wfin((size_t)PO * D * 4);
+    if (zko_product_prove(FID, ot.data(), PO, D, len, claim, otr, wc.data(), wch.data(), wfin.data())) { printf("oracle refused\n"); return 1; }
+    // the library's side: host transcript + host rounds (oracle pieces stand in for the big kernels), then the tail
+    zk::HostTranscript tr; tr.append(prefix.data(), prefix.size());
+    zk::HFe hclaim; memcpy(hclaim.l, claim, 32); tr.append_be(f, hclaim);
+    zk::Interpolator ip(f, D);
+    int bad = 0;
+    zk::HFe r = f.zero();
+    uint64_t cur_len = len;
+    std::vector<uint64_t> cur_ot = ot;
+    for (int k = 0; k < host_rounds; ++k) {
+        zk::HFe ev[8], co[8];
+        zko_generate_round_univariate(FID, cur_ot.data(), PO, D, cur_len, (uint64_t*)ev);
+        ip.coefficients(ev, co);
+        uint8_t bytes[32 * 8];
+        for (int i = 0; i < NE; ++i) f.to_bytes_le(co[i], bytes + 32 * i);
+        tr.append(bytes, 32 * NE);
+        r = tr.challenge(f);
+        if (memcmp(co, &wc[(size_t)k * NE * 4], 32 * NE) || memcmp(r.l, &wch[(size_t)k * 4], 32)) { ++bad; printf("host round %d mismatch\n", k); }
+        if (k + 1 < host_rounds) {   // fold everything (the last host challenge stays pending for the tail)
+            std::vector<uint64_t> nxt((size_t)PO * D * (cur_len / 2) * 4);
+            for (int t = 0; t < PO * D; ++t)
+                zko_mle_partial_evaluate(FID, &cur_ot[(size_t)t * cur_len * 4], cur_len, 0, r.l, &nxt[(size_t)t * (cur_len / 2) * 4]);
+            cur_ot.swap(nxt); cur_len /= 2;
+        }
+    }
+    // tables as the kernels would hold them at hand-over: length cur_len, fold by r pending (if any host round ran)
+    for (int t = 0; t < T; ++t) {
+        int p = t < P * D ? t / D : P + (t - P * D), d = t < P * D ? t % D : 0;
+        tabs[t].resize(cur_len);
+        for (uint64_t i = 0; i < cur_len; ++i) tabs[t][i] = to_fe(&cur_ot[(((size_t)p * D + d) * cur_len + i) * 4]);
+    }
+    zk::TailArgs a; memset(&a, 0, sizeof a);
+    zk::TailOut out; memset(&out, 0, sizeof out);
+    zk::TailShared sh;
+    for (int t = 0; t < T; ++t) a.tp.t[t] = tabs[t].data();
+    a.log_len = 0; while ((1ull << a.log_len) < cur_len) ++a.log_len;
+    a.pending = host_rounds > 0; a.mode = zk::kTailProduct; a.seq = 77;
+    if (a.pending) a.ft = host_fold_table(f, r);
+    fill_tail_consts<FID>(a, f, D);
+    tr.export_state(a.sponge.s, &a.sponge.pos);
+    a.out = &out;
+    HostExec ex;
+    zk::sumcheck_tail_body<FID, P, D, NLIN>(a, sh, ex);
+    if (out.seq != 77 || (int)out.rounds != n - host_rounds) { ++bad; printf("tail rounds %u (want %d)\n", out.rounds, n - host_rounds); }
+    for (int k = host_rounds; k < n; ++k) {
+        if (memcmp(out.round_vals[k - host_rounds], &wc[(size_t)k * NE * 4], 32 * NE)) { ++bad; printf("tail<%d,%d,%d,%d> n=%d coeffs of round %d mismatch\n", FID, P, D, NLIN, n, k); }
+        if (memcmp(&out.challenges[k - host_rounds], &wch[(size_t)k * 4], 32)) { ++bad; printf("tail challenge of round %d mismatch\n", k); }
+    }
+    for (int t = 0; t < T; ++t) {
+        int p = t < P * D ? t / D : P + (t - P * D), d = t < P * D ? t % D : 0;
+        if (memcmp(&out.finals[t], &wfin[((size_t)p * D + d) * 4], 32) || memcmp(&tabs[t][0], &out.finals[t], 32)) { ++bad; printf("tail final value of table %d mismatch\n", t); }
+    }
+    // the transcript continues on the host exactly where the oracle's is
+    tr.import_state(out.sponge.s, out.sponge.pos);
+    uint8_t d1[32], d2[32]; tr.sample(d1); zko_transcript_sample(otr, d2);
+    if (memcmp(d1, d2, 32)) { ++bad; printf("transcript after the tail differs\n"); }
+    zko_transcript_free(otr);
+    return bad;
+}
+
+// plain sumcheck (basic_sumcheck::Prover): the table absorb and the claimed sum on the host, the rounds in the tail
+template <int FID> static int run_tail_plain(int n, int host_rounds) {
+    const uint64_t len = 1ull << n;
+    zk::HostField f(FID);
+    std::vector<uint64_t> table(len * 4);
+    for (uint64_t i = 0; i < len; ++i) rand_fe(FID, &table[4 * i], (rnd() % 16 == 0) ? (int)(rnd() % 6) : 0);
+    uint64_t claim[4], fin[4];
+    std::vector<uint64_t> rp((size_t)n * 8), ch((size_t)n * 4);
+    if (zko_basic_prove(FID, table.data(), len, claim, rp.data(), ch.data(), fin)) { printf("oracle refused\n"); return 1; }
+    zk::HostTranscript tr;
+    std::vector<uint8_t> bytes(len * 32);
+    zko_mle_to_bytes(FID, table.data(), len, bytes.data());
+    tr.append(bytes.data(), bytes.size());
+    zk::HFe hclaim; memcpy(hclaim.l, claim, 32); tr.append_be(f, hclaim);
+    int bad = 0;
+    zk::HFe r = f.zero();
+    std::vector<uint64_t> cur = table; uint64_t cur_len = len;
+    for (int k = 0; k < host_rounds; ++k) {
+        zk::HFe ev[2]; zko_split_and_sum(FID, cur.data(), cur_len, (uint64_t*)ev);
+        uint8_t b[64]; f.to_bytes_be(ev[0], b); f.to_bytes_be(ev[1], b + 32); tr.append(b, 64);
+        r = tr.challenge(f);
+        if (memcmp(ev, &rp[(size_t)k * 8], 64) || memcmp(r.l, &ch[(size_t)k * 4], 32)) { ++bad; printf("plain host round %d mismatch\n", k); }
+        if (k + 1 < host_rounds) {
+            std::vector<uint64_t> nxt((cur_len / 2) * 4);
+            zko_mle_partial_evaluate(FID, cur.data(), cur_len, 0, r.l, nxt.data());
+            cur.swap(nxt); cur_len /= 2;
+        }
+    }
+    std::vector<zk::Fe> tab(cur_len);
+    for (uint64_t i = 0; i < cur_len; ++i) tab[i] = to_fe(&cur[4 * i]);
+    zk::TailArgs a; memset(&a, 0, sizeof a);
+    zk::TailOut out; memset(&out, 0, sizeof out);
+    zk::TailShared sh;
+    a.tp.t[0] = tab.data();
+    a.log_len = 0; while ((1ull << a.log_len) < cur_len) ++a.log_len;
+    a.pending = host_rounds > 0; a.mode = zk::kTailPlain; a.seq = 5;
+    if (a.pending) a.ft = host_fold_table(f, r);
+    fill_tail_consts<FID>(a, f, 1);
+    tr.export_state(a.sponge.s, &a.sponge.pos);
+    a.out = &out;
+    HostExec ex;
+    zk::sumcheck_tail_body<FID, 1, 1, 0>(a, sh, ex);
+    if (out.seq != 5 || (int)out.rounds != n - host_rounds) { ++bad; printf("plain tail rounds %u (want %d)\n", out.rounds, n - host_rounds); }
+    for (int k = host_rounds; k < n; ++k) {
+        if (memcmp(out.round_vals[k - host_rounds], &rp[(size_t)k * 8], 64)) { ++bad; printf("plain tail n=%d round %d sums mismatch\n", n, k); }
+        if (memcmp(&out.challenges[k - host_rounds], &ch[(size_t)k * 4], 32)) { ++bad; printf("plain tail challenge %d mismatch\n", k); }
+    }
+    if (memcmp(&out.finals[0], fin, 32)) { ++bad; printf("plain tail final evaluation mismatch\n"); }
+    return bad;
+}
+
+template <int FID> static int run_tails() {
+    int bad = 0;
+    for (int n = 1; n <= 7; ++n)
+        for (int h = 0; h <= n && h <= 3; ++h) {
+            bad += run_tail_product<FID, 1, 2, 0>(n, h, 3 * n + h);
+            bad += run_tail_product<FID, 2, 2, 0>(n, h, 8 * h);
+            bad += run_tail_product<FID, 1, 2, 1>(n, h, 0);
+            bad += run_tail_plain<FID>(n, h);
+        }
+    bad += run_tail_product<FID, 2, 3, 0>(4, 1, 1);
+    bad += run_tail_product<FID, 1, 3, 0>(3, 0, 2);
+    bad += run_tail_product<FID, 4, 2, 0>(3, 2, 135);
+    bad += run_tail_product<FID, 3, 2, 0>(5, 5, 136);
+    printf("tail field %d: %s\n", FID, bad ? "FAIL" : "ok");
+    return bad;
+}
+
 int main() {
     int bad = run<0>() + run<1>() + run<2>();
+    bad += test_dev_sponge();
+    bad += run_tails<0>() + run_tails<1>() + run_tails<2>();
+    bad += run_round_accs<0>() + run_round_accs<1>() + run_round_accs<2>();
     return bad ? 1 : 0;
 }

@@ -17,4 +17,4 @@ def test_fp_cuh_host_emulation(tmp_path):
     subprocess.check_call(cmd)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]
-    assert out.stdout.count("ok") == 3
+    assert out.stdout.count("ok") == 10, out.stdout[-2000:]

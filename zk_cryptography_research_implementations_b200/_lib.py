@@ -16,7 +16,7 @@ u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
 ZK_OK, ZK_ERR_ASSERT, ZK_ERR_CUDA, ZK_ERR_ARG = 0, -1, -2, -3
-FLAG_DIRECT_S1, FLAG_SKIP_ABSORB, FLAG_NCCL_EXCHANGE, FLAG_NO_CLAIM_ABSORB = 1, 2, 4, 8
+FLAG_DIRECT_S1, FLAG_SKIP_ABSORB, FLAG_NCCL_EXCHANGE, FLAG_NO_CLAIM_ABSORB, FLAG_HOST_ROUNDS = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); every symbol include/zk_sumcheck.h declares
 SIGNATURES = {
@@ -27,6 +27,8 @@ SIGNATURES = {
     "zk_last_error": (C.c_char_p, [vp]),
     "zk_ctx_synchronize": (C.c_int, [vp]),
     "zk_ctx_set_profiling": (C.c_int, [vp, C.c_int]),
+    "zk_ctx_set_tail_log": (C.c_int, [vp, C.c_int]),
+    "zk_ctx_get_tail_log": (C.c_int, [vp]),
     "zk_ctx_reset_stats": (C.c_int, [vp]),
     "zk_ctx_get_stats": (C.c_int, [vp, u64p, u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "zk_fe_from_u64": (C.c_int, [C.c_int, C.c_uint64, u64p]),

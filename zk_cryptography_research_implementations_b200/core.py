@@ -121,6 +121,13 @@ class Context:
     def set_profiling(self, on: bool) -> None:
         self.check(self.lib.zk_ctx_set_profiling(self.h, int(on)))
 
+    def set_tail_log(self, tail_log: int) -> None:
+        """Tables of at most 2**tail_log entries finish in one launch with the transcript on the device (0: never)."""
+        self.check(self.lib.zk_ctx_set_tail_log(self.h, int(tail_log)))
+
+    def tail_log(self) -> int:
+        return int(self.lib.zk_ctx_get_tail_log(self.h))
+
     def reset_stats(self) -> None:
         self.check(self.lib.zk_ctx_reset_stats(self.h))
 

@@ -18,6 +18,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "round_launch.cuh"
+#include "tail_launch.cuh"
 #include "internal.h"
 
 using namespace zk;
@@ -131,12 +132,22 @@ static int ctx_create(zk_ctx** out, int fid, int device, void* stream, bool own_
     ctx->own_stream = own_stream;
     ctx->max_grid = ctx->sm_count * 8;
     if (const char* cap = getenv("ZKB200_GRID_CAP")) ctx->grid_cap = atoi(cap);
-    ZK_CUDA(cudaMalloc(&ctx->partials, (size_t)ctx->max_grid * kMaxEvals * sizeof(Fe)));
+    ZK_CUDA(cudaMalloc(&ctx->gacc, (size_t)kMaxCols * sizeof(unsigned long long)));
+    ZK_CUDA(cudaMemsetAsync(ctx->gacc, 0, (size_t)kMaxCols * sizeof(unsigned long long), ctx->stream));
     ZK_CUDA(cudaMalloc(&ctx->ticket, sizeof(unsigned)));
     ZK_CUDA(cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream));
     ZK_CUDA(cudaHostAlloc(&ctx->mail_host, sizeof(Mailbox), cudaHostAllocMapped));
     memset(ctx->mail_host, 0, sizeof(Mailbox));
     ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->mail_dev, ctx->mail_host, 0));
+    ZK_CUDA(cudaHostAlloc(&ctx->tail_host, sizeof(TailOut), cudaHostAllocMapped));
+    memset(ctx->tail_host, 0, sizeof(TailOut));
+    ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->tail_dev, ctx->tail_host, 0));
+    if (const char* tl = getenv("ZKB200_TAIL_LOG")) ctx->tail_log = atoi(tl);
+    if (ctx->tail_log < 0 || ctx->tail_log > kTailMaxLog) ctx->tail_log = ctx->tail_log < 0 ? 0 : kTailMaxLog;
+    {
+        HFe cur = ctx->field.one(), m232 = ctx->field.from_u64(1ull << 32);
+        for (int i = 0; i < 8; ++i) { ctx->pow32[i] = cur; cur = ctx->field.mul(cur, m232); }
+    }
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = c.release();
     return ZK_OK;
@@ -155,9 +166,10 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     zk_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    cudaFree(ctx->partials);
+    cudaFree(ctx->gacc);
     cudaFree(ctx->ticket);
     cudaFreeHost(ctx->mail_host);
+    cudaFreeHost(ctx->tail_host);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -167,6 +179,12 @@ extern "C" int zk_ctx_synchronize(zk_ctx* ctx) {
     return ZK_OK;
 }
 extern "C" int zk_ctx_set_profiling(zk_ctx* ctx, int on) { ctx->profiling = on != 0; return ZK_OK; }
+extern "C" int zk_ctx_set_tail_log(zk_ctx* ctx, int tail_log) {
+    if (tail_log < 0 || tail_log > kTailMaxLog) return fail(ctx, ZK_ERR_ARG, "tail_log must be in 0..16");
+    ctx->tail_log = tail_log;
+    return ZK_OK;
+}
+extern "C" int zk_ctx_get_tail_log(const zk_ctx* ctx) { return ctx->tail_log; }
 extern "C" int zk_ctx_reset_stats(zk_ctx* ctx) {
     ctx->launches = ctx->round_launches = 0;
     ctx->round_ms = ctx->round_bytes = 0;
@@ -341,19 +359,21 @@ extern "C" void zk_table_free(zk_ctx* ctx, zk_table* t) {
 // =================================================================================== kernel launchers
 namespace zk {
 
-int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own) {
+int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own) { return wait_seq(ctx, &box->seq, seq, own); }
+
+int wait_seq(zk_ctx* ctx, const volatile unsigned* word, unsigned seq, bool own) {
     auto t0 = std::chrono::steady_clock::now();
     for (uint64_t spins = 0;; ++spins) {
-        if (box->seq == seq) break;
+        if (*word == seq) break;
         if ((spins & 0x3ff) == 0x3ff) {
             cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q != cudaSuccess && q != cudaErrorNotReady) {
                 ctx->err = std::string("round kernel failed: ") + cudaGetErrorString(q);
                 return ZK_ERR_CUDA;
             }
-            if (q == cudaSuccess && own && box->seq != seq) {
+            if (q == cudaSuccess && own && *word != seq) {
                 // the stream drained: the write must have landed; re-read once before giving up
-                if (box->seq == seq) break;
+                if (*word == seq) break;
                 return fail(ctx, ZK_ERR_CUDA, "round kernel finished without publishing its result");
             }
             if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
@@ -390,6 +410,56 @@ int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t l
 int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, const FoldTable& ft) {
     ZK_DISPATCH_FID(ctx, (fold0_kernel<FID><<<grid_for(ctx, len / 2, 4), kThreads, 0, ctx->stream>>>(tp, ntables, len / 2, ft)));
     return post_launch(ctx);
+}
+
+bool tail_applies(const zk_ctx* ctx, uint64_t len, uint32_t flags) {
+    return !(flags & ZK_FLAG_HOST_ROUNDS) && ctx->tail_log > 0 && len >= 2 && len <= (1ull << ctx->tail_log);
+}
+
+int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
+             uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals) {
+    const int NE = D + 1, T = P * D + nlin;
+    if (!is_pow2(len) || len < 2 || ilog2(len) > (uint32_t)kTailMaxLog) return fail(ctx, ZK_ERR_ARG, "internal: table too long for the device tail");
+    TailArgs a;
+    memset(&a, 0, sizeof a);
+    a.tp = tp;
+    a.log_len = ilog2(len);
+    a.pending = pending_r ? 1u : 0u;
+    a.mode = (uint32_t)mode;
+    a.seq = ++ctx->tail_seq;
+    if (pending_r) a.ft = make_fold_table(ctx->field, *pending_r);
+    memcpy(a.interp, interp_for(ctx, D).matrix(), (size_t)NE * NE * sizeof(Fe));
+    memcpy(a.pow32, ctx->pow32, sizeof a.pow32);
+    tr.export_state(a.sponge.s, &a.sponge.pos);
+    a.out = ctx->tail_dev;
+    // algorithmic bytes of the rounds the launch covers (same accounting as the per-round launches)
+    double bytes = 0;
+    {
+        uint64_t l = len;
+        bool pend = pending_r != nullptr;
+        while (pend ? l > 2 : l >= 2) {
+            bytes += pend ? 48.0 * T * (double)l : 32.0 * T * (double)l;
+            if (pend) l /= 2;
+            pend = true;
+        }
+    }
+    prof_begin(ctx);
+    int rc;
+    ZK_DISPATCH_FID(ctx, rc = launch_tail_pd<FID>(ctx, P, D, nlin, a));
+    prof_end(ctx, bytes);
+    if (rc) return rc;
+    rc = wait_seq(ctx, &ctx->tail_host->seq, a.seq, true);
+    if (rc) return rc;
+    const TailOut* o = ctx->tail_host;
+    const uint32_t expect = a.log_len - (a.pending ? 1u : 0u);
+    if (o->rounds != expect) return fail(ctx, ZK_ERR_CUDA, "device tail ran an unexpected number of rounds");
+    for (uint32_t k = 0; k < o->rounds; ++k) {
+        memcpy(vals_out + (size_t)k * NE * 4, o->round_vals[k], (size_t)NE * sizeof(Fe));
+        if (chal_out) memcpy(chal_out + (size_t)k * 4, &o->challenges[k], sizeof(Fe));
+    }
+    if (finals) memcpy(finals, o->finals, (size_t)T * sizeof(Fe));
+    tr.import_state(o->sponge.s, o->sponge.pos);
+    return ZK_OK;
 }
 
 }  // namespace zk
@@ -623,6 +693,13 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
     for (uint32_t k = 0; k < n; ++k) {                                           // :37
         const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
         int rc;
+        if (tail_applies(ctx, sp->len, flags)) {   // rounds k..n-1 and the last fold in one launch, transcript on the device
+            rc = run_tail(ctx, tp, P, D, NL, kTailProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
+                          coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
+            if (rc) return rc;
+            set_len(sp, 1);
+            return ZK_OK;
+        }
         if (k == 0) {
             rc = launch_round_evals(ctx, tp, P, D, sp->len, false, NL);          // :41 generate_round_univariate
         } else {
@@ -696,6 +773,13 @@ extern "C" int zk_prove_basic_device(zk_ctx* ctx, zk_table* t, uint64_t claimed_
     tr.append_be(f, claimed);                                                    // :40-41
     memcpy(claimed_sum, claimed.l, 32);
     for (uint32_t k = 0; k < n; ++k) {                                           // :46
+        if (k > 0 && tail_applies(ctx, t->len, flags)) {   // rounds k..n-1 and the last fold in one launch
+            uint64_t* chal = challenges ? challenges + (size_t)k * 4 : nullptr;
+            rc = run_tail(ctx, tp, 1, 1, 0, kTailPlain, t->len, &r, tr, round_polys + (size_t)k * 8, chal, final_value);
+            if (rc) return rc;
+            t->len = 1;
+            return ZK_OK;
+        }
         if (k > 0) {
             rc = launch_fold_evals(ctx, tp, 1, 1, t->len, make_fold_table(f, r), false);  // :61-63 fused with :50
             t->len /= 2;

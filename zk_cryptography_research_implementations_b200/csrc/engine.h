@@ -6,7 +6,7 @@
 #include <vector>
 #include "host_field.h"
 
-namespace zk { struct Fe; struct Mailbox; }
+namespace zk { struct Fe; struct Mailbox; struct TailOut; }
 
 struct zk_ctx {
     explicit zk_ctx(int field_id) : fid(field_id), field(field_id) {}
@@ -19,8 +19,8 @@ struct zk_ctx {
     bool own_stream = true;
     zk::HostField field;
     std::map<int, zk::Interpolator> interps;   // one inverse Vandermonde per degree
-    // grid-wide reduction scratch + the published round evaluations (mapped pinned host memory)
-    zk::Fe* partials = nullptr;
+    // grid-wide reduction scratch (column totals, kernels.cuh) + the published round evaluations (mapped pinned host memory)
+    unsigned long long* gacc = nullptr;
     unsigned* ticket = nullptr;
     zk::Mailbox* mail_host = nullptr;   // this context's own mailbox (unsharded operations)
     zk::Mailbox* mail_dev = nullptr;
@@ -31,6 +31,12 @@ struct zk_ctx {
     size_t xmail_bytes = 0;
     unsigned xmail_seq = 0;
     bool exchange_pending = false;      // the last round kernel published into the shared mailbox
+    // device tail (tail.cuh): all remaining rounds in one launch once the tables hold <= 2^tail_log entries
+    zk::TailOut* tail_host = nullptr;   // mapped pinned host memory
+    zk::TailOut* tail_dev = nullptr;
+    unsigned tail_seq = 0;
+    int tail_log = 13;                  // ZKB200_TAIL_LOG / zk_ctx_set_tail_log; 0 = always host-driven rounds
+    zk::HFe pow32[8];                   // Montgomery forms of 2^(32 i)
     // general scratch (evaluate / convert_to_bytes / out-of-place folds)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

@@ -265,35 +265,52 @@ template <int FID> struct Fp {
     }
 
     // ---------------------------------------------------------------- lazy accumulators
-    // Montgomery-reduce a 17-limb accumulator A (sum of < 2^32 unreduced products of canonical
-    // Montgomery elements): returns A / 2^256 mod p, canonical.  Runs once per thread, so it is
-    // written for clarity (word-serial REDC), not for IMAD count.
-    ZK_DEV static void redc_wide(Fe& r, const uint32_t acc[17]) {
-        uint32_t t[18];
+    // t = (a + M p) / 2^256 for the M in [0, 2^256) that makes the division exact: a * 2^-256 mod p
+    // up to one multiple of p (t <= p).  a is ANY 256-bit integer.  Same window scheme as mont_mul with
+    // the a*b rows left out: 8 rows of two independent four-slot chains.
+    ZK_DEV static void redc256(uint32_t t[8], const uint32_t a[8]) {
+        uint32_t X[9], Y[8];
+        LimbsOfP P;
 #pragma unroll
-        for (int k = 0; k < 17; ++k) t[k] = acc[k];
-        t[17] = 0;
+        for (int k = 0; k < 8; ++k) { X[k] = a[k]; Y[k] = 0; }
+        uint32_t m = X[0] * F::inv32;
+        row_mad(X, P, 0, m);
+        X[8] = ptx::addc(0u, 0u);
+        row_mad(Y, P, 1, m);   // Y was zero: no carry out
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint32_t m = t[i] * F::inv32;
-            // t += m * p << (32 i), limb by limb (lo and hi chains separately)
-            t[i] = ptx::mad_lo_cc(m, F::p(0), t[i]);
+        for (int i = 1; i < 8; ++i) {
+            uint32_t nX[9], nY[8];
 #pragma unroll
-            for (int j = 1; j < 8; ++j) t[i + j] = ptx::madc_lo_cc(m, F::p(j), t[i + j]);
+            for (int k = 0; k < 8; ++k) nX[k] = Y[k];
 #pragma unroll
-            for (int j = i + 8; j < 17; ++j) t[j] = ptx::addc_cc(t[j], 0u);
-            t[17] = ptx::addc(t[17], 0u);
-            t[i + 1] = ptx::mad_hi_cc(m, F::p(0), t[i + 1]);
+            for (int k = 0; k < 7; ++k) nY[k] = X[k + 2];
+            nY[7] = 0;
+            nX[0] = ptx::add_cc(nX[0], X[1]);   // the straggler word; its carry enters the Y chain
+            m = nX[0] * F::inv32;               // mul.lo leaves the carry flag alone
+            row_madc(nY, P, 1, m);
+            row_mad(nX, P, 0, m);
+            nX[8] = ptx::addc(0u, 0u);
 #pragma unroll
-            for (int j = 1; j < 8; ++j) t[i + j + 1] = ptx::madc_hi_cc(m, F::p(j), t[i + j + 1]);
+            for (int k = 0; k < 9; ++k) X[k] = nX[k];
 #pragma unroll
-            for (int j = i + 9; j < 17; ++j) t[j] = ptx::addc_cc(t[j], 0u);
-            t[17] = ptx::addc(t[17], 0u);
+            for (int k = 0; k < 8; ++k) Y[k] = nY[k];
         }
-        // t[8..17] = A / 2^256 < 2^288 + p < 2^291
-        uint32_t s[10];
+        t[0] = ptx::add_cc(Y[0], X[1]);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s[k] = t[k + 8];
+        for (int k = 1; k < 7; ++k) t[k] = ptx::addc_cc(Y[k], X[k + 1]);
+        t[7] = ptx::addc(Y[7], X[8]);
+    }
+    // Montgomery-reduce a 17-limb accumulator A (sum of < 2^32 unreduced products of canonical
+    // Montgomery elements): returns A / 2^256 mod p, canonical.
+    //   A = A_lo + 2^256 A_hi  =>  A / 2^256 == redc256(A_lo) + A_hi  (mod p),  < p + 1 + 2^288 < 2^291.
+    ZK_DEV static void redc_wide(Fe& r, const uint32_t acc[17]) {
+        uint32_t t[8], s[10];
+        redc256(t, acc);
+        s[0] = ptx::add_cc(t[0], acc[8]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s[k] = ptx::addc_cc(t[k], acc[k + 8]);
+        s[8] = ptx::addc_cc(acc[16], 0u);
+        s[9] = ptx::addc(0u, 0u);
         barrett(r.v, s);
     }
     // 9-limb sum of canonical elements (plain-sumcheck round sums) -> canonical

@@ -177,6 +177,7 @@ class Interpolator {
         }
     }
     int degree() const { return n_ - 1; }
+    const HFe* matrix() const { return m_.data(); }   // row-major (degree+1)^2, Montgomery form
     void coefficients(const HFe* evals, HFe* coeffs) const {
         for (int i = 0; i < n_; ++i) {
             HFe acc = f_.zero();
@@ -227,6 +228,9 @@ class Keccak256 {
         c.permute();
         memcpy(out, c.s_, 32);
     }
+    // hand the sponge over to / take it back from the device transcript (dev_transcript.cuh KeccakState)
+    void export_state(uint64_t s[25], uint32_t* pos) const { memcpy(s, s_, sizeof s_); *pos = (uint32_t)pos_; }
+    void import_state(const uint64_t s[25], uint32_t pos) { memcpy(s_, s, sizeof s_); pos_ = pos; }
 
   private:
     static constexpr size_t kRate = 136;
@@ -282,6 +286,8 @@ class HostTranscript {
         sample(d);
         return f.from_le_bytes32_mod_order(d);
     }
+    void export_state(uint64_t s[25], uint32_t* pos) const { h_.export_state(s, pos); }
+    void import_state(const uint64_t s[25], uint32_t pos) { h_.import_state(s, pos); }
     void append_be(const HostField& f, const HFe& x) { uint8_t b[32]; f.to_bytes_be(x, b); append(b, 32); }
     void append_le(const HostField& f, const HFe& x) { uint8_t b[32]; f.to_bytes_le(x, b); append(b, 32); }
 

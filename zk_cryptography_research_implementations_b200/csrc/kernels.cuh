@@ -12,22 +12,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "fp.cuh"
+#include "round_acc.cuh"
 
 namespace zk {
 
 #ifndef ZK_TWO_BLOCK_TABLES
 #define ZK_TWO_BLOCK_TABLES 4   // up to this many tables the round kernels are compiled for two resident blocks per SM
 #endif
-constexpr int kMaxTables = 8;   // P * D
-constexpr int kMaxEvals = 5;    // D + 1
 #ifndef ZK_THREADS
 #define ZK_THREADS 256
 #endif
 constexpr int kThreads = ZK_THREADS;   // threads per block of every kernel
-
-struct TablePtrs {
-    Fe* t[kMaxTables];
-};
 
 template <int FID> __device__ __forceinline__ void fold_by_scalar(Fe& out, const Fe& lo, const Fe& hi, const FoldTable& ft) {
     FoldScalar<FID>::fold(out, lo, hi, ft);
@@ -59,7 +54,7 @@ __device__ __forceinline__ Fe ld256_cg(const Fe* p) {
     return r;
 }
 
-// ---------------------------------------------------------------- grid-wide reduction of NE field elements
+// ---------------------------------------------------------------- grid-wide reduction of the round sums
 // The published result of a round kernel: the d+1 field elements plus a sequence number written LAST
 // (after a system-scope fence).  The mailbox lives in mapped pinned host memory -- for sharded runs in a
 // segment shared by all rank processes -- so the host sees the round's result a PCIe write after the
@@ -70,10 +65,10 @@ struct Mailbox {
     unsigned pad[7];
 };
 struct ReduceScratch {
-    Fe* partials;        // [gridDim.x][NE]
-    unsigned* ticket;    // zero before the launch; reset by the last block
-    Mailbox* out;        // mapped pinned host memory (device address)
-    unsigned seq;        // value to publish in out->seq
+    unsigned long long* gacc;   // [kMaxCols] grid-wide column totals; zero before the launch, re-zeroed by the last block
+    unsigned* ticket;           // zero before the launch; reset by the last block
+    Mailbox* out;               // mapped pinned host memory (device address)
+    unsigned seq;               // value to publish in out->seq
 };
 
 template <int FID> __device__ __forceinline__ Fe warp_sum(Fe v) {
@@ -87,7 +82,8 @@ template <int FID> __device__ __forceinline__ Fe warp_sum(Fe v) {
     return v;
 }
 
-// Sum `vals` over the block; result valid in thread 0.
+// Sum `vals` over the block with modular additions; result valid in thread 0.  (General-purpose helper of the
+// GKR table builders; the round kernels use the exact column sums below.)
 template <int FID, int NE> __device__ __forceinline__ void block_sum(Fe (&vals)[NE]) {
     __shared__ Fe sm[NE][kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -112,126 +108,70 @@ template <int FID, int NE> __device__ __forceinline__ void block_sum(Fe (&vals)[
     }
 }
 
-// Called by every thread of every block with its per-thread sums.
-template <int FID, int NE> __device__ __forceinline__ void grid_sum_publish(Fe (&vals)[NE], const ReduceScratch& rs) {
-    __shared__ bool is_last;
-    block_sum<FID, NE>(vals);
-    if (threadIdx.x == 0) {
+// Exact integer sum of every thread's NC 32-bit columns over the block: tot[c] = sum over threads of col[c], valid
+// for all threads after the call.  One REDUX pair per column and warp (16-bit halves, so nothing wraps), then NC
+// threads add the per-warp sums.  Needs blockDim.x >= NC.
+template <int NC> __device__ __forceinline__ void block_column_sums(const uint32_t (&col)[NC], unsigned long long* tot /* shared, [NC] */) {
+    static_assert(NC <= kThreads, "one thread per column");
+    __shared__ unsigned long long warp_cols[kThreads / 32][NC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) st256(&rs.partials[(size_t)blockIdx.x * NE + e], vals[e]);
-        __threadfence();
-        unsigned t = atomicAdd(rs.ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+    for (int c = 0; c < NC; ++c) {
+        unsigned lo = __reduce_add_sync(0xffffffffu, col[c] & 0xffffu);
+        unsigned hi = __reduce_add_sync(0xffffffffu, col[c] >> 16);
+        if (lane == (c & 31)) warp_cols[warp][c] = (unsigned long long)lo + ((unsigned long long)hi << 16);
     }
     __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-        Fe acc;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc.v[k] = 0;
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            Fe v = ld256_cg(&rs.partials[(size_t)b * NE + e]);
-            Fp<FID>::add(acc, acc, v);
-        }
-        vals[e] = acc;
+    if (threadIdx.x < NC) {
+        unsigned long long s = 0;
+        for (int w = 0; w < nwarps; ++w) s += warp_cols[w][threadIdx.x];
+        tot[threadIdx.x] = s;
     }
-    block_sum<FID, NE>(vals);
+    __syncthreads();
+}
+
+// Grid-wide version: every block adds its column sums into rs.gacc (one RED per column), takes a ticket, and the
+// last block to arrive gets the grid totals in tot[] and returns true (all its threads); it also re-arms gacc and
+// the ticket for the next launch.  A one-block grid skips the global stage altogether.
+template <int NC> __device__ __forceinline__ bool grid_column_sums(const uint32_t (&col)[NC], const ReduceScratch& rs, unsigned long long* tot) {
+    __shared__ bool is_last;
+    block_column_sums<NC>(col, tot);
+    if (gridDim.x == 1) return true;
+    if (threadIdx.x < NC) {
+        atomicAdd(rs.gacc + threadIdx.x, tot[threadIdx.x]);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(rs.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    if (threadIdx.x < NC) {
+        tot[threadIdx.x] = __ldcg(rs.gacc + threadIdx.x);
+        rs.gacc[threadIdx.x] = 0;
+    }
+    if (threadIdx.x == 0) *rs.ticket = 0;
+    __syncthreads();
+    return true;
+}
+
+// Epilogue of a round kernel: called by every thread of every block with its accumulator.
+template <class RA> __device__ __forceinline__ void publish_round(const RA& ra, const ReduceScratch& rs) {
+    __shared__ unsigned long long tot[RA::NC];
+    uint32_t col[RA::NC];
+    ra.columns(col);
+    if (!grid_column_sums<RA::NC>(col, rs, tot)) return;
+    if (threadIdx.x < RA::NE) {
+        Fe out;
+        RA::finalize(out, threadIdx.x, tot);
+        rs.out->vals[threadIdx.x] = out;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) rs.out->vals[e] = vals[e];
-        *rs.ticket = 0;
         __threadfence_system();
         *reinterpret_cast<volatile unsigned*>(&rs.out->seq) = rs.seq;
     }
 }
-
-// ---------------------------------------------------------------- evaluation of the round polynomial
-// Given the (lo, hi) values of all T = P*D tables at one pair index, accumulate the unreduced
-// contributions to s(X), X = 0..D:  s(X) += sum_p prod_d (lo + X (hi - lo)).
-// (sumcheck_gkr_protocol.rs:127-137 evaluates the same sums with D+1 full folds of every table.)
-// D == 1 (plain sumcheck, prover.rs:74-89) accumulates 9-limb sums; D >= 2 accumulates 17-limb
-// unreduced products.  SKIP1 leaves s(1) out (the host derives it from the running claim).
-// NLIN extra tables enter the sum LINEARLY (a product with the all-ones table, which is then neither stored, folded
-// nor multiplied): s(X) += sum_l (lo_l + X (hi_l - lo_l)).  The sparse GKR layer prover's phases have exactly that
-// shape, h1*W + h2*1 (gkr_wide.cu).  Only the two half sums are accumulated; finish() spreads them over the s(X).
-template <int FID, int P, int D, bool SKIP1, int NLIN = 0> struct RoundAcc {
-    static constexpr int NE = D + 1;
-    static constexpr int W = (D == 1) ? 9 : 17;
-    static constexpr int T = P * D + NLIN;
-    uint32_t acc[NE][W];
-    uint32_t lin[NLIN > 0 ? 2 : 1][9];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-#pragma unroll
-            for (int k = 0; k < W; ++k) acc[e][k] = 0;
-#pragma unroll
-        for (int e = 0; e < (NLIN > 0 ? 2 : 1); ++e)
-#pragma unroll
-            for (int k = 0; k < 9; ++k) lin[e][k] = 0;
-    }
-    __device__ __forceinline__ void add_point(int e, const Fe (&v)[T]) {
-        if (D == 1) {
-#pragma unroll
-            for (int p = 0; p < P; ++p) Fp<FID>::acc9_add(acc[e], v[p]);
-        } else {
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                Fe prod = v[p * D];
-#pragma unroll
-                for (int d = 1; d < D - 1; ++d) Fp<FID>::mont_mul(prod, prod, v[p * D + d]);
-                Fp<FID>::mul_acc(acc[e], prod, v[p * D + D - 1]);
-            }
-        }
-    }
-    __device__ __forceinline__ void add_pair(const Fe (&lo)[T], const Fe (&hi)[T]) {
-        add_point(0, lo);
-        if (!SKIP1) add_point(1, hi);
-#pragma unroll
-        for (int l = 0; l < NLIN; ++l) {
-            Fp<FID>::acc9_add(lin[0], lo[P * D + l]);
-            Fp<FID>::acc9_add(lin[1], hi[P * D + l]);
-        }
-        if (D >= 2) {
-            Fe cur[T], diff[T];
-#pragma unroll
-            for (int t = 0; t < P * D; ++t) {
-                Fp<FID>::sub(diff[t], hi[t], lo[t]);
-                Fp<FID>::add(cur[t], hi[t], diff[t]);  // value at X = 2
-            }
-            add_point(2, cur);
-#pragma unroll
-            for (int x = 3; x <= D; ++x) {
-#pragma unroll
-                for (int t = 0; t < P * D; ++t) Fp<FID>::add(cur[t], cur[t], diff[t]);
-                add_point(x, cur);
-            }
-        }
-    }
-    __device__ __forceinline__ void finish(Fe (&out)[NE]) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            if (D == 1) Fp<FID>::reduce9(out[e], acc[e]);
-            else Fp<FID>::redc_wide(out[e], acc[e]);
-        }
-        if (NLIN > 0) {   // linear part at X = 0, 1, 2, ...: S_lo, S_hi, 2 S_hi - S_lo, ...
-            Fe slo, shi, cur, diff;
-            Fp<FID>::reduce9(slo, lin[0]);
-            Fp<FID>::reduce9(shi, lin[1]);
-            Fp<FID>::add(out[0], out[0], slo);
-            if (!SKIP1) Fp<FID>::add(out[1], out[1], shi);
-            Fp<FID>::sub(diff, shi, slo);
-            cur = shi;
-#pragma unroll
-            for (int x = 2; x <= D; ++x) {
-                Fp<FID>::add(cur, cur, diff);
-                Fp<FID>::add(out[x], out[x], cur);
-            }
-        }
-    }
-};
 
 // Round 0: evaluations only.  half = N/2 pairs (j, j + half).
 template <int FID, int P, int D, int NLIN = 0>
@@ -256,9 +196,7 @@ __global__ void __launch_bounds__(kThreads, (P * D + NLIN <= ZK_TWO_BLOCK_TABLES
         }
         ra.add_pair(lo, hi);
     }
-    Fe out[D + 1];
-    ra.finish(out);
-    grid_sum_publish<FID, D + 1>(out, rs);
+    publish_round(ra, rs);
 }
 
 // Rounds k >= 1: fold table_{k-1} (4q entries per table) by r in place into table_k (2q entries) and
@@ -297,9 +235,7 @@ __global__ void __launch_bounds__(kThreads, (P * D + NLIN <= ZK_TWO_BLOCK_TABLES
         }
         ra.add_pair(lo, hi);
     }
-    Fe out[D + 1];
-    ra.finish(out);
-    grid_sum_publish<FID, D + 1>(out, rs);
+    publish_round(ra, rs);
 }
 
 // Plain fold of variable 0, in place: table[j] = table[j] + r (table[j+half] - table[j]).

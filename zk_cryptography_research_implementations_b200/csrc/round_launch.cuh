@@ -30,11 +30,11 @@ inline ReduceScratch reduce_scratch(zk_ctx* ctx, bool shared) {
     if (shared) {
         unsigned seq = ++ctx->xmail_seq;
         ctx->exchange_pending = true;
-        return ReduceScratch{ctx->partials, ctx->ticket, ctx->xmail_dev + (size_t)(seq & 1u) * ctx->world + ctx->rank, seq};
+        return ReduceScratch{ctx->gacc, ctx->ticket, ctx->xmail_dev + (size_t)(seq & 1u) * ctx->world + ctx->rank, seq};
     }
     unsigned seq = ++ctx->mail_seq;
     ctx->exchange_pending = false;
-    return ReduceScratch{ctx->partials, ctx->ticket, ctx->mail_dev, seq};
+    return ReduceScratch{ctx->gacc, ctx->ticket, ctx->mail_dev, seq};
 }
 inline int unsupported_pd(zk_ctx* ctx) {
     ctx->err = "unsupported (P, D): supported are (1,1) (1,2) (2,2) (3,2) (4,2) (1,3) (2,3), and (1,2) with one linear table";
