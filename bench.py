@@ -157,22 +157,45 @@ def run_gkr_wide(args, wl):
     circuit = gkr.WideCircuit(ctx, bits, layers)
     setup_s = time.perf_counter() - t0
     I = gkr_inputs(field, w)
+    dev_I = ctx.upload(I)                                # value: the input layer is resident in HBM when the clock starts
     proof = None
     for _ in range(args.warmup):
-        proof = gkr.prove_wide(ctx, circuit, I)
+        proof = gkr.prove_wide(ctx, circuit, dev_I)
     ctx.set_profiling(True)
     ctx.reset_stats()
     sampler = ClockSampler(0)
     times = []
     for _ in range(args.steps):
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        proof = gkr.prove_wide(ctx, circuit, I)      # inputs on the host -> proof on the host
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        proof = gkr.prove_wide(ctx, circuit, dev_I)  # resident inputs -> proof on the host
+        e1.record()
         torch.cuda.synchronize()
-        times.append((time.perf_counter() - t0) * 1e3)
-    clocks = sampler.stop()
+        times.append(e0.elapsed_time(e1))
     st = ctx.stats()
+    ctx.set_profiling(False)
     ms = statistics.mean(times)
+    # e2e: the reference-facing call, inputs in pinned HOST memory, proof back on the host
+    e2e_ms = None
+    if not args.no_e2e:
+        pin = C.c_void_p()
+        if ctx.lib.zk_pinned_alloc(C.c_size_t(I.nbytes), C.byref(pin)) == 0:
+            host_I = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint64)), shape=(I.size,)).reshape(I.shape)
+            host_I[:] = I
+            gkr.prove_wide(ctx, circuit, host_I)
+            ts = []
+            for _ in range(max(1, min(args.steps, args.e2e_steps))):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                proof_e = gkr.prove_wide(ctx, circuit, host_I)
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            e2e_ms = statistics.mean(ts)
+            assert np.array_equal(proof_e.claimed_sum, proof.claimed_sum)
+            del host_I
+            ctx.lib.zk_pinned_free(pin)
+    clocks = sampler.stop()
     hbm_peak, peak_src = peaks()
     achieved = st["round_bytes"] / (st["round_ms"] * 1e-3) / 1e9 if st["round_ms"] > 0 else 0.0
     cpu = None
@@ -191,15 +214,17 @@ def run_gkr_wide(args, wl):
                        "layer_bits": bits, "sumcheck_rounds": rounds, "prover": "sparse two-phase (csrc/gkr_wide.cu)",
                        "circuit_setup_s": setup_s, "l2": "per phase 4 tables x %d MiB" % ((32 << w) >> 20)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "fold_evals_kernel / round_evals_kernel <%s,P=1,D=2,+1 linear table> (%d launches; most are on tables far smaller than L2: "
+                         "peak_source": peak_src, "kernel": "fold_evals_kernel / round_evals_kernel / sumcheck_tail_kernel <%s,P=1,D=2,+1 linear table> (%d launches; most are on tables far smaller than L2: "
                                    "latency-bound, the fraction is not a bandwidth statement)" % (fname, st["round_launches"]),
                          "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)},
             "cpu_baseline": cpu,
-            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": int(I.nbytes), "d2h_bytes_per_step": int(rounds * 4 * 32),
-                    "note": "value already is the host-to-host zk_gkr_prove_wide call (inputs on the host, proof on the host; the circuit's CSR lives on the GPU)"},
-            "gpu_launches": st["launches"], "clocks": clocks,
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(I.nbytes), "d2h_bytes_per_step": int(rounds * 4 * 32),
+                    "call": "zk_gkr_prove_wide: input layer in pinned host memory -> proof on the host (the circuit's CSR lives on the GPU); "
+                            "`value` is zk_gkr_prove_wide_device with the input layer already in HBM"},
+            "gpu_launches": st["launches"], "clocks": clocks, "tail_log": ctx.tail_log(),
             "proof_digest": int(np.bitwise_xor.reduce(coeffs.reshape(-1))) & 0xFFFFFFFF}
     print(json.dumps(line), flush=True)
+    dev_I.free()
     circuit.close()
     ctx.close()
 
@@ -435,7 +460,30 @@ def config_dict(name, wl, log2, gpus):
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region.  NVML in a background thread every ~5 ms (so that
+    even millisecond-long timed regions see samples); falls back to an `nvidia-smi -lms 100` child process."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index: int):
+        self.sm, self.mx, self.pw, self.reasons = [], [], [], set()
+        self.thread = self.p = None
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                         "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                         "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                         "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.path = "/tmp/zk_clocks_%d.csv" % os.getpid()
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -446,7 +494,37 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(self.max_sm)
+                try:
+                    self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for nm, bit in self.bits.items():
+                        if mask & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+            except Exception:
+                break
+            self.stop_flag.wait(0.005)
+
+    def _summary(self, source):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "power_w_max": max(self.pw) if self.pw else None, "samples": len(self.sm), "reasons": sorted(self.reasons),
+                "source": source}
+
     def stop(self):
+        if self.thread:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            return self._summary("nvml, 5 ms period, sampled during the timed region")
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -455,22 +533,19 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.close()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                self.sm.append(float(parts[0])); self.mx.append(float(parts[1])); self.pw.append(float(parts[2]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
+            for nm, v in zip(self.NAMES, parts[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
+                    self.reasons.add(nm)
         os.unlink(self.path)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return self._summary("nvidia-smi -lms 100")
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -580,7 +655,7 @@ def run_ours(args, wl):
     achieved = st["round_bytes"] / (st["round_ms"] * 1e-3) / 1e9 if st["round_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "fold_evals_kernel / round_evals_kernel <%s,P=%d,D=%d> (all %d launches of %d steps, rank 0)"
+                "kernel": "fold_evals_kernel / round_evals_kernel (+ one sumcheck_tail_kernel per prove) <%s,P=%d,D=%d> (all %d launches of %d steps, rank 0)"
                           % (fname, P, D, st["round_launches"], args.steps),
                 "algorithmic_bytes_per_step_per_rank": st["round_bytes"] / max(args.steps, 1),
                 "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)}
@@ -662,7 +737,7 @@ def run_ours(args, wl):
             "roofline": roofline, "integer_roofline": integer, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "exchange": (None if world == 1 else ("ncclAllGather per round" if args.nccl_exchange else
                                                    "shared-memory mailboxes written by the round kernels (no per-round collective)")),
-            "clocks": clocks, "proof_digest": proof_digest,
+            "clocks": clocks, "proof_digest": proof_digest, "tail_log": ctx.tail_log(),
         }
         if D == 1:
             line["config"]["note"] = ("value = the n fused rounds with the host Fiat-Shamir per round, table already absorbed; "

@@ -204,6 +204,10 @@ uint64_t zk_wide_circuit_total_rounds(const zk_wide_circuit *);   /* sum over la
 int  zk_gkr_prove_wide(zk_ctx *, const zk_wide_circuit *, const uint64_t *inputs, uint64_t n_inputs, uint64_t *output,
                        uint64_t *claimed_sum, uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges,
                        uint64_t *wb, uint64_t *wc, uint32_t flags);
+/* same with the input layer already resident in HBM (a table of 2^layer_bits[n_layers] entries; it is not modified) */
+int  zk_gkr_prove_wide_device(zk_ctx *, const zk_wide_circuit *, const zk_table *inputs, uint64_t *output,
+                              uint64_t *claimed_sum, uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges,
+                              uint64_t *wb, uint64_t *wc, uint32_t flags);
 
 /* ---- one process per GPU: tables sharded on the LOW index bits (rank q holds entries q, q+G, q+2G, ...) ----
  * NCCL over NVLink/NVSwitch carries one all-gather of (D+1) elements per round; folds stay local.

@@ -21,6 +21,8 @@ LIB = os.path.join(HERE, "libzkb200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+    # host side (transcript Keccak, per-round field arithmetic): BMI2 andn/rorx; every B200 host CPU is x86-64-v3 or newer
+    "-Xcompiler", "-march=x86-64-v3",
 ]
 # kernel-variant experiments: ZKB200_DEFINES="-DZK_PIPE_VARIANT=1" python -m ...build --force
 NVCC_FLAGS += os.environ.get("ZKB200_DEFINES", "").split()

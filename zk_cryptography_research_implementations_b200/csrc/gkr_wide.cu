@@ -335,9 +335,27 @@ extern "C" uint64_t zk_wide_circuit_total_rounds(const zk_wide_circuit* wc) {
 // gkr_protocol::prove (gkr_protocol.rs:26-143), sparse two-phase layers.  Outputs as zk_gkr_prove; `output` may be
 // NULL (wide output layers).  flags: ZK_FLAG_SKIP_ABSORB leaves the output layer out of the transcript (its absorb
 // is a serial host Keccak over 32 * 2^bits[0] bytes).
-extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* inputs, uint64_t n_inputs,
+static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* inputs, const Fe* device_inputs, uint64_t n_inputs,
+                              uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
+                              uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags);
+
+extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const uint64_t* inputs, uint64_t n_inputs,
                                  uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
                                  uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags) {
+    return gkr_prove_wide_impl(ctx, wc, inputs, nullptr, n_inputs, output, claimed_sum, layer_claims, coeffs_out, challenges_out,
+                               wb_out, wc_out, flags);
+}
+// same, the input layer already resident in HBM (a zk_table of 2^layer_bits[L] entries; left untouched)
+extern "C" int zk_gkr_prove_wide_device(zk_ctx* ctx, const zk_wide_circuit* wc, const zk_table* inputs,
+                                        uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
+                                        uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags) {
+    return gkr_prove_wide_impl(ctx, wc, nullptr, inputs->d, inputs->len, output, claimed_sum, layer_claims, coeffs_out, challenges_out,
+                               wb_out, wc_out, flags);
+}
+
+static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* inputs, const Fe* device_inputs, uint64_t n_inputs,
+                              uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
+                              uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags) {
     zk_wide_circuit* wc = const_cast<zk_wide_circuit*>(wc_);   // the workspace inside the circuit object is mutable
     // ZKB200_TRACE=1: coarse host-side timeline of one prove (stream synchronised at each mark)
     const bool trace = getenv("ZKB200_TRACE") != nullptr;
@@ -355,7 +373,8 @@ extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc_, const 
     if (n_inputs != (1ull << wc->bits[L])) return fail(ctx, ZK_ERR_ASSERT, "different number of variables");
     // ---- circuit.evaluate on the device: all layer values stay resident (gkr_protocol.rs:27)
     std::vector<DevBuf>& W = wc->W;
-    ZK_CUDA(cudaMemcpyAsync(W[L].p, inputs, n_inputs * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    if (device_inputs) ZK_CUDA(cudaMemcpyAsync(W[L].p, device_inputs, n_inputs * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
+    else ZK_CUDA(cudaMemcpyAsync(W[L].p, inputs, n_inputs * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
     for (uint32_t li = L; li-- > 0;) {
         const uint64_t n_out = 1ull << wc->bits[li];
         if (wc->layers[li].n_gates / n_out >= 64) {   // heavy fan-in: a block per output

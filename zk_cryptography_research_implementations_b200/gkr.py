@@ -115,7 +115,10 @@ class WideCircuit:
 def prove_wide(ctx: Context, circuit: WideCircuit, inputs, flags: int = 0, want_output: bool = True) -> Proof:
     """gkr_protocol::prove with the sparse two-phase layer sumcheck (same proof as `prove` on reference shapes)."""
     lib = ctx.lib
-    inputs = as_elems(inputs).reshape(-1, 4)
+    from .core import DeviceTable
+    resident = isinstance(inputs, DeviceTable)      # input layer already in HBM: no host-to-device copy in the call
+    if not resident:
+        inputs = as_elems(inputs).reshape(-1, 4)
     L = circuit.n_layers
     R = circuit.total_rounds()
     n_out = 1 << circuit.layer_bits[0]
@@ -126,8 +129,12 @@ def prove_wide(ctx: Context, circuit: WideCircuit, inputs, flags: int = 0, want_
     chal = np.zeros((R, 4), dtype=np.uint64)
     wb = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
     wc = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
-    ctx.check(lib.zk_gkr_prove_wide(ctx.h, circuit.h, _ptr(inputs), inputs.shape[0], _ptr(output) if want_output else None,
-                                    _ptr(claimed), _ptr(claims), _ptr(coeffs), _ptr(chal), _ptr(wb), _ptr(wc), flags))
+    if resident:
+        ctx.check(lib.zk_gkr_prove_wide_device(ctx.h, circuit.h, inputs.h, _ptr(output) if want_output else None,
+                                               _ptr(claimed), _ptr(claims), _ptr(coeffs), _ptr(chal), _ptr(wb), _ptr(wc), flags))
+    else:
+        ctx.check(lib.zk_gkr_prove_wide(ctx.h, circuit.h, _ptr(inputs), inputs.shape[0], _ptr(output) if want_output else None,
+                                        _ptr(claimed), _ptr(claims), _ptr(coeffs), _ptr(chal), _ptr(wb), _ptr(wc), flags))
     proofs, o = [], 0
     for i in range(L):
         r = 2 * circuit.layer_bits[i + 1]
