@@ -151,7 +151,41 @@ template <int FID> static int run_round_accs() {
 
 // ---------------------------------------------------------------------------------------------------------------
 // The device transcript and the whole tail body (tail.cuh) under a one-thread host policy, against the oracle.
+// 32 lanes of a warp as an array: the host stand-in for one-value-per-thread registers, so that warp_keccak_f1600
+// (dev_transcript.cuh) runs here exactly as written
+struct LaneVec { uint32_t v[32]; };
+#define LV_BIN(OP) \
+    static LaneVec operator OP(const LaneVec& a, const LaneVec& b) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] OP b.v[i]; return r; } \
+    static LaneVec operator OP(const LaneVec& a, uint32_t b) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] OP b; return r; }
+LV_BIN(^) LV_BIN(&) LV_BIN(|) LV_BIN(+)
+#undef LV_BIN
+static LaneVec operator>>(const LaneVec& a, int n) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] >> n; return r; }
+static LaneVec operator~(const LaneVec& a) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = ~a.v[i]; return r; }
+// (global namespace, next to LaneVec: found by argument-dependent lookup from the template in dev_transcript.cuh)
+static LaneVec wk_shfl(const LaneVec& v, const LaneVec& src) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = v.v[src.v[i] & 31]; return r; }
+static uint32_t funnel1(uint32_t lo, uint32_t hi, uint32_t n) { n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi; }
+static LaneVec wk_funnel_l(const LaneVec& lo, const LaneVec& hi, const LaneVec& n) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = funnel1(lo.v[i], hi.v[i], n.v[i]); return r; }
+static LaneVec wk_funnel_l(const LaneVec& lo, const LaneVec& hi, uint32_t n) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = funnel1(lo.v[i], hi.v[i], n); return r; }
+static LaneVec wk_lane0_mask(const LaneVec&) { LaneVec r; for (int i = 0; i < 32; ++i) r.v[i] = i == 0 ? 0xffffffffu : 0u; return r; }
+static void lanes_permute(uint64_t a[25]) {   // what CudaExec::permute does, on the lane array
+    LaneVec lo, hi, A, B;
+    for (int i = 0; i < 32; ++i) { uint64_t w = i < 25 ? a[i] : 0x1111111111111111ull * i; lo.v[i] = (uint32_t)w; hi.v[i] = (uint32_t)(w >> 32); A.v[i] = zk::kWkA[i]; B.v[i] = zk::kWkB[i]; }
+    zk::warp_keccak_f1600<LaneVec>(lo, hi, A, B);
+    for (int i = 0; i < 25; ++i) a[i] = (uint64_t)lo.v[i] | ((uint64_t)hi.v[i] << 32);
+}
+
 struct HostExec {
+    int lane() const { return 0; }
+    int warp() const { return 0; }
+    void permute(uint64_t* s) const { lanes_permute(s); }
+    void finalize(const uint64_t* s, uint32_t pos, uint64_t* digest) const {
+        uint64_t a[25];
+        memcpy(a, s, sizeof a);
+        a[pos >> 3] ^= 0x01ull << (8 * (pos & 7));
+        a[16] ^= 0x8000000000000000ull;
+        lanes_permute(a);
+        memcpy(digest, a, 32);
+    }
     int tid() const { return 0; }
     int nthreads() const { return 1; }
     void sync() const {}
@@ -163,6 +197,36 @@ struct HostExec {
 
 static int test_dev_sponge() {
     int bad = 0;
+    // the warp-wide permutation (lane array) against the one-thread permutation
+    for (int it = 0; it < 200; ++it) {
+        uint64_t a[25], b[25];
+        for (int i = 0; i < 25; ++i) a[i] = b[i] = it == 0 ? 0 : rnd();
+        zk::keccak_f1600(a);
+        lanes_permute(b);
+        if (memcmp(a, b, sizeof a)) { ++bad; printf("warp keccak differs from the scalar permutation (it=%d)\n", it); break; }
+    }
+    // cooperative absorb / sample (what the tail kernel's warp 0 runs) at every alignment against the oracle
+    for (int prefix = 0; prefix < 140; ++prefix) {
+        std::vector<uint8_t> data(prefix + 8 * 64);
+        for (auto& x : data) x = (uint8_t)rnd();
+        zk::KeccakState st; memset(&st, 0, sizeof st);
+        zko_transcript* ot = zko_transcript_new();
+        for (int i = 0; i < prefix; ++i) zk::sponge_absorb_byte(&st, data[i]);
+        zko_transcript_append(ot, data.data(), prefix);
+        HostExec ex;
+        uint32_t pos = st.pos;
+        for (int rep = 0; rep < 4; ++rep) {
+            uint64_t words[16]; memcpy(words, &data[prefix + 128 * rep], 128);
+            int nw = 12 + rep;   // 96 .. 120 bytes per step
+            zk::coop_absorb_words(ex, st.s, pos, words, nw);
+            zko_transcript_append(ot, &data[prefix + 128 * rep], 8 * nw);
+            uint64_t dg[4]; uint8_t want[32];
+            zk::coop_sample(ex, st.s, pos, dg);
+            zko_transcript_sample(ot, want);
+            if (memcmp(dg, want, 32)) { ++bad; printf("cooperative sponge digest mismatch prefix=%d rep=%d\n", prefix, rep); }
+        }
+        zko_transcript_free(ot);
+    }
     // byte-wise and word-wise absorbs at every alignment against the oracle's Keccak / transcript
     for (int prefix = 0; prefix < 300; prefix += (prefix < 20 ? 1 : 37)) {
         std::vector<uint8_t> data(prefix + 8 * 40);

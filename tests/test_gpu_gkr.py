@@ -185,3 +185,32 @@ def test_wide_prover_on_general_shapes(zk, co, ctx_for, bits):
                   [c for (_, _, ch) in want.sumcheck_proofs for c in ch],
                   [cl for (cl, _, _) in want.sumcheck_proofs], want.wb_evaluations, want.wc_evaluations, want.claimed_sum)
     assert zk.fe_to_ints(fid, proof.circuit_output) == want.circuit_output
+
+
+def test_wide_prover_reduction_layer_with_heavy_fan_in(zk, co, ctx_for):
+    """the shape of bench.py's synthetic wide circuit in miniature: layer 0 folds all 2^7 wires into TWO outputs (64 gates
+    each: the sliced evaluation kernels), the layer below is full width; checked against the generalised dense Python model"""
+    import pyoracle as po
+    from zk_cryptography_research_implementations_b200 import gkr
+    fid = 0
+    p = po.P["BN254_FQ"]
+    rng = random.Random(4242)
+    w = 7
+    bits = [1, w, w]
+    layer0 = [(g, rng.randrange(1 << w), g & 1, rng.randrange(2)) for g in range(1 << w)]
+    layer1 = [(rng.randrange(1 << w), rng.randrange(1 << w), g, rng.randrange(2)) for g in range(1 << w)]
+    layers = [layer0, layer1]
+    inputs = [rng.randrange(p) for _ in range(1 << w)]
+    want = po.gkr_prove_general([[po.Gate(*g) for g in l] for l in layers], bits, inputs, p)
+    ctx = ctx_for(fid)
+    for tail_log in (13, 0):
+        ctx.set_tail_log(tail_log)
+        try:
+            proof = gkr.prove_wide(ctx, gkr.WideCircuit(ctx, bits, layers), zk.fe_from_ints(fid, inputs))
+        finally:
+            ctx.set_tail_log(13)
+        _compare_wide(zk, fid, proof,
+                      [c for (_, polys, _) in want.sumcheck_proofs for poly in polys for c in poly],
+                      [c for (_, _, ch) in want.sumcheck_proofs for c in ch],
+                      [cl for (cl, _, _) in want.sumcheck_proofs], want.wb_evaluations, want.wc_evaluations, want.claimed_sum)
+        assert zk.fe_to_ints(fid, proof.circuit_output) == want.circuit_output

@@ -78,11 +78,14 @@ def test_f_times_g_hand_over(zk, co, ctx_for, restore_tail, fid):
         ctx.set_tail_log(13)
         ctx.reset_stats()
         c2 = np.zeros((n, 3, 4), dtype=np.uint64); ch2 = np.zeros((n, 4), dtype=np.uint64); fin2 = np.zeros((2, 4), dtype=np.uint64)
-        ctx.check(ctx.lib.zk_prove_product_host(ctx.h, _ptr(host), 1, 2, 1 << n, _ptr(claimed), Transcript().h, _ptr(c2), _ptr(ch2), _ptr(fin2), 16))
+        tr = Transcript()    # keep it alive across the call (a temporary would be freed before the library uses it)
+        ctx.check(ctx.lib.zk_prove_product_host(ctx.h, _ptr(host), 1, 2, 1 << n, _ptr(claimed), tr.h, _ptr(c2), _ptr(ch2), _ptr(fin2), 16))
         assert np.array_equal(c2, coeffs) and np.array_equal(fin2, fin[0])
         assert ctx.stats()["round_launches"] == n            # one launch per round
         ctx.reset_stats()
-        ctx.check(ctx.lib.zk_prove_product_host(ctx.h, _ptr(host), 1, 2, 1 << n, _ptr(claimed), Transcript().h, _ptr(c2), _ptr(ch2), _ptr(fin2), 0))
+        tr = Transcript()
+        ctx.check(ctx.lib.zk_prove_product_host(ctx.h, _ptr(host), 1, 2, 1 << n, _ptr(claimed), tr.h, _ptr(c2), _ptr(ch2), _ptr(fin2), 0))
+        assert np.array_equal(c2, coeffs) and np.array_equal(fin2, fin[0])
         # host-driven while the tables to fold are longer than 2^13 (round 0 and rounds 1..n-13), then ONE tail launch
         assert ctx.stats()["round_launches"] == (1 if n <= 13 else n - 11)
 

@@ -78,7 +78,7 @@ struct zk_wide_circuit {
     int device = 0;
     // prover workspace, allocated with the circuit so a prove never calls cudaMalloc/cudaFree:
     std::vector<DevBuf> W;        // all layer values (Circuit::evaluate result), resident
-    DevBuf wtab, eqa, eqb, h1, h2, Wc, factors, half_hi, half_lo;
+    DevBuf wtab, eqa, h1, h2, Wc, half_hi, half_lo, half_hi2, half_lo2;
 };
 
 namespace {
@@ -87,33 +87,6 @@ inline int grid_of(const zk_ctx* ctx, uint64_t work, int bps) {
     if (blocks > cap) blocks = cap;
     if (ctx->grid_cap > 0 && blocks > (uint64_t)ctx->grid_cap) blocks = ctx->grid_cap;
     return (int)(blocks < 1 ? 1 : blocks);
-}
-
-// out[a] = prod_v (bit_v(a) ? r_v : 1 - r_v), variable 0 = most significant bit of a.
-// factors[2 v] = 1 - r_v, factors[2 v + 1] = r_v (device memory)
-template <int FID> __global__ void __launch_bounds__(kThreads) eq_kernel(Fe* out, uint32_t nbits, const Fe* factors, Fe scale) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = 1ull << nbits;
-    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride) {
-        Fe acc = scale;
-        for (uint32_t v = 0; v < nbits; ++v) {
-            uint32_t bit = (uint32_t)(a >> (nbits - 1 - v)) & 1u;
-            Fe fct = factors[2 * v + bit];
-            Fp<FID>::mont_mul(acc, acc, fct);
-        }
-        st256(out + a, acc);
-    }
-}
-
-// out[a] = hi[a >> lo_bits] * lo[a & (2^lo_bits - 1)]: eq over k variables from two half-width eq tables, one
-// multiply per entry (the direct product above costs k multiplies per entry)
-template <int FID>
-__global__ void __launch_bounds__(kThreads) eq_outer_kernel(Fe* out, const Fe* hi, const Fe* lo, uint32_t lo_bits, uint64_t n) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = (1ull << lo_bits) - 1;
-    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride) {
-        Fe h = hi[a >> lo_bits], l = lo[a & mask], o;
-        Fp<FID>::mont_mul(o, h, l);
-        st256(out + a, o);
-    }
 }
 
 // Circuit::evaluate for one layer (arithmetic_circuit.rs:82-97): out[o] = sum over gates with output o of op(in[l], in[r])
@@ -149,6 +122,39 @@ __global__ void __launch_bounds__(kThreads) eval_layer_block_kernel(GateCsr g, c
         }
         block_sum<FID, 1>(acc);
         if (threadIdx.x == 0) st256(out + o, acc[0]);
+    }
+}
+
+// heavy fan-in, few outputs (a reduction layer: 2 outputs collecting 2^21 gates each): every output is cut into S
+// slices, one block per (output, slice) writes a partial sum, sum_slices_kernel adds the S partials.  A block per
+// output alone would leave all but n_out SMs idle.
+template <int FID>
+__global__ void __launch_bounds__(kThreads) eval_layer_slices_kernel(GateCsr g, const Fe* in, Fe* partial, uint64_t n_out, uint32_t S) {
+    for (uint64_t w = blockIdx.x; w < n_out * S; w += gridDim.x) {
+        const uint64_t o = w / S, s = w % S;
+        const uint64_t b = g.off[o], e = g.off[o + 1], chunk = (e - b + S - 1) / S;
+        const uint64_t lo = b + s * chunk, hi = lo + chunk < e ? lo + chunk : e;
+        Fe acc[1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[0].v[k] = 0;
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            Fe l = ld256(in + g.x[i]), r = ld256(in + g.y[i]), v;
+            if (g.op[i] == 0) Fp<FID>::add(v, l, r);
+            else Fp<FID>::mont_mul(v, l, r);
+            Fp<FID>::add(acc[0], acc[0], v);
+        }
+        block_sum<FID, 1>(acc);
+        if (threadIdx.x == 0) st256(partial + w, acc[0]);
+    }
+}
+template <int FID> __global__ void __launch_bounds__(kThreads) sum_slices_kernel(const Fe* partial, Fe* out, uint64_t n_out, uint32_t S) {
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += (uint64_t)gridDim.x * blockDim.x) {
+        Fe acc = ld256(partial + o * S);
+        for (uint32_t s = 1; s < S; ++s) {
+            Fe v = ld256(partial + o * S + s);
+            Fp<FID>::add(acc, acc, v);
+        }
+        st256(out + o, acc);
     }
 }
 
@@ -232,39 +238,92 @@ void free_csr(GateCsr* g) {
     *g = GateCsr();
 }
 
-// factors for eq_kernel from host challenges
-int upload_factors(zk_ctx* ctx, const std::vector<HFe>& r, Fe* dst) {
-    const HostField& f = ctx->field;
-    std::vector<HFe> fac(2 * r.size());
-    for (size_t v = 0; v < r.size(); ++v) {
-        fac[2 * v] = f.sub(f.one(), r[v]);
-        fac[2 * v + 1] = r[v];
+// ---- eq tables.  w(a) = s1 eq(r1, a) [+ s2 eq(r2, a)] over k variables is built from half-width tables
+// (eq over the leading kh and the trailing kl variables): one launch fills the two halves of a term straight from
+// factors passed as kernel arguments (no staging copy, no stream synchronisation), one launch forms the outer
+// products and adds the two terms.  A direct product would cost k multiplies per entry; this costs one per term.
+constexpr int kEqHalfBits = 15;   // layers are at most 2^30 wide
+struct EqHalfArgs {
+    Fe* out[2];                   // hi table (scaled), lo table
+    uint32_t bits[2];
+    Fe factors[2][2 * kEqHalfBits];   // [half][2 v + bit]: 1 - r_v, r_v
+    Fe scale;                     // multiplies the hi table
+};
+template <int FID> __global__ void __launch_bounds__(kThreads) eq_halves_kernel(const __grid_constant__ EqHalfArgs a) {
+    const int h = blockIdx.y;
+    const uint32_t nbits = a.bits[h];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n = 1ull << nbits;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fe acc;
+        if (h == 0) acc = a.scale;
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc.v[k] = FieldParams<FID>::r2(k);
+            Fe one;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) one.v[k] = (k == 0);
+            Fp<FID>::mont_mul(acc, acc, one);   // R^2 / R = R: the Montgomery one
+        }
+        for (uint32_t v = 0; v < nbits; ++v) {
+            const uint32_t bit = (uint32_t)(i >> (nbits - 1 - v)) & 1u;
+            Fp<FID>::mont_mul(acc, acc, a.factors[h][2 * v + bit]);
+        }
+        st256(a.out[h] + i, acc);
     }
-    ZK_CUDA(cudaMemcpyAsync(dst, fac.data(), fac.size() * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
-    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+// out[a] = hi1[a >> lo_bits] lo1[a & mask] (+ hi2[..] lo2[..])
+template <int FID, bool TWO>
+__global__ void __launch_bounds__(kThreads) eq_outer2_kernel(Fe* out, const Fe* hi1, const Fe* lo1, const Fe* hi2, const Fe* lo2, uint32_t lo_bits, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = (1ull << lo_bits) - 1;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride) {
+        Fe h = hi1[a >> lo_bits], l = lo1[a & mask], o;
+        Fp<FID>::mont_mul(o, h, l);
+        if (TWO) {
+            Fe h2 = hi2[a >> lo_bits], l2 = lo2[a & mask], o2;
+            Fp<FID>::mont_mul(o2, h2, l2);
+            Fp<FID>::add(o, o, o2);
+        }
+        st256(out + a, o);
+    }
+}
+
+int launch_eq_halves(zk_ctx* ctx, const std::vector<HFe>& r, const HFe& scale, Fe* hi, Fe* lo, uint32_t kh, uint32_t kl) {
+    const HostField& f = ctx->field;
+    EqHalfArgs a;
+    a.out[0] = hi; a.out[1] = lo;
+    a.bits[0] = kh; a.bits[1] = kl;
+    for (uint32_t v = 0; v < kh + kl; ++v) {
+        const int h = v < kh ? 0 : 1;
+        const uint32_t j = v < kh ? v : v - kh;
+        HFe omr = f.sub(f.one(), r[v]);
+        memcpy(a.factors[h][2 * j].v, omr.l, 32);
+        memcpy(a.factors[h][2 * j + 1].v, r[v].l, 32);
+    }
+    memcpy(a.scale.v, scale.l, 32);
+    const uint64_t widest = 1ull << (kh > kl ? kh : kl);
+    dim3 grid((unsigned)grid_of(ctx, widest, 4), 2);
+    ZK_FID_SWITCH(ctx, (eq_halves_kernel<FID><<<grid, kThreads, 0, ctx->stream>>>(a)));
+    ctx->launches++;
+    ZK_CUDA(cudaGetLastError());
     return ZK_OK;
 }
-// out[a] = scale * eq(r, a) for all a in {0,1}^k (variable 0 = most significant bit)
-int build_eq(zk_ctx* ctx, zk_wide_circuit* wc, const std::vector<HFe>& r, const HFe& scale, Fe* out) {
-    const uint32_t k = (uint32_t)r.size(), kh = k / 2, kl = k - kh;
-    int rc = upload_factors(ctx, r, wc->factors.p);
+// out[a] = s1 eq(r1, a) + s2 eq(r2, a) for all a in {0,1}^k (variable 0 = most significant bit); r2 == nullptr: one term
+int build_eq2(zk_ctx* ctx, zk_wide_circuit* wc, const std::vector<HFe>& r1, const HFe& s1, const std::vector<HFe>* r2, const HFe& s2, Fe* out) {
+    const uint32_t k = (uint32_t)r1.size(), kh = k / 2, kl = k - kh;
+    if (kl > (uint32_t)kEqHalfBits) return fail(ctx, ZK_ERR_ARG, "layer wider than 2^30");
+    int rc = launch_eq_halves(ctx, r1, s1, wc->half_hi.p, wc->half_lo.p, kh, kl);
     if (rc) return rc;
-    Fe scale_fe, one_fe;
-    HFe one = ctx->field.one();
-    memcpy(scale_fe.v, scale.l, 32);
-    memcpy(one_fe.v, one.l, 32);
-    if (k <= 8) {
-        ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(out, k, wc->factors.p, scale_fe)));
-        ctx->launches++;
+    if (r2) {
+        rc = launch_eq_halves(ctx, *r2, s2, wc->half_hi2.p, wc->half_lo2.p, kh, kl);
+        if (rc) return rc;
+        ZK_FID_SWITCH(ctx, (eq_outer2_kernel<FID, true><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(
+                                out, wc->half_hi.p, wc->half_lo.p, wc->half_hi2.p, wc->half_lo2.p, kl, 1ull << k)));
     } else {
-        ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, 1ull << kh, 4), kThreads, 0, ctx->stream>>>(wc->half_hi.p, kh, wc->factors.p, scale_fe)));
-        ZK_FID_SWITCH(ctx, (eq_kernel<FID><<<grid_of(ctx, 1ull << kl, 4), kThreads, 0, ctx->stream>>>(wc->half_lo.p, kl, wc->factors.p + 2 * kh, one_fe)));
-        ZK_FID_SWITCH(ctx, (eq_outer_kernel<FID><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(out, wc->half_hi.p, wc->half_lo.p, kl, 1ull << k)));
-        ctx->launches += 3;
+        ZK_FID_SWITCH(ctx, (eq_outer2_kernel<FID, false><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(
+                                out, wc->half_hi.p, wc->half_lo.p, nullptr, nullptr, kl, 1ull << k)));
     }
+    ctx->launches++;
     ZK_CUDA(cudaGetLastError());
-    // `factors` is reused by the next build_eq: make sure the kernels above have consumed it
-    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZK_OK;
 }
 }  // namespace
@@ -302,12 +361,12 @@ extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint
         wc->W.resize(n_layers + 1);
         cudaError_t e = cudaSuccess;
         for (uint32_t li = 0; li <= n_layers && e == cudaSuccess; ++li) e = wc->W[li].alloc(1ull << wc->bits[li]);
-        DevBuf* bufs[] = {&wc->wtab, &wc->eqa, &wc->eqb, &wc->h1, &wc->h2, &wc->Wc};
+        DevBuf* bufs[] = {&wc->wtab, &wc->eqa, &wc->h1, &wc->h2, &wc->Wc};
         for (DevBuf* b : bufs)
             if (e == cudaSuccess) e = b->alloc(maxn);
-        if (e == cudaSuccess) e = wc->factors.alloc(2 * 32);
-        if (e == cudaSuccess) e = wc->half_hi.alloc(1ull << 16);
-        if (e == cudaSuccess) e = wc->half_lo.alloc(1ull << 16);
+        DevBuf* halves[] = {&wc->half_hi, &wc->half_lo, &wc->half_hi2, &wc->half_lo2};   // half_hi doubles as the slice scratch of evaluate
+        for (DevBuf* b : halves)
+            if (e == cudaSuccess) e = b->alloc(1ull << 16);
         if (e != cudaSuccess) {
             ctx->err = std::string("cudaMalloc (GKR workspace): ") + cudaGetErrorString(e);
             zk_wide_circuit_free(ctx, wc);
@@ -377,8 +436,14 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
     else ZK_CUDA(cudaMemcpyAsync(W[L].p, inputs, n_inputs * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
     for (uint32_t li = L; li-- > 0;) {
         const uint64_t n_out = 1ull << wc->bits[li];
-        if (wc->layers[li].n_gates / n_out >= 64) {   // heavy fan-in: a block per output
-            int blocks = (int)std::min<uint64_t>(n_out, (uint64_t)ctx->sm_count * 4);
+        const uint64_t full_grid = (uint64_t)ctx->sm_count * 4;
+        if (wc->layers[li].n_gates / n_out >= 64 && n_out * 2 <= full_grid) {   // heavy fan-in, few outputs: slices
+            const uint32_t S = (uint32_t)std::min<uint64_t>(full_grid / n_out, (wc->layers[li].n_gates / n_out + kThreads - 1) / kThreads);
+            ZK_FID_SWITCH(ctx, (eval_layer_slices_kernel<FID><<<(int)(n_out * S), kThreads, 0, ctx->stream>>>(wc->layers[li].by_out, W[li + 1].p, wc->half_hi.p, n_out, S)));
+            ZK_FID_SWITCH(ctx, (sum_slices_kernel<FID><<<1, kThreads, 0, ctx->stream>>>(wc->half_hi.p, W[li].p, n_out, S)));
+            ctx->launches++;
+        } else if (wc->layers[li].n_gates / n_out >= 64) {   // heavy fan-in, many outputs: a block per output
+            int blocks = (int)std::min<uint64_t>(n_out, full_grid);
             ZK_FID_SWITCH(ctx, (eval_layer_block_kernel<FID><<<blocks, kThreads, 0, ctx->stream>>>(wc->layers[li].by_out, W[li + 1].p, W[li].p, n_out)));
         } else {
             ZK_FID_SWITCH(ctx, (eval_layer_kernel<FID><<<grid_of(ctx, n_out, 4), kThreads, 0, ctx->stream>>>(wc->layers[li].by_out, W[li + 1].p, W[li].p, n_out)));
@@ -411,7 +476,7 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
     HFe claim = w0[0];
 
     // ---- scratch tables
-    DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &eqb = wc->eqb, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
+    DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
 
 
     HFe alpha = f.zero(), beta = f.zero();
@@ -426,12 +491,9 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         int rc;
         // ---- w(a): eq(r_a, .) at the output layer, alpha eq(r_b, .) + beta eq(r_c, .) below
         if (li == 0) {
-            if ((rc = build_eq(ctx, wc, ra, f.one(), wtab.p))) return rc;
+            if ((rc = build_eq2(ctx, wc, ra, f.one(), nullptr, f.one(), wtab.p))) return rc;
         } else {
-            if ((rc = build_eq(ctx, wc, rb, alpha, eqa.p))) return rc;
-            if ((rc = build_eq(ctx, wc, rcv, beta, eqb.p))) return rc;
-            ZK_FID_SWITCH(ctx, (ew_kernel<FID, EW_ADD><<<grid_of(ctx, na, 4), kThreads, 0, ctx->stream>>>(eqa.p, eqb.p, wtab.p, na)));
-            ctx->launches++;
+            if ((rc = build_eq2(ctx, wc, rb, alpha, &rcv, beta, wtab.p))) return rc;
         }
         mark(1);
         // ---- phase 1 tables and sumcheck over b
@@ -460,7 +522,7 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         const HFe Wu = fin1[1];                                                                           // W(r_b)
         std::vector<HFe> u(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + m);
         // ---- phase 2 tables and sumcheck over c
-        if ((rc = build_eq(ctx, wc, u, f.one(), eqa.p))) return rc;
+        if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
         Fe Wu_fe;
         memcpy(Wu_fe.v, Wu.l, 32);
         ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_fe, h1.p, h2.p, nm)));

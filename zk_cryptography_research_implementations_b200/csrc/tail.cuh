@@ -11,7 +11,7 @@
 // (the GKR prover keeps absorbing after every layer sumcheck).
 //
 // The body is written against an `Exec` policy (thread id, barrier, block-wide column sums, 256-bit memory
-// access).  The kernel instantiates it with the CUDA policy; tests/host_emu instantiates it with a one-thread
+// access, the warp-wide Keccak permutation).  The kernel instantiates it with the CUDA policy; tests/host_emu instantiates it with a one-thread
 // host policy and checks whole tails against the oracle's provers without a GPU.
 #pragma once
 #include "dev_transcript.cuh"
@@ -49,6 +49,7 @@ struct TailShared {
     KeccakState sponge;
     Fe evals[kMaxEvals];
     uint64_t words[kMaxEvals][4];   // what the transcript absorbs this round, as little-endian words of the byte stream
+    uint64_t digest[4];
     Fe r_plain;
     unsigned long long tot[kMaxCols];
 };
@@ -159,12 +160,14 @@ ZK_DEV void sumcheck_tail_body(const TailArgs& a, TailShared& sh, Exec& ex) {
             }
         }
         ex.sync();
-        if (tid == 0) {
-            for (int i = 0; i < NE; ++i)
-                for (int w = 0; w < 4; ++w) sponge_absorb_word(&sh.sponge, sh.words[i][w]);
-            uint64_t digest[4];
-            sponge_sample(&sh.sponge, digest);
-            TF::challenge_plain(sh.r_plain, digest);
+        if (ex.warp() == 0) {   // the transcript step, one warp: absorb, sample, challenge (dev_transcript.cuh)
+            uint32_t pos = sh.sponge.pos;
+            coop_absorb_words(ex, sh.sponge.s, pos, &sh.words[0][0], NE * 4);
+            coop_sample(ex, sh.sponge.s, pos, sh.digest);
+            if (ex.lane() == 0) {
+                sh.sponge.pos = pos;
+                TF::challenge_plain(sh.r_plain, sh.digest);
+            }
         }
         ex.sync();
         for (int i = tid; i < 9; i += nt) {   // rows of the next fold table, and the challenge as the proof reports it

@@ -9,6 +9,32 @@
 namespace zk {
 
 struct CudaExec {
+    uint32_t wk_a, wk_b;   // this lane's routing words for the warp-wide Keccak (dev_transcript.cuh)
+    __device__ __forceinline__ CudaExec() : wk_a(kWkA[threadIdx.x & 31u]), wk_b(kWkB[threadIdx.x & 31u]) {}
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+    __device__ __forceinline__ int warp() const { return (int)(threadIdx.x >> 5); }
+    // Keccak-f[1600] on a state in shared memory, by the whole (converged) warp
+    __device__ __forceinline__ void permute(uint64_t* s) const {
+        __syncwarp();
+        const int l = lane();
+        const uint64_t a = l < 25 ? s[l] : 0ull;
+        uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+        warp_keccak_f1600<uint32_t>(lo, hi, wk_a, wk_b);
+        if (l < 25) s[l] = (uint64_t)lo | ((uint64_t)hi << 32);
+        __syncwarp();
+    }
+    // Keccak-256 digest of a CLONE of the sponge (pad 0x01 .. 0x80, permute, first four words); s is left untouched
+    __device__ __forceinline__ void finalize(const uint64_t* s, uint32_t pos, uint64_t* digest) const {
+        __syncwarp();
+        const int l = lane();
+        uint64_t a = l < 25 ? s[l] : 0ull;
+        if (l == (int)(pos >> 3)) a ^= 0x01ull << (8 * (pos & 7));
+        if (l == 16) a ^= 0x8000000000000000ull;
+        uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+        warp_keccak_f1600<uint32_t>(lo, hi, wk_a, wk_b);
+        if (l < 4) digest[l] = (uint64_t)lo | ((uint64_t)hi << 32);
+        __syncwarp();
+    }
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
