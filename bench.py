@@ -660,6 +660,22 @@ def run_ours(args, wl):
                 "algorithmic_bytes_per_step_per_rank": st["round_bytes"] / max(args.steps, 1),
                 "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)}
     launches = st["launches"]
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (one fold_evals launch of the f*g
+    # workload, old table length 2^25: 48 * T * 2^25 algorithmic bytes) -- bytes moved per launch, to set against them
+    if P == 1 and D == 2:
+        cap = os.path.join(ROOT, "profiles", "r01b_fold_evals_2p27_ncu_full_summary.csv")
+        try:
+            vals = {}
+            import csv
+            for row in csv.reader(open(cap)):
+                if len(row) == 4 and row[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    vals[row[1]] = float(row[3]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[row[2]]
+            if len(vals) == 2:
+                roofline["traffic"] = sum(vals.values())
+                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fold_evals_kernel<BN254_FQ,1,2> launch folding 2 x 2^25 "
+                                            "entries (ncu --set full, %s): algorithmic bytes of that launch %.4g" % (os.path.relpath(cap, ROOT), 48.0 * 2 * (1 << 25)))
+        except OSError:
+            pass
 
     # ---- integer-multiply ceiling (register-resident probe, same clocks)
     integer = {}

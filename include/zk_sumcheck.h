@@ -35,8 +35,8 @@ enum {
     ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
     ZK_FLAG_HOST_ROUNDS = 16   /* keep every round on the host-driven path: one kernel + one host Fiat-Shamir step per
-                                  round.  Default: once the tables are down to 2^tail_log entries (zk_ctx_set_tail_log,
-                                  default 13) ONE single-block launch runs all remaining rounds with the transcript on the
+                                  round.  Default: once tables x entries <= 2^tail_log (zk_ctx_set_tail_log, default 13)
+                                  ONE single-block launch runs all remaining rounds with the transcript on the
                                   device (transcripts/.../fiat_shamir_transcript.rs:12-43 restated in csrc/dev_transcript.cuh);
                                   the proof is identical either way */
 };
@@ -60,7 +60,8 @@ int  zk_ctx_synchronize(zk_ctx *);
 int  zk_ctx_set_profiling(zk_ctx *, int on);
 int  zk_ctx_reset_stats(zk_ctx *);
 int  zk_ctx_get_stats(zk_ctx *, uint64_t *launches, uint64_t *round_launches, double *round_ms, double *round_bytes);
-/* Device tail: a sumcheck whose tables hold at most 2^tail_log entries finishes in ONE single-block launch that runs
+/* Device tail: a sumcheck whose tables together hold at most 2^tail_log entries (one table: 2^tail_log; the three
+ * tables of a GKR phase: 2^(tail_log-2) each, rounded down) finishes in ONE single-block launch that runs
  * every remaining round -- sums, fold, Lagrange coefficients (dense_univariate.rs:74-127), transcript absorb and
  * challenge (fiat_shamir_transcript.rs:22-43) -- on the GPU.  Default 13 (env ZKB200_TAIL_LOG); 0 keeps every round
  * host-driven; at most 16.  Proofs are bit-identical for every setting. */

@@ -86,8 +86,8 @@ def test_f_times_g_hand_over(zk, co, ctx_for, restore_tail, fid):
         tr = Transcript()
         ctx.check(ctx.lib.zk_prove_product_host(ctx.h, _ptr(host), 1, 2, 1 << n, _ptr(claimed), tr.h, _ptr(c2), _ptr(ch2), _ptr(fin2), 0))
         assert np.array_equal(c2, coeffs) and np.array_equal(fin2, fin[0])
-        # host-driven while the tables to fold are longer than 2^13 (round 0 and rounds 1..n-13), then ONE tail launch
-        assert ctx.stats()["round_launches"] == (1 if n <= 13 else n - 11)
+        # two tables: host-driven while they are longer than 2^13 / 2 (round 0 and rounds 1..n-12), then ONE tail launch
+        assert ctx.stats()["round_launches"] == (1 if n <= 12 else n - 10)
 
 
 @pytest.mark.parametrize("fid", [0, 1, 2])

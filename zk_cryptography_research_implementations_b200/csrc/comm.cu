@@ -262,7 +262,7 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
             sharded = false;
         }
         TablePtrs tp = ptrs_of(sp);
-        if (!sharded && tail_applies(ctx, sp->len, flags)) {   // collapsed and small: the rest in one launch per rank
+        if (!sharded && tail_applies(ctx, sp->len, P * D, flags)) {   // collapsed and small: the rest in one launch per rank
             rc = run_tail(ctx, tp, P, D, 0, kTailProduct, sp->len, need_plain_evals ? nullptr : &r, tr->t,
                           coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
             if (rc) return rc;
@@ -348,7 +348,7 @@ extern "C" int zk_prove_basic_sharded(zk_ctx* ctx, zk_table* local, zk_transcrip
             sharded = false;
         }
         TablePtrs tp = ptrs_of(&sp);
-        if (k > 0 && !sharded && tail_applies(ctx, sp.len, flags)) {   // the rest in one launch (the claimed sum is in)
+        if (k > 0 && !sharded && tail_applies(ctx, sp.len, 1, flags)) {   // the rest in one launch (the claimed sum is in)
             rc = run_tail(ctx, tp, 1, 1, 0, kTailPlain, sp.len, plain ? nullptr : &r, tr->t, round_polys + (size_t)k * 8,
                           challenges ? challenges + (size_t)k * 4 : nullptr, final_value);
             if (rc) return rc;

@@ -165,6 +165,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     zk_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pool) cudaFree(ctx->pool);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->gacc);
     cudaFree(ctx->ticket);
@@ -211,6 +212,19 @@ int ensure_scratch(zk_ctx* ctx, size_t bytes) {
     }
     ZK_CUDA(cudaMalloc(&ctx->scratch, bytes));
     ctx->scratch_bytes = bytes;
+    return ZK_OK;
+}
+
+int ensure_pool(zk_ctx* ctx, size_t bytes) {
+    if (ctx->pool_bytes >= bytes) return ZK_OK;
+    if (ctx->pool) {
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        ZK_CUDA(cudaFree(ctx->pool));
+        ctx->pool = nullptr;
+        ctx->pool_bytes = 0;
+    }
+    ZK_CUDA(cudaMalloc(&ctx->pool, bytes));
+    ctx->pool_bytes = bytes;
     return ZK_OK;
 }
 
@@ -412,8 +426,12 @@ int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, co
     return post_launch(ctx);
 }
 
-bool tail_applies(const zk_ctx* ctx, uint64_t len, uint32_t flags) {
-    return !(flags & ZK_FLAG_HOST_ROUNDS) && ctx->tail_log > 0 && len >= 2 && len <= (1ull << ctx->tail_log);
+// One block folds ~256 pairs of ONE table per microsecond, a host-driven round costs 16-23 us: the hand-over pays once
+// tables x entries fits 2^tail_log (profiles/r01b: 2^13 entries for one table, 2^11 for the three of a GKR phase).
+bool tail_applies(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags) {
+    if ((flags & ZK_FLAG_HOST_ROUNDS) || ctx->tail_log <= 0 || len < 2) return false;
+    uint64_t budget = (1ull << ctx->tail_log) / (uint64_t)(tables < 1 ? 1 : tables);
+    return len <= budget;
 }
 
 int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
@@ -693,7 +711,7 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
     for (uint32_t k = 0; k < n; ++k) {                                           // :37
         const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
         int rc;
-        if (tail_applies(ctx, sp->len, flags)) {   // rounds k..n-1 and the last fold in one launch, transcript on the device
+        if (tail_applies(ctx, sp->len, T, flags)) {   // rounds k..n-1 and the last fold in one launch, transcript on the device
             rc = run_tail(ctx, tp, P, D, NL, kTailProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
                           coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
             if (rc) return rc;
@@ -773,7 +791,7 @@ extern "C" int zk_prove_basic_device(zk_ctx* ctx, zk_table* t, uint64_t claimed_
     tr.append_be(f, claimed);                                                    // :40-41
     memcpy(claimed_sum, claimed.l, 32);
     for (uint32_t k = 0; k < n; ++k) {                                           // :46
-        if (k > 0 && tail_applies(ctx, t->len, flags)) {   // rounds k..n-1 and the last fold in one launch
+        if (k > 0 && tail_applies(ctx, t->len, 1, flags)) {   // rounds k..n-1 and the last fold in one launch
             uint64_t* chal = challenges ? challenges + (size_t)k * 4 : nullptr;
             rc = run_tail(ctx, tp, 1, 1, 0, kTailPlain, t->len, &r, tr, round_polys + (size_t)k * 8, chal, final_value);
             if (rc) return rc;

@@ -41,6 +41,10 @@ struct zk_ctx {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     void* pinned = nullptr;
+    // table pool of the dense GKR prover (gkr.cu): kept across proves -- a 2 GiB cudaMalloc/cudaFree per call costs
+    // milliseconds and varies from call to call
+    void* pool = nullptr;
+    size_t pool_bytes = 0;
     // accounting
     bool profiling = false;
     uint64_t launches = 0, round_launches = 0;

@@ -57,11 +57,6 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Fe* table, const uint
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st256(table + pos[i], val[i]);
 }
 
-struct DevPool {   // one allocation for all per-layer tables of a prove (cudaMalloc/cudaFree per layer cost more than the kernels)
-    Fe* p = nullptr;
-    ~DevPool() { if (p) cudaFree(p); }
-};
-
 // zero a table and scatter (position -> value) pairs with unique positions
 int fill_sparse(zk_ctx* ctx, zk_table* t, const std::map<uint64_t, HFe>& entries) {
     ZK_CUDA(cudaMemsetAsync(t->d, 0, (size_t)t->len * sizeof(Fe), ctx->stream));
@@ -171,12 +166,12 @@ extern "C" int zk_gkr_prove(zk_ctx* ctx, const zk_circuit_desc* c, const uint64_
 
     // one pool for the four 4^(i+1)-entry tables and W of the widest layer
     const uint64_t nbc_max = 1ull << (2 * bc_bits(L - 1)), w_max = 1ull << bc_bits(L - 1);
-    DevPool pool;
     ZK_CUDA(cudaSetDevice(ctx->device));
-    ZK_CUDA(cudaMalloc(&pool.p, (size_t)(4 * nbc_max + w_max) * sizeof(Fe)));
+    if ((rc = ensure_pool(ctx, (size_t)(4 * nbc_max + w_max) * sizeof(Fe)))) return rc;   // kept in the context across proves
+    Fe* pool = (Fe*)ctx->pool;
     zk_table view[5];
     for (int i = 0; i < 5; ++i) {
-        view[i].d = pool.p + (size_t)i * nbc_max;
+        view[i].d = pool + (size_t)i * nbc_max;
         view[i].owned = false;
     }
 

@@ -13,6 +13,7 @@ void set_len(zk_sumpoly* sp, uint64_t len);
 int sync_len(zk_ctx* ctx, zk_sumpoly* sp);
 int table_alloc(zk_ctx* ctx, uint64_t n, zk_table** out);
 int ensure_scratch(zk_ctx* ctx, size_t bytes);
+int ensure_pool(zk_ctx* ctx, size_t bytes);   // persistent table pool of the dense GKR prover
 int tensor_into(zk_ctx* ctx, const zk::Fe* wb, const zk::Fe* wc, uint64_t n, zk::Fe* out, int op);
 namespace zk {
 int fetch_result(zk_ctx* ctx, HFe* out, int ne);
@@ -26,7 +27,7 @@ int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, co
 // single-block launch, transcript included; `pending_r` (may be null) is a challenge the tables still have to be
 // folded by.  mode: kTailProduct / kTailPlain.  vals_out receives (D+1) elements per round, chal_out (may be null)
 // one; finals (may be null) the T single entries left.  The tables end with one entry each.
-bool tail_applies(const zk_ctx* ctx, uint64_t len, uint32_t flags);
+bool tail_applies(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags);
 int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
              uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals);
 }
