@@ -377,6 +377,7 @@ def run_mle(args, wl):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_eval = timed(ev, lambda: None)
+    digest = int(np.bitwise_xor.reduce(out)) & 0xFFFFFFFF
     launches = ctx.stats()["launches"]
     # one partial_evaluate of variable 0 (in place: read N, write N/2), table refilled between steps
     r0 = np.ascontiguousarray(rs[0])
@@ -384,6 +385,23 @@ def run_mle(args, wl):
                     lambda: table.regenerate(SEED, 0, m, rank, world))
     clocks = sampler.stop() if sampler else None
     hbm_peak, peak_src = peaks()
+    # --sweep a,b,c: the same two measurements at other table sizes (BASELINE.json configs[4] is a sweep), same context
+    sweep = []
+    for lg in [int(x) for x in args.sweep.split(",") if x] if args.sweep else []:
+        if lg == log2 or (1 << lg) < world:
+            continue
+        mm = (1 << lg) // world
+        t2 = ctx.generate(SEED, 0, mm, first=rank, step=world)
+        rs2 = np.ascontiguousarray(ctx.generate(SEED, 99, 64).download()[:lg])
+        ms_e = timed(lambda: ctx.check(lib.zk_mle_evaluate_sharded(ctx.h, t2.h, _ptr(rs2), lg, _ptr(out))), lambda: None)
+        r02 = np.ascontiguousarray(rs2[0])
+        ms_f = timed(lambda: ctx.check(lib.zk_mle_partial_evaluate(ctx.h, t2.h, 0, _ptr(r02))), lambda: t2.regenerate(SEED, 0, mm, rank, world))
+        sweep.append({"log2_entries": lg, "evaluate_ms": ms_e, "evaluate_elements_per_s": (1 << lg) / (ms_e * 1e-3),
+                      "evaluate_frac_hbm": 32.0 * mm / (ms_e * 1e-3) / 1e9 / hbm_peak,
+                      "partial_evaluate_ms": ms_f, "partial_evaluate_elements_per_s": (1 << lg) / (ms_f * 1e-3),
+                      "partial_evaluate_frac_hbm": 48.0 * mm / (ms_f * 1e-3) / 1e9 / hbm_peak,
+                      "l2": "table larger than L2" if mm * 32 > 126e6 else "table fits L2 (timed back to back: L2-resident)"})
+        t2.free()
     if rank == 0:
         ach_eval = 32.0 * m / (ms_eval * 1e-3) / 1e9          # algorithmic: ONE read of the table
         ach_fold = 48.0 * m / (ms_fold * 1e-3) / 1e9
@@ -415,8 +433,8 @@ def run_mle(args, wl):
                                          % ((m - 1) * 84 / 8.86e12 * 1e3, 32.0 * m / (hbm_peak * 1e9) * 1e3, ((m - 1) * 84 / 8.86e12 * 1e3) / ms_eval)},
             "partial_evaluate": {"ms": ms_fold, "elements_per_s": N / (ms_fold * 1e-3), "achieved_GBps": ach_fold, "frac": ach_fold / hbm_peak,
                                  "kernel": "fold0_kernel (read N, write N/2: 48 N bytes)"},
-            "cpu_baseline": cpu, "e2e": None, "gpu_launches": launches, "clocks": clocks,
-            "result_digest": int(np.bitwise_xor.reduce(out)) & 0xFFFFFFFF}), flush=True)
+            "cpu_baseline": cpu, "e2e": None, "gpu_launches": launches, "clocks": clocks, "sweep": sweep,
+            "result_digest": digest}), flush=True)
     barrier()
     ctx.close()
     if world > 1:
@@ -780,6 +798,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
     ap.add_argument("--nccl-exchange", action="store_true", dest="nccl_exchange",
                     help="per-round partial exchange with ncclAllGather instead of the shared-memory mailboxes")
+    ap.add_argument("--sweep", default="", help="mle workload: comma-separated extra log2 sizes measured in the same run")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
