@@ -214,3 +214,46 @@ def test_wide_prover_reduction_layer_with_heavy_fan_in(zk, co, ctx_for):
                       [c for (_, _, ch) in want.sumcheck_proofs for c in ch],
                       [cl for (cl, _, _) in want.sumcheck_proofs], want.wb_evaluations, want.wc_evaluations, want.claimed_sum)
         assert zk.fe_to_ints(fid, proof.circuit_output) == want.circuit_output
+
+
+def test_wide_prover_row_form_eq_tables_match_entry_wise_form(zk, co, ctx_for):
+    """layers wide enough (2^16) for the row-form eq tables (one fold table per row, 84 multiplies per entry) and the
+    multi-block round kernels: the proof must equal the one built with the entry-wise Montgomery products"""
+    import os
+    from zk_cryptography_research_implementations_b200 import gkr
+    fid = 0
+    ctx = ctx_for(fid)
+    rng = np.random.default_rng(99)
+    w = 16
+    bits = [1, w, w]
+    n = 1 << w
+    g = np.arange(n, dtype=np.int64)
+    layer0 = np.stack([g, rng.integers(0, n, size=n), g & 1, rng.integers(0, 2, size=n)], axis=1)
+    layer1 = np.stack([rng.integers(0, n, size=n), rng.integers(0, n, size=n), g, rng.integers(0, 2, size=n)], axis=1)
+    inputs = ctx.generate(11, 0, n).download()
+    proofs = []
+    for knob in ("1", "0"):
+        os.environ["ZKB200_EQ_ROWS"] = knob
+        try:
+            wc = gkr.WideCircuit(ctx, bits, [layer0, layer1])
+            proofs.append(gkr.prove_wide(ctx, wc, inputs))
+            wc.close()
+        finally:
+            del os.environ["ZKB200_EQ_ROWS"]
+    a, b = proofs
+    assert np.array_equal(a.claimed_sum, b.claimed_sum) and np.array_equal(a.circuit_output, b.circuit_output)
+    assert np.array_equal(a.wb_evaluations, b.wb_evaluations) and np.array_equal(a.wc_evaluations, b.wc_evaluations)
+    for x, y in zip(a.sumcheck_proofs, b.sumcheck_proofs):
+        assert np.array_equal(x.random_challenges, y.random_challenges)
+        assert all(np.array_equal(p.coefficients, q.coefficients) for p, q in zip(x.round_univariate_polynomials, y.round_univariate_polynomials))
+    # the circuit output against a plain host evaluation with the oracle's field (2^15 gates per output: the sliced
+    # evaluation kernels at scale)
+    assert np.array_equal(_host_layer(co, fid, layer0, 2, _host_layer(co, fid, layer1, n, inputs)), a.circuit_output)
+
+
+def _host_layer(co, fid, layer, n_out, values):
+    """Circuit::evaluate for one layer on the host (arithmetic_circuit.rs:82-97), oracle field arithmetic"""
+    out = np.zeros((n_out, 4), dtype=np.uint64)
+    for l, r, o, op in layer:
+        out[o] = co.fe_op("add", fid, out[o], co.fe_op("add" if op == 0 else "mul", fid, values[l], values[r]))
+    return out

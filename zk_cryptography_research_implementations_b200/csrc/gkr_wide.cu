@@ -147,14 +147,18 @@ __global__ void __launch_bounds__(kThreads) eval_layer_slices_kernel(GateCsr g, 
         if (threadIdx.x == 0) st256(partial + w, acc[0]);
     }
 }
+// one block per output adds its S partial sums
 template <int FID> __global__ void __launch_bounds__(kThreads) sum_slices_kernel(const Fe* partial, Fe* out, uint64_t n_out, uint32_t S) {
-    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += (uint64_t)gridDim.x * blockDim.x) {
-        Fe acc = ld256(partial + o * S);
-        for (uint32_t s = 1; s < S; ++s) {
+    for (uint64_t o = blockIdx.x; o < n_out; o += gridDim.x) {
+        Fe acc[1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[0].v[k] = 0;
+        for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
             Fe v = ld256(partial + o * S + s);
-            Fp<FID>::add(acc, acc, v);
+            Fp<FID>::add(acc[0], acc[0], v);
         }
-        st256(out + o, acc);
+        block_sum<FID, 1>(acc);
+        if (threadIdx.x == 0) st256(out + o, acc[0]);
     }
 }
 
@@ -184,8 +188,11 @@ __global__ void __launch_bounds__(kThreads) phase1_kernel(GateCsr g, const Fe* w
 // phase-2 tables: one thread per c
 template <int FID>
 __global__ void __launch_bounds__(kThreads)
-    phase2_kernel(GateCsr g, const Fe* w, const Fe* equ, Fe Wu, Fe* A, Fe* B, uint64_t nc) {
+    phase2_kernel(GateCsr g, const Fe* w, const Fe* equ, const __grid_constant__ FoldTable Wu, Fe* A, Fe* B, uint64_t nc) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    Fe zero;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) zero.v[k] = 0;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += stride) {
         Fe addu, mulu;
 #pragma unroll
@@ -197,8 +204,8 @@ __global__ void __launch_bounds__(kThreads)
             else Fp<FID>::add(mulu, mulu, t);
         }
         Fe a, m, bsum;
-        Fp<FID>::mont_mul(a, Wu, addu);
-        Fp<FID>::mont_mul(m, Wu, mulu);
+        FoldScalar<FID>::fold(a, zero, addu, Wu);   // W(u) * add_u(c): a product by a per-launch constant (0 + W(u) (x - 0))
+        FoldScalar<FID>::fold(m, zero, mulu, Wu);
         Fp<FID>::add(bsum, addu, m);
         st256(A + c, a);
         st256(B + c, bsum);
@@ -287,6 +294,45 @@ __global__ void __launch_bounds__(kThreads) eq_outer2_kernel(Fe* out, const Fe* 
     }
 }
 
+// Row form of the outer product for wide tables: along a row the hi factor is a constant, so its eight multiples
+// h 2^(32 i) mod p are formed once per row (8 threads, one Montgomery product each) and every entry costs a
+// fold-by-scalar (84 multiplies) instead of a Montgomery product (137).  Rows have 2^lo_bits >= 256 entries.
+struct Pow32Args {
+    Fe pow32[8];   // Montgomery forms of 2^(32 i)
+};
+template <int FID, bool TWO>
+__global__ void __launch_bounds__(kThreads) eq_outer_rows_kernel(Fe* out, const Fe* hi1, const Fe* lo1, const Fe* hi2, const Fe* lo2, uint32_t lo_bits,
+                                                                 uint64_t n_rows, const __grid_constant__ Pow32Args pw) {
+    __shared__ FoldTable tab[TWO ? 2 : 1];
+    const uint64_t row_len = 1ull << lo_bits;
+    Fe zero;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) zero.v[k] = 0;
+    for (uint64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        __syncthreads();   // the previous row's readers are done with tab
+        if (threadIdx.x < (TWO ? 16u : 8u)) {
+            const int t = threadIdx.x >> 3, i = threadIdx.x & 7;
+            Fe h = (t ? hi2 : hi1)[row], plain, r;
+            Fp<FID>::redc256(plain.v, h.v);          // out of Montgomery form
+            Fp<FID>::cond_sub_p(plain.v);
+            Fp<FID>::mont_mul(r, plain, pw.pow32[i]);   // h 2^(32 i) mod p as a plain integer
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tab[t].w[i][k] = r.v[k];
+        }
+        __syncthreads();
+        for (uint64_t j = threadIdx.x; j < row_len; j += blockDim.x) {
+            Fe x = lo1[j], o;
+            FoldScalar<FID>::fold(o, zero, x, tab[0]);
+            if (TWO) {
+                Fe y = lo2[j], o2;
+                FoldScalar<FID>::fold(o2, zero, y, tab[TWO ? 1 : 0]);
+                Fp<FID>::add(o, o, o2);
+            }
+            st256(out + (row << lo_bits) + j, o);
+        }
+    }
+}
+
 int launch_eq_halves(zk_ctx* ctx, const std::vector<HFe>& r, const HFe& scale, Fe* hi, Fe* lo, uint32_t kh, uint32_t kl) {
     const HostField& f = ctx->field;
     EqHalfArgs a;
@@ -313,11 +359,27 @@ int build_eq2(zk_ctx* ctx, zk_wide_circuit* wc, const std::vector<HFe>& r1, cons
     if (kl > (uint32_t)kEqHalfBits) return fail(ctx, ZK_ERR_ARG, "layer wider than 2^30");
     int rc = launch_eq_halves(ctx, r1, s1, wc->half_hi.p, wc->half_lo.p, kh, kl);
     if (rc) return rc;
+    // rows of at least one block's worth of entries; ZKB200_EQ_ROWS=0 forces the entry-wise kernel (test hook: the two
+    // must give the same proof)
+    const char* knob = getenv("ZKB200_EQ_ROWS");
+    const bool rows = kl >= 8 && !(knob && knob[0] == '0');
+    Pow32Args pw;
+    memcpy(pw.pow32, ctx->pow32, sizeof pw.pow32);
+    const uint64_t n_rows = 1ull << kh;
+    const int row_grid = (int)std::min<uint64_t>(n_rows, (uint64_t)ctx->sm_count * 4);
     if (r2) {
         rc = launch_eq_halves(ctx, *r2, s2, wc->half_hi2.p, wc->half_lo2.p, kh, kl);
         if (rc) return rc;
-        ZK_FID_SWITCH(ctx, (eq_outer2_kernel<FID, true><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(
-                                out, wc->half_hi.p, wc->half_lo.p, wc->half_hi2.p, wc->half_lo2.p, kl, 1ull << k)));
+        if (rows) {
+            ZK_FID_SWITCH(ctx, (eq_outer_rows_kernel<FID, true><<<row_grid, kThreads, 0, ctx->stream>>>(
+                                    out, wc->half_hi.p, wc->half_lo.p, wc->half_hi2.p, wc->half_lo2.p, kl, n_rows, pw)));
+        } else {
+            ZK_FID_SWITCH(ctx, (eq_outer2_kernel<FID, true><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(
+                                    out, wc->half_hi.p, wc->half_lo.p, wc->half_hi2.p, wc->half_lo2.p, kl, 1ull << k)));
+        }
+    } else if (rows) {
+        ZK_FID_SWITCH(ctx, (eq_outer_rows_kernel<FID, false><<<row_grid, kThreads, 0, ctx->stream>>>(
+                                out, wc->half_hi.p, wc->half_lo.p, nullptr, nullptr, kl, n_rows, pw)));
     } else {
         ZK_FID_SWITCH(ctx, (eq_outer2_kernel<FID, false><<<grid_of(ctx, 1ull << k, 4), kThreads, 0, ctx->stream>>>(
                                 out, wc->half_hi.p, wc->half_lo.p, nullptr, nullptr, kl, 1ull << k)));
@@ -440,7 +502,7 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         if (wc->layers[li].n_gates / n_out >= 64 && n_out * 2 <= full_grid) {   // heavy fan-in, few outputs: slices
             const uint32_t S = (uint32_t)std::min<uint64_t>(full_grid / n_out, (wc->layers[li].n_gates / n_out + kThreads - 1) / kThreads);
             ZK_FID_SWITCH(ctx, (eval_layer_slices_kernel<FID><<<(int)(n_out * S), kThreads, 0, ctx->stream>>>(wc->layers[li].by_out, W[li + 1].p, wc->half_hi.p, n_out, S)));
-            ZK_FID_SWITCH(ctx, (sum_slices_kernel<FID><<<1, kThreads, 0, ctx->stream>>>(wc->half_hi.p, W[li].p, n_out, S)));
+            ZK_FID_SWITCH(ctx, (sum_slices_kernel<FID><<<(int)n_out, kThreads, 0, ctx->stream>>>(wc->half_hi.p, W[li].p, n_out, S)));
             ctx->launches++;
         } else if (wc->layers[li].n_gates / n_out >= 64) {   // heavy fan-in, many outputs: a block per output
             int blocks = (int)std::min<uint64_t>(n_out, full_grid);
@@ -523,9 +585,8 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         std::vector<HFe> u(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + m);
         // ---- phase 2 tables and sumcheck over c
         if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
-        Fe Wu_fe;
-        memcpy(Wu_fe.v, Wu.l, 32);
-        ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_fe, h1.p, h2.p, nm)));
+        const FoldTable Wu_ft = make_fold_table(f, Wu);
+        ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nm)));
         ctx->launches += 1;
         ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_CUDA(cudaGetLastError());
