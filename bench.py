@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEED = 0xB200
+MEGA = 1e6      # BASELINE.json quotes the sumcheck metric in Melems/s
 WORKLOADS = {
     # name: (field id, field name, P, D, default log2 N, description)
     "product30": (0, "BN254_FQ", 1, 2, 30, "degree-2 product sumcheck f*g (BASELINE.json configs[2])"),
@@ -324,14 +325,14 @@ def run_mle(args, wl):
             co.mle_evaluate(field, tab, rs)
             times.append(time.perf_counter() - t0)
         t = statistics.mean(times)
-        v = (1 << sl) / t
-        print(json.dumps({"impl": "reference", "metric": "mle_evaluate_field_elements_per_s", "value": v, "unit": "elements/s",
+        v = (1 << sl) / t / MEGA
+        print(json.dumps({"impl": "reference", "metric": "mle_evaluate_Melems_per_s", "value": v, "unit": "Melems/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery limbs)", "data": "synthetic",
                           "config": {"workload": "mle: " + desc, "field": fname, "log2_entries": log2},
-                          "cpu_baseline": {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
+                          "cpu_baseline": {"value": v, "unit": "Melems/s", "cores": 1, "kind": "port",
                                            "sample": "evaluate of a 2^%d-entry sample, oracle C restatement (n folds with fresh vectors), 1 thread" % sl},
-                          "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                          "e2e": {"value": v, "unit": "Melems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     import torch
     import torch.distributed as dist
@@ -416,10 +417,10 @@ def run_mle(args, wl):
             t0 = time.perf_counter()
             co.mle_evaluate(field, tab, tab[:sl].copy())
             t = time.perf_counter() - t0
-            cpu = {"value": (1 << sl) / t, "unit": "elements/s", "cores": 1, "kind": "port",
+            cpu = {"value": (1 << sl) / t / MEGA, "unit": "Melems/s", "cores": 1, "kind": "port",
                    "sample": "evaluate of a 2^%d-entry sample (%.2f s), oracle C restatement, 1 thread" % (sl, t)}
         print(json.dumps({
-            "metric": "mle_evaluate_field_elements_per_s", "value": N / (ms_eval * 1e-3), "unit": "elements/s", "n_gpus": world,
+            "metric": "mle_evaluate_Melems_per_s", "value": N / (ms_eval * 1e-3) / MEGA, "unit": "Melems/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_eval, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
             "config": {"workload": "mle: " + desc, "field": fname, "log2_entries": log2, "table_bytes_total": N * 32,
@@ -452,17 +453,17 @@ def run_reference(args, wl):
         cpu_prove_once(field, P, D, min(sample_log2, 16))
     times = [cpu_prove_once(field, P, D, sample_log2) for _ in range(args.steps)]
     t = statistics.mean(times)
-    value = (1 << sample_log2) / t
+    value = (1 << sample_log2) / t / MEGA
     sample = "2^%d-entry sample of the 2^%d workload, oracle C restatement of the reference prover%s, 1 thread" % (
         sample_log2, log2, " (posed as f*g + 0*0, the only form the reference accepts)" if (P == 1 and D > 1) else "")
     line = {
-        "impl": "reference", "metric": "sumcheck_prove_field_elements_per_s", "value": value, "unit": "elements/s",
+        "impl": "reference", "metric": "sumcheck_prove_Melems_per_s", "value": value, "unit": "Melems/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery limbs)",
         "data": "synthetic",
         "config": config_dict(args.workload, wl, log2, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": 1, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": "Melems/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Melems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -665,7 +666,7 @@ def run_ours(args, wl):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, st = timed_steps(prove_resident, regenerate, args.steps, args.warmup, True)
     clocks = sampler.stop() if sampler else None
-    value = N / (ms * 1e-3)
+    value = N / (ms * 1e-3) / MEGA
     proof_digest = int(np.bitwise_xor.reduce((coeffs if D > 1 else rpolys).reshape(-1))) & 0xFFFFFFFF
 
     # ---- roofline of the dominant kernel family (round kernels), CUDA events on the launching stream
@@ -726,7 +727,7 @@ def run_ours(args, wl):
                 break
             host.append(p)
     if not args.no_e2e and host is None:
-        e2e = {"value": None, "unit": "elements/s", "unavailable": "cudaHostAlloc of %d x %d bytes of pinned host memory failed on this box" % (T, m * 32)}
+        e2e = {"value": None, "unit": "Melems/s", "unavailable": "cudaHostAlloc of %d x %d bytes of pinned host memory failed on this box" % (T, m * 32)}
     elif not args.no_e2e:
         regenerate()
         for i in range(T):
@@ -746,7 +747,7 @@ def run_ours(args, wl):
         e_steps = max(1, min(args.steps, args.e2e_steps))
         ms_e2e, _ = timed_steps(upload_and_prove, lambda: None, e_steps, 1, False)
         d2h = (n_rounds * (D + 1 if D > 1 else 2) + T + 1) * 32
-        e2e = {"value": N / (ms_e2e * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": T * m * 32 * world,
+        e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Melems/s", "h2d_bytes_per_step": T * m * 32 * world,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
                "call": "zk_table_upload_into (pinned host -> HBM) + %s" % ("zk_prove_basic_device incl. the Keccak absorb of the table"
                                                                            if D == 1 else "zk_prove_product_sharded")}
@@ -758,13 +759,13 @@ def run_ours(args, wl):
     if rank == 0 and world == 1 and not args.no_cpu:
         sample_log2 = min(log2, args.cpu_log2)
         t = cpu_prove_once(field, P, D, sample_log2)
-        cpu = {"value": (1 << sample_log2) / t, "unit": "elements/s", "cores": 1, "kind": "port",
+        cpu = {"value": (1 << sample_log2) / t / MEGA, "unit": "Melems/s", "cores": 1, "kind": "port",
                "sample": "one prove of a 2^%d-entry sample (%.1f s) by oracle/zkoracle.c -- C restatement of the single-threaded "
                          "reference prover with its pass structure; host has %d cores" % (sample_log2, t, os.cpu_count() or 0)}
 
     if rank == 0:
         line = {
-            "metric": "sumcheck_prove_field_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
+            "metric": "sumcheck_prove_Melems_per_s", "value": value, "unit": "Melems/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
             "config": config_dict(args.workload, wl, log2, world),
