@@ -699,7 +699,7 @@ def run_ours(args, wl):
     # ---- integer-multiply ceiling (register-resident probe, same clocks)
     integer = {}
     if rank == 0 and not args.no_probe:
-        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced"), (3, "fp64_fma")):
+        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced"), (7, "mul_acc_columns"), (3, "fp64_fma")):
             ops, pms = C.c_double(), C.c_double()
             ctx.check(lib.zk_arith_probe(ctx.h, kind, 1500, 2, C.byref(ops), C.byref(pms)))
             integer[name + "_Gops"] = ops.value / 1e9

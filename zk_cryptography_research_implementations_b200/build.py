@@ -15,8 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libzkb200.so")
+# ZKB200_VARIANT=name builds an experiment next to the product (objects in build_name/, library libzkb200_name.so);
+# select it at run time with ZKB200_LIB=<path> (see _lib.py).  Used for A/B runs of kernel variants on the GPU box.
+_VARIANT = os.environ.get("ZKB200_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _VARIANT if _VARIANT else ""))
+LIB = os.path.join(HERE, "libzkb200" + ("_" + _VARIANT if _VARIANT else "") + ".so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -234,6 +234,41 @@ template <int FID> struct Fp {
         acc[16] = ptx::addc(acc[16], 0u);
     }
 
+    // ---------------------------------------------------------------- unreduced products without carry chains
+    // Column accumulator: slot k collects every limb product a_i b_j with i + j == k as a 96-bit integer
+    // (lo, hi, top) at weight 2^(32 k).  A product costs one carry-OUT-only IMAD.WIDE.U32 plus one IADD3.X, on two
+    // different pipes, and the 64 products of a multiplication are independent of each other -- no IMAD.WIDE.U32.X.
+    // Up to 2^29 products per slot fit (8 x 2^29 x 2^64 < 2^96).
+    struct ColAcc {
+        uint32_t lo[15], hi[15], top[15];
+    };
+    ZK_DEV static void cols_init(ColAcc& c) {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) c.lo[k] = c.hi[k] = c.top[k] = 0;
+    }
+    ZK_DEV static void mul_acc_cols(ColAcc& c, const Fe& a, const Fe& b) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ptx::mad_wide_top(c.lo[i + j], c.hi[i + j], c.top[i + j], a.v[i], b.v[j]);
+    }
+    // the slots as one 17-limb integer (the sum of < 2^32 products of canonical elements fits: < 2^542)
+    ZK_DEV static void cols_to_limbs(uint32_t t[17], const ColAcc& c) {
+        // limb p collects lo[p] + hi[p-1] + top[p-2]: three carry chains added one after the other
+        t[0] = c.lo[0];
+#pragma unroll
+        for (int p = 1; p < 15; ++p) t[p] = c.lo[p];
+        t[15] = t[16] = 0;
+        t[1] = ptx::add_cc(t[1], c.hi[0]);
+#pragma unroll
+        for (int p = 2; p < 16; ++p) t[p] = ptx::addc_cc(t[p], c.hi[p - 1]);
+        t[16] = ptx::addc(t[16], 0u);
+        t[2] = ptx::add_cc(t[2], c.top[0]);
+#pragma unroll
+        for (int p = 3; p < 16; ++p) t[p] = ptx::addc_cc(t[p], c.top[p - 2]);
+        t[16] = ptx::addc(t[16], c.top[14]);
+    }
+
     // ---------------------------------------------------------------- Barrett step
     // s[0..9] < 2^291  ->  r = s mod p (canonical).
     //   x = s >> 232 (< 2^59);  q = (x * floor(2^296/p)) >> 64  in {floor(s/p)-1, floor(s/p)};
@@ -344,6 +379,42 @@ template <int FID> struct FoldScalar {
         const uint32_t* v;
         ZK_DEV uint32_t operator()(int i) const { return v[i]; }
     };
+#ifndef ZK_FOLD_COLS
+#define ZK_FOLD_COLS 1   // 1: carry-chain-free column form (below); 0: the chained even/odd rows
+#endif
+#if ZK_FOLD_COLS
+    // Column form: limb j of every table row lands in slot j, so the 64 limb products fall into 8 independent 96-bit
+    // slots -- 64 carry-OUT-only IMAD.WIDE.U32 (full rate) and ~33 IADD3.X that collect two carries each, instead of
+    // 19 + 45 carry-chained IMAD.WIDE.U32.X (half rate).  Same integer S, same Barrett step.
+    ZK_DEV static void fold(Fe& out, const Fe& lo, const Fe& hi, const FoldTable& tab) {
+        Fe d;
+        P::sub_lazy(d, hi, lo);  // hi - lo + p in (0, 2p)
+        uint32_t cl[8], ch[8], ct[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            cl[j] = lo.v[j];
+            ch[j] = ct[j] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ptx::mad_wide_top(cl[j], ch[j], ct[j], d.v[i], tab.w[i][j]);
+        // S = sum_j (cl[j] + ch[j] 2^32 + ct[j] 2^64) 2^(32 j) < p (1 + 2^35) < 2^291
+        uint32_t s[10];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = cl[k];
+        s[8] = s[9] = 0;
+        s[1] = ptx::add_cc(s[1], ch[0]);
+#pragma unroll
+        for (int k = 2; k < 9; ++k) s[k] = ptx::addc_cc(s[k], ch[k - 1]);
+        s[9] = ptx::addc(s[9], 0u);
+        s[2] = ptx::add_cc(s[2], ct[0]);
+#pragma unroll
+        for (int k = 3; k < 9; ++k) s[k] = ptx::addc_cc(s[k], ct[k - 2]);
+        s[9] = ptx::addc(s[9], ct[7]);
+        P::barrett(out.v, s);
+    }
+#else
     ZK_DEV static void fold(Fe& out, const Fe& lo, const Fe& hi, const FoldTable& tab) {
         Fe d;
         P::sub_lazy(d, hi, lo);  // hi - lo + p in (0, 2p)
@@ -375,6 +446,7 @@ template <int FID> struct FoldScalar {
         s[9] = ptx::addc(E[9], O[8]);
         P::barrett(out.v, s);
     }
+#endif
 };
 
 }  // namespace zk

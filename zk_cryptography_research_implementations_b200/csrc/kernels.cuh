@@ -174,10 +174,14 @@ template <class RA> __device__ __forceinline__ void publish_round(const RA& ra, 
 }
 
 // Round 0: evaluations only.  half = N/2 pairs (j, j + half).
+#ifndef ZK_ROUND0_COLS
+#define ZK_ROUND0_COLS 1   // round 0 of degree-2 sumchecks accumulates its three products per pair in column accumulators
+#endif
+template <int D> struct Round0Cols { static constexpr bool value = ZK_ROUND0_COLS != 0 && D == 2; };
 template <int FID, int P, int D, int NLIN = 0>
-__global__ void __launch_bounds__(kThreads, (P * D + NLIN <= ZK_TWO_BLOCK_TABLES && D <= 2) ? 2 : 1) round_evals_kernel(TablePtrs tp, uint64_t half, ReduceScratch rs) {
+__global__ void __launch_bounds__(kThreads, (!Round0Cols<D>::value && P * D + NLIN <= ZK_TWO_BLOCK_TABLES && D <= 2) ? 2 : 1) round_evals_kernel(TablePtrs tp, uint64_t half, ReduceScratch rs) {
     constexpr int T = P * D + NLIN;
-    RoundAcc<FID, P, D, false, NLIN> ra;
+    RoundAcc<FID, P, D, false, NLIN, Round0Cols<D>::value> ra;
     ra.init();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
@@ -429,6 +433,40 @@ __global__ void __launch_bounds__(kThreads) arith_probe_kernel(Fe* out, uint32_t
     for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int k = 0; k < 8; ++k) r.v[k] += x[c].v[k] * (2 * c + 1) + acc[c][k] + acc[c][k + 8];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// Probe of the carry-chain-free unreduced product (Fp::mul_acc_cols): two independent chains per thread (kind 7 of
+// zk_arith_probe), to set against mul_acc (kind 2).
+template <int FID> __global__ void __launch_bounds__(kThreads) cols_probe_kernel(Fe* out, uint32_t iters) {
+    Fe x[2], y[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x[c].v[k] = (threadIdx.x * 2654435761u + blockIdx.x + 977u * c + k) & 0x0fffffffu;
+            y[c].v[k] = (threadIdx.x * 40503u + 31u * blockIdx.x + 13u * c + 7u * k) & 0x0fffffffu;
+        }
+    typename Fp<FID>::ColAcc acc[2];
+    Fp<FID>::cols_init(acc[0]);
+    Fp<FID>::cols_init(acc[1]);
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            Fp<FID>::mul_acc_cols(acc[c], x[c], y[c]);
+            x[c].v[0] ^= acc[c].top[14];
+        }
+    }
+    Fe r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t t[17];
+        Fp<FID>::cols_to_limbs(t, acc[c]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[k] += x[c].v[k] * (2 * c + 1) + t[k] + t[k + 8];
+    }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 

@@ -35,6 +35,8 @@ inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c)    { return addc(mul
 inline void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b)     { lo = mul_lo(a, b); hi = mul_hi(a, b); }
 inline void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b)  { lo = mad_lo_cc(a, b, lo); hi = madc_hi_cc(a, b, hi); }
 inline void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = madc_lo_cc(a, b, lo); hi = madc_hi_cc(a, b, hi); }
+// 96-bit slot: (lo, hi) += a * b, the carry out of the slot lands in `top` -- no carry enters, no chain leaves
+inline void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t& top, uint32_t a, uint32_t b) { mad_wide_cc(lo, hi, a, b); top = addc(top, 0u); }
 }}  // namespace zk::ptx
 #else
 #define ZK_DEV __device__ __forceinline__
@@ -77,6 +79,13 @@ ZK_DEV void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
 }
 ZK_DEV void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// 96-bit slot: (lo, hi) += a * b with the carry out of the slot caught in `top`: IMAD.WIDE.U32 (carry OUT only -- the
+// full-rate form; the carry-IN form IMAD.WIDE.U32.X issues at half that rate) + one IADD3.X on the alu pipe.
+// (volatile like every statement that touches the condition code: the front end must not move it into another chain;
+// ptxas turns the flag into predicates and then schedules the independent slots freely)
+ZK_DEV void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t& top, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(top) : "r"(a), "r"(b));
 }
 }}  // namespace zk::ptx
 #endif
