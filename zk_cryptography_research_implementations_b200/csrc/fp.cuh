@@ -236,9 +236,12 @@ template <int FID> struct Fp {
 
     // ---------------------------------------------------------------- unreduced products without carry chains
     // Column accumulator: slot k collects every limb product a_i b_j with i + j == k as a 96-bit integer
-    // (lo, hi, top) at weight 2^(32 k).  A product costs one carry-OUT-only IMAD.WIDE.U32 plus one IADD3.X, on two
-    // different pipes, and the 64 products of a multiplication are independent of each other -- no IMAD.WIDE.U32.X.
-    // Up to 2^29 products per slot fit (8 x 2^29 x 2^64 < 2^96).
+    // (lo, hi, top) at weight 2^(32 k).  A product costs one carry-OUT-only IMAD.WIDE.U32 plus half an IADD3.X (ptxas
+    // feeds two carry predicates into one IADD3.X), and the 64 products of a multiplication are independent of each
+    // other -- no IMAD.WIDE.U32.X.  Up to 2^29 products per slot fit (8 x 2^29 x 2^64 < 2^96).  Measured on B200
+    // (zk_arith_probe kind 7): 122 G products/s against 102 G/s for the chained mul_acc -- the carry-OUT form is not
+    // the full-rate instruction either -- and 45 registers per accumulator instead of 17; the round kernels that
+    // tried it (ZK_ROUND0_COLS) lost more to the halved occupancy than they gained.  Kept as a tested experiment.
     struct ColAcc {
         uint32_t lo[15], hi[15], top[15];
     };
@@ -380,12 +383,13 @@ template <int FID> struct FoldScalar {
         ZK_DEV uint32_t operator()(int i) const { return v[i]; }
     };
 #ifndef ZK_FOLD_COLS
-#define ZK_FOLD_COLS 1   // 1: carry-chain-free column form (below); 0: the chained even/odd rows
+#define ZK_FOLD_COLS 0   // 0: the chained even/odd rows (product); 1: the carry-chain-free column form (measured slower)
 #endif
 #if ZK_FOLD_COLS
-    // Column form: limb j of every table row lands in slot j, so the 64 limb products fall into 8 independent 96-bit
-    // slots -- 64 carry-OUT-only IMAD.WIDE.U32 (full rate) and ~33 IADD3.X that collect two carries each, instead of
-    // 19 + 45 carry-chained IMAD.WIDE.U32.X (half rate).  Same integer S, same Barrett step.
+    // Column form (EXPERIMENT, off by default): limb j of every table row lands in slot j, so the 64 limb products fall
+    // into 8 independent 96-bit slots -- 64 carry-OUT-only IMAD.WIDE.U32 and ~33 IADD3.X that collect two carries each,
+    // instead of 19 + 45 carry-chained IMAD.WIDE.U32.X.  Same integer S, same Barrett step, bit-identical results;
+    // on B200 the carry-out form issues no faster than the carry-in form (fold probe 86 vs 91 G/s).
     ZK_DEV static void fold(Fe& out, const Fe& lo, const Fe& hi, const FoldTable& tab) {
         Fe d;
         P::sub_lazy(d, hi, lo);  // hi - lo + p in (0, 2p)

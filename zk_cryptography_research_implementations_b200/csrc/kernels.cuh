@@ -175,7 +175,7 @@ template <class RA> __device__ __forceinline__ void publish_round(const RA& ra, 
 
 // Round 0: evaluations only.  half = N/2 pairs (j, j + half).
 #ifndef ZK_ROUND0_COLS
-#define ZK_ROUND0_COLS 1   // round 0 of degree-2 sumchecks accumulates its three products per pair in column accumulators
+#define ZK_ROUND0_COLS 0   // 1: round 0 of degree-2 sumchecks accumulates its products in column accumulators (experiment: slower)
 #endif
 template <int D> struct Round0Cols { static constexpr bool value = ZK_ROUND0_COLS != 0 && D == 2; };
 template <int FID, int P, int D, int NLIN = 0>

@@ -80,8 +80,9 @@ ZK_DEV void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
 ZK_DEV void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
 }
-// 96-bit slot: (lo, hi) += a * b with the carry out of the slot caught in `top`: IMAD.WIDE.U32 (carry OUT only -- the
-// full-rate form; the carry-IN form IMAD.WIDE.U32.X issues at half that rate) + one IADD3.X on the alu pipe.
+// 96-bit slot: (lo, hi) += a * b with the carry out of the slot caught in `top`: IMAD.WIDE.U32 with a carry-OUT
+// predicate + an IADD3.X on the alu pipe (measured: the carry-out form issues at about the rate of the carry-in form
+// IMAD.WIDE.U32.X, half the rate of a plain IMAD.WIDE.U32).
 // (volatile like every statement that touches the condition code: the front end must not move it into another chain;
 // ptxas turns the flag into predicates and then schedules the independent slots freely)
 ZK_DEV void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t& top, uint32_t a, uint32_t b) {
