@@ -547,8 +547,8 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
     for (uint32_t li = 0; li < L; ++li)
         if (wc->bits[li + 1] == 0) return fail(ctx, ZK_ERR_ARG, "every layer must read at least two wires");
     for (uint32_t li = 0; li < L; ++li) {
-        const uint32_t ab = wc->bits[li], m = wc->bits[li + 1];
-        const uint64_t na = 1ull << ab, nm = 1ull << m;
+        const uint32_t m = wc->bits[li + 1];
+        const uint64_t nm = 1ull << m;
         const WideLayer& wl = wc->layers[li];
         int rc;
         // ---- w(a): eq(r_a, .) at the output layer, alpha eq(r_b, .) + beta eq(r_c, .) below

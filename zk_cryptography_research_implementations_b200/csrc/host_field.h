@@ -205,7 +205,7 @@ class Keccak256 {
             if (pos_ == 0 && take == kRate) {
                 const uint64_t* w = reinterpret_cast<const uint64_t*>(d);
                 if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {
-                    for (int i = 0; i < kRate / 8; ++i) s_[i] ^= w[i];
+                    for (size_t i = 0; i < kRate / 8; ++i) s_[i] ^= w[i];
                 } else {
                     for (size_t i = 0; i < kRate; ++i) sb[i] ^= d[i];
                 }
