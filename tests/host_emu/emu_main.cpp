@@ -69,6 +69,27 @@ template <int FID> static int run() {
             if (it % 50 == 0) for (int k = 0; k < 3000; ++k) P::mul_acc(acc, A, B);
             if (memcmp(acc, limbs, sizeof acc)) { ++bad; printf("column accumulator differs from the chained accumulator\n"); }
         }
+        // the same sums through flag-free radix-2^29 columns (six multiplications per flush)
+        {
+            typename P::Cols29 cc; P::cols29_init(cc);
+            uint32_t acc29[17] = {0}, accw[17] = {0};
+            int pending = 0;
+            int reps = (it % 50 == 0) ? 500 : 1;
+            for (int rep = 0; rep < reps; ++rep) {
+                const zk::Fe* xs[3] = {&A, &B, &A};
+                zk::Fe Cc = to_fe(c);
+                const zk::Fe* ys[3] = {&B, &Cc, &Cc};
+                for (int q = 0; q < 3; ++q) {
+                    typename P::Digits29 da, db;
+                    P::to_digits29(da, *xs[q]); P::to_digits29(db, *ys[q]);
+                    P::mul_cols29(cc, da, db);
+                    if (++pending == P::kCols29Budget) { P::cols29_flush(acc29, cc); pending = 0; }
+                    P::mul_acc(accw, *xs[q], *ys[q]);
+                }
+            }
+            P::cols29_flush(acc29, cc);
+            if (memcmp(acc29, accw, sizeof accw)) { ++bad; printf("radix-2^29 accumulator differs from the chained accumulator (it=%d)\n", it); }
+        }
         // fold by scalar table: out = lo + r*(hi-lo); r = b, lo = a, hi = c
         {
             zk::FoldTable tab;

@@ -862,9 +862,11 @@ extern "C" int zk_prove_product_host(zk_ctx* ctx, const uint64_t* host_tables, u
 // Times `iters` x 4 field operations per thread on a full grid (blocks_per_sm x SMs x 256 threads);
 // returns operations per second.  kind: 0 mont_mul, 1 fold-by-scalar, 2 unreduced multiply-accumulate,
 // 3: double-precision FMA, 4: IMAD.WIDE.U32, 5: IMAD (32-bit), 6: carry-chained IMAD.WIDE.U32.X (8 x iters per thread each),
-// 7: unreduced product through the carry-chain-free column accumulator (2 x iters per thread).
+// 7: unreduced product through the carry-chain-free column accumulator, 8: through flag-free radix-2^29 columns, operand
+// conversion and flushes included, 9: the chained mul_acc on the same fully varying operand stream as 8 (2 x iters per
+// thread each; iters a multiple of 6 for kinds 8 and 9).
 extern "C" int zk_arith_probe(zk_ctx* ctx, int kind, uint32_t iters, int blocks_per_sm, double* ops_per_s, double* ms_out) {
-    if (kind < 0 || kind > 7 || blocks_per_sm < 1 || blocks_per_sm > 8) return fail(ctx, ZK_ERR_ARG, "bad probe arguments");
+    if (kind < 0 || kind > 9 || blocks_per_sm < 1 || blocks_per_sm > 8) return fail(ctx, ZK_ERR_ARG, "bad probe arguments");
     int grid = ctx->sm_count * blocks_per_sm;
     int rc = ensure_scratch(ctx, (size_t)grid * kThreads * sizeof(Fe));
     if (rc) return rc;
@@ -879,6 +881,8 @@ extern "C" int zk_arith_probe(zk_ctx* ctx, int kind, uint32_t iters, int blocks_
         else if (kind == 5) { imad_probe_kernel<5><<<grid, kThreads, 0, ctx->stream>>>((uint64_t*)ctx->scratch, iters); }
         else if (kind == 6) { imad_probe_kernel<6><<<grid, kThreads, 0, ctx->stream>>>((uint64_t*)ctx->scratch, iters); }
         else if (kind == 7) { ZK_DISPATCH_FID(ctx, (cols_probe_kernel<FID><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters))); }
+        else if (kind == 8) { ZK_DISPATCH_FID(ctx, (cols29_probe_kernel<FID, 0><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters))); }
+        else if (kind == 9) { ZK_DISPATCH_FID(ctx, (cols29_probe_kernel<FID, 1><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters))); }
         else if (kind == 0) { ZK_DISPATCH_FID(ctx, (arith_probe_kernel<FID, 0><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters, ft))); }
         else if (kind == 1) { ZK_DISPATCH_FID(ctx, (arith_probe_kernel<FID, 1><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters, ft))); }
         else { ZK_DISPATCH_FID(ctx, (arith_probe_kernel<FID, 2><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters, ft))); }
@@ -892,6 +896,6 @@ extern "C" int zk_arith_probe(zk_ctx* ctx, int kind, uint32_t iters, int blocks_
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_out) *ms_out = ms;
-    if (ops_per_s) *ops_per_s = (double)grid * kThreads * (kind == 7 ? 2.0 : kind >= 3 ? 8.0 : 4.0) * iters / (ms * 1e-3);
+    if (ops_per_s) *ops_per_s = (double)grid * kThreads * (kind >= 7 ? 2.0 : kind >= 3 ? 8.0 : 4.0) * iters / (ms * 1e-3);
     return ZK_OK;
 }

@@ -272,6 +272,66 @@ template <int FID> struct Fp {
         t[16] = ptx::addc(t[16], c.top[14]);
     }
 
+    // ---------------------------------------------------------------- flag-free products in radix 2^29 (EXPERIMENT)
+    // Nine 29-bit digits per operand: a digit product is < 2^58 and a column collects at most 9 of them per
+    // multiplication, so SIX multiplications accumulate in 64-bit columns with the flag-free IMAD.WIDE.U32 -- the one
+    // form of the instruction that issues at full rate -- before the columns are carried out into the 32-bit-limb
+    // accumulator.  81 multiplies instead of 64, none of them carry-chained.
+    struct Digits29 {
+        uint32_t v[9];
+    };
+    struct Cols29 {
+        uint64_t c[17];   // sum_k c[k] 2^(29 k)
+    };
+    static constexpr int kCols29Budget = 6;   // multiplications per flush: 6 x 9 x 2^58 < 2^64
+    ZK_DEV static void to_digits29(Digits29& o, const Fe& a) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int bit = 29 * k, w = bit >> 5, sh = bit & 31;
+            const uint32_t lo = a.v[w], hi = (w + 1 < 8) ? a.v[w + 1] : 0u;
+            o.v[k] = ptx::funnel_r(lo, hi, sh) & 0x1fffffffu;
+        }
+    }
+    ZK_DEV static void cols29_init(Cols29& c) {
+#pragma unroll
+        for (int k = 0; k < 17; ++k) c.c[k] = 0;
+    }
+    ZK_DEV static void mul_cols29(Cols29& c, const Digits29& a, const Digits29& b) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) ptx::mad_wide_noflags(c.c[i + j], a.v[i], b.v[j]);
+    }
+    // acc (17 x 32-bit limbs) += sum_k c[k] 2^(29 k); c = 0
+    ZK_DEV static void cols29_flush(uint32_t acc[17], Cols29& c) {
+        // radix-2^29 carry propagation: 18 exact digits + what is left above
+        uint32_t dg[19];
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < 17; ++k) {
+            const uint64_t t = c.c[k] + carry;
+            dg[k] = (uint32_t)t & 0x1fffffffu;
+            carry = t >> 29;
+            c.c[k] = 0;
+        }
+        dg[17] = (uint32_t)carry & 0x1fffffffu;
+        dg[18] = (uint32_t)(carry >> 29);
+        // repack into 32-bit limbs: limb p = bits [32 p, 32 p + 32) of sum_k dg[k] 2^(29 k)
+        uint32_t t[17];
+#pragma unroll
+        for (int p = 0; p < 17; ++p) {
+            const int bit = 32 * p, k = bit / 29, off = bit - 29 * k;   // limb p starts `off` bits into digit k
+            uint32_t v = dg[k] >> off;
+            if (k + 1 < 19) v |= dg[k + 1] << (29 - off);
+            if (29 - off + 29 < 32 && k + 2 < 19) v |= dg[k + 2] << (58 - off);
+            t[p] = v;
+        }
+        acc[0] = ptx::add_cc(acc[0], t[0]);
+#pragma unroll
+        for (int p = 1; p < 16; ++p) acc[p] = ptx::addc_cc(acc[p], t[p]);
+        acc[16] = ptx::addc(acc[16], t[16]);
+    }
+
     // ---------------------------------------------------------------- Barrett step
     // s[0..9] < 2^291  ->  r = s mod p (canonical).
     //   x = s >> 232 (< 2^59);  q = (x * floor(2^296/p)) >> 64  in {floor(s/p)-1, floor(s/p)};

@@ -470,6 +470,62 @@ template <int FID> __global__ void __launch_bounds__(kThreads) cols_probe_kernel
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// Probe of the flag-free radix-2^29 product (Fp::mul_cols29, operand conversion and the flush every six products
+// included) against the chained mul_acc ON THE SAME OPERAND STREAM: two independent chains per thread, every limb of
+// both operands changes from product to product (otherwise ptxas hoists the loop-invariant digit products out of the
+// loop).  MODE 0: radix 2^29 (kind 8 of zk_arith_probe), MODE 1: chained mul_acc (kind 9).
+template <int FID, int MODE> __global__ void __launch_bounds__(kThreads) cols29_probe_kernel(Fe* out, uint32_t iters) {
+    Fe x[2], y[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x[c].v[k] = (threadIdx.x * 2654435761u + blockIdx.x + 977u * c + k) & 0x0fffffffu;
+            y[c].v[k] = (threadIdx.x * 40503u + 31u * blockIdx.x + 13u * c + 7u * k) & 0x0fffffffu;
+        }
+    typename Fp<FID>::Cols29 cols[2];
+    uint32_t acc[2][17];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        Fp<FID>::cols29_init(cols[c]);
+#pragma unroll
+        for (int k = 0; k < 17; ++k) acc[c][k] = 0;
+    }
+    for (uint32_t it = 0; it < iters; it += Fp<FID>::kCols29Budget) {
+#pragma unroll
+        for (int u = 0; u < Fp<FID>::kCols29Budget; ++u) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (MODE == 0) {
+                    typename Fp<FID>::Digits29 dx, dy;
+                    Fp<FID>::to_digits29(dx, x[c]);
+                    Fp<FID>::to_digits29(dy, y[c]);
+                    Fp<FID>::mul_cols29(cols[c], dx, dy);
+                } else {
+                    Fp<FID>::mul_acc(acc[c], x[c], y[c]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // fresh operands for the next product (16 alu instructions in both modes)
+                    x[c].v[k] ^= MODE == 0 ? (uint32_t)cols[c].c[k + 4] : acc[c][k + 4];
+                    y[c].v[k] += x[c].v[k];
+                }
+            }
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) Fp<FID>::cols29_flush(acc[c], cols[c]);
+        }
+    }
+    Fe r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[k] += x[c].v[k] * (2 * c + 1) + acc[c][k] + acc[c][k + 8];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread (kind 3 of zk_arith_probe).  Not used by any kernel;
 // it answers whether a double-precision limb product (Emmart-style 52-bit limbs, 2 DFMA per product) could
 // relieve the half-rate IMAD.WIDE pipe in a later round.
