@@ -4,6 +4,7 @@ product, unreduced multiply-accumulate + wide REDC, fold-by-scalar (table + Barr
 including 0 / 1 / p-1 / all-ones edge inputs.  CPU only."""
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -21,3 +22,17 @@ def test_fp_cuh_host_emulation(tmp_path, defines):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]
     assert out.stdout.count("ok") == 10, out.stdout[-2000:]
+
+
+def test_warp_keccak_lane_tables_match_their_generator():
+    """the packed lane-routing words in csrc/dev_transcript.cuh are exactly what tools/gen_keccak_lanes.py derives (and
+    checks against a textbook Keccak-f[1600] and hashlib's SHA3-256)"""
+    import re
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_keccak_lanes.py")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    gen = {m.group(1): re.findall(r"0x[0-9a-f]{8}u", m.group(2)) for m in re.finditer(r"#define ZK_WK_([AB])_INIT \{(.*)\}", out.stdout)}
+    src = open(os.path.join(ROOT, "zk_cryptography_research_implementations_b200", "csrc", "dev_transcript.cuh")).read()
+    for name in "AB":
+        body = src[src.index("#define ZK_WK_%s_INIT" % name):]
+        body = body[:body.index("}")]
+        assert re.findall(r"0x[0-9a-f]{8}u", body) == gen[name] and len(gen[name]) == 32
