@@ -588,10 +588,12 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         const FoldTable Wu_ft = make_fold_table(f, Wu);
         ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nm)));
         ctx->launches += 1;
-        ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_CUDA(cudaGetLastError());
         mark(4);
         for (int i = 0; i < 3; ++i) { tabs1[i]->len = nm; }
+        // this sumcheck is the last reader of the layer's values (the next layer works on W[li + 2]): fold them in place
+        // instead of copying 2^m elements into the scratch table first
+        t_W.d = W[li + 1].p;
         zk_table* tabs2[3] = {&t_h2, &t_W, &t_h1};                                                       // B*W + A*1 (A in h1, B in h2)
         zk_sumpoly sp2;
         sp2.P = 1; sp2.D = 2; sp2.nlin = 1; sp2.len = nm;
