@@ -774,6 +774,10 @@ def run_ours(args, wl):
                                                    "shared-memory mailboxes written by the round kernels (no per-round collective)")),
             "clocks": clocks, "proof_digest": proof_digest, "tail_log": ctx.tail_log(),
         }
+        if D > 1:
+            line["config"]["claimed_sum"] = ("0 -- `prove(sum_polynomial, claimed_sum, transcript)` takes the claim from its caller "
+                                             "(sumcheck_gkr_protocol.rs:24-28) and neither the reference nor this prover reads it beyond absorbing it; "
+                                             "round 0 computes s(1) directly for that reason.  Proofs of true claims are what tests/ check.")
         if D == 1:
             line["config"]["note"] = ("value = the n fused rounds with the host Fiat-Shamir per round, table already absorbed; "
                                       "e2e = full Prover::prove from a host table incl. the 32*N-byte serial Keccak absorb")
