@@ -779,7 +779,7 @@ def run_ours(args, wl):
                                              "(sumcheck_gkr_protocol.rs:24-28) and neither the reference nor this prover reads it beyond absorbing it; "
                                              "round 0 computes s(1) directly for that reason.  Proofs of true claims are what tests/ check.")
         if D == 1:
-            line["config"]["note"] = ("value = the n fused rounds with the host Fiat-Shamir per round, table already absorbed; "
+            line["config"]["note"] = ("value = the n fused rounds (host Fiat-Shamir per round, the last ones in the device-tail launch), table already absorbed; "
                                       "e2e = full Prover::prove from a host table incl. the 32*N-byte serial Keccak absorb")
         print(json.dumps(line), flush=True)
     lib.zk_sumpoly_free(ctx.h, sp)
