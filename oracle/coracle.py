@@ -23,10 +23,24 @@ u8p = C.POINTER(C.c_uint8)
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "zkoracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    deps = [os.path.join(_HERE, f) for f in ("zkoracle.c", "zkoracle.h", "field_consts.h", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-C", _HERE, "libzkoracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
+
+
+def set_threads(n: int) -> None:
+    """all-core mode of the data-parallel loops (NOT the reference's behaviour -- it is single-threaded; used for the
+    labelled 'stronger than the reference' CPU baseline of bench.py).  1 restores the restated reference loops."""
+    lib().zko_set_threads(C.c_int(int(n)))
+
+
+def get_threads() -> int:
+    return int(lib().zko_get_threads())
+
+
+def openmp_enabled() -> bool:
+    return bool(lib().zko_openmp_enabled())
 
 
 class _Circuit(C.Structure):

@@ -133,9 +133,39 @@ void zko_fe_add(int fid, const uint64_t a[4], const uint64_t b[4], uint64_t out[
 void zko_fe_sub(int fid, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { fe r; f_sub(fid, &r, (const fe *)a, (const fe *)b); memcpy(out, r.l, 32); }
 void zko_fe_mul(int fid, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) { fe r; f_mul(fid, &r, (const fe *)a, (const fe *)b); memcpy(out, r.l, 32); }
 void zko_fe_inv(int fid, const uint64_t a[4], uint64_t out[4]) { fe r; f_inv(fid, &r, (const fe *)a); memcpy(out, r.l, 32); }
+/* ---- optional all-core mode (NOT the reference's behaviour: the reference is single-threaded, no rayon) ----
+ * zko_set_threads(n > 1) lets the data-parallel loops of the prover path (fold, element-wise reduce, sums, byte
+ * conversion) run on n OpenMP threads; the results are the same field elements.  bench.py reports it as a separate,
+ * labelled "stronger than the reference" baseline.  Default 1: every loop runs exactly as restated from the reference. */
+static int g_threads = 1;
+void zko_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+int zko_get_threads(void) { return g_threads; }
+int zko_openmp_enabled(void) {
+#ifdef _OPENMP
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 void zko_fe_sum(int fid, const uint64_t *v, uint64_t n, uint64_t out[4]) {
     fe acc = f_zero();
-    for (uint64_t i = 0; i < n; ++i) f_add(fid, &acc, &acc, (const fe *)(v + 4 * i));
+    if (g_threads > 1 && n >= 4096) {
+        enum { MAXT = 256 };
+        int nt = g_threads > MAXT ? MAXT : g_threads;
+        fe part[MAXT];
+        for (int t = 0; t < nt; ++t) part[t] = f_zero();
+#pragma omp parallel for num_threads(nt) schedule(static)
+        for (int t = 0; t < nt; ++t) {
+            uint64_t lo = n * (uint64_t)t / nt, hi = n * (uint64_t)(t + 1) / nt;
+            fe a = f_zero();
+            for (uint64_t i = lo; i < hi; ++i) f_add(fid, &a, &a, (const fe *)(v + 4 * i));
+            part[t] = a;
+        }
+        for (int t = 0; t < nt; ++t) f_add(fid, &acc, &acc, &part[t]);
+    } else {
+        for (uint64_t i = 0; i < n; ++i) f_add(fid, &acc, &acc, (const fe *)(v + 4 * i));
+    }
     memcpy(out, acc.l, 32);
 }
 
@@ -272,6 +302,18 @@ int zko_mle_partial_evaluate(int fid, const uint64_t *in_, uint64_t len, uint32_
     if (!is_pow2(half)) return -1;
     uint32_t nvars = ilog2_u64(len);
     uint32_t power = nvars - 1 - var;           /* :82 */
+    if (g_threads > 1 && half >= 4096) {        /* all-core mode: same pairs, index computed instead of walked */
+        const uint64_t low_mask = (1ull << power) - 1;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (uint64_t i = 0; i < half; ++i) {
+            uint64_t j = ((i & ~low_mask) << 1) | (i & low_mask);
+            fe d, m;
+            f_sub(fid, &d, &in[j | (1ull << power)], &in[j]);
+            f_mul(fid, &m, r, &d);
+            f_add(fid, &out[i], &in[j], &m);
+        }
+        return 0;
+    }
     uint64_t i = 0, j = 0;
     while (i < half) {                          /* :69 */
         const fe *y1 = &in[j];                  /* :70 */
@@ -304,6 +346,7 @@ int zko_mle_evaluate(int fid, const uint64_t *in, uint64_t len, const uint64_t *
 }
 /* convert_to_bytes -- evaluation_form.rs:35-43 */
 void zko_mle_to_bytes(int fid, const uint64_t *in, uint64_t len, uint8_t *out) {
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && len >= 4096)
     for (uint64_t i = 0; i < len; ++i) zko_fe_to_bytes_be(fid, in + 4 * i, out + 32 * i);
 }
 /* scalar_mul -- evaluation_form.rs:49-57 */
@@ -337,10 +380,14 @@ void zko_sumpoly_reduce(int fid, const uint64_t *tables, uint32_t P, uint32_t D,
         memcpy(prod, t0, len * 32);                                  /* product_polynomial.rs:64 */
         for (uint32_t d = 1; d < D; ++d) {
             const fe *td = (const fe *)(tables + (uint64_t)(p * D + d) * len * 4);
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && len >= 4096)
             for (uint64_t i = 0; i < len; ++i) f_mul(fid, &prod[i], &prod[i], &td[i]); /* :66-70 */
         }
         if (p == 0) memcpy(out, prod, len * 32);                     /* sum_polynomial.rs:63-65 */
-        else for (uint64_t i = 0; i < len; ++i) f_add(fid, &out[i], &out[i], &prod[i]); /* :67-73 */
+        else {
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && len >= 4096)
+            for (uint64_t i = 0; i < len; ++i) f_add(fid, &out[i], &out[i], &prod[i]); /* :67-73 */
+        }
     }
     free(prod);
 }

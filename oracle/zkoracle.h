@@ -38,6 +38,11 @@ extern "C" {
 
 enum { ZKO_BN254_FQ = 0, ZKO_BN254_FR = 1, ZKO_BLS12_381_FR = 2 };
 
+/* ---- all-core mode for the timed CPU baseline (default 1 thread = the reference's behaviour; see zkoracle.c) ---- */
+void zko_set_threads(int n);
+int  zko_get_threads(void);
+int  zko_openmp_enabled(void);    /* 0: built without OpenMP, zko_set_threads has no effect */
+
 /* ---- field (ark-ff 0.5.0 MontBackend restated) ---- */
 void zko_fe_from_u64(int fid, uint64_t v, uint64_t out[4]);
 void zko_fe_from_canonical(int fid, const uint64_t in[4], uint64_t out[4]); /* in < p, plain -> Montgomery */

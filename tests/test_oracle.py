@@ -213,3 +213,31 @@ def test_generalised_python_gkr_model_reduces_to_the_reference_shape():
         assert a.sumcheck_proofs == b.sumcheck_proofs and a.claimed_sum == b.claimed_sum
         assert a.wb_evaluations == b.wb_evaluations and a.wc_evaluations == b.wc_evaluations
         assert po.gkr_verify(layers, a, inputs, p)
+
+
+def test_all_core_mode_gives_the_same_proofs(co):
+    """zko_set_threads(n > 1) only changes who runs the data-parallel loops (the labelled all-core CPU baseline of
+    bench.py); every output is the same field element as in the single-threaded, reference-shaped mode"""
+    import numpy as np
+    fid = 0
+    rng = np.random.default_rng(3)
+    n = 1 << 13
+    raw = rng.integers(0, 1 << 62, size=(2, 2, n, 4), dtype=np.uint64)
+    raw[..., 3] &= np.uint64((1 << 58) - 1)
+    claimed = np.zeros(4, dtype=np.uint64)
+    co.lib().zko_fe_sum(fid, co._p(co.sumpoly_reduce(fid, raw)), n, co._p(claimed))
+    try:
+        outs = []
+        for threads in (1, 4):
+            co.set_threads(threads)
+            assert co.get_threads() == threads
+            c2 = np.zeros(4, dtype=np.uint64)
+            co.lib().zko_fe_sum(fid, co._p(co.sumpoly_reduce(fid, raw)), n, co._p(c2))
+            assert np.array_equal(c2, claimed)
+            outs.append((co.product_prove(fid, raw, claimed, co.Transcript()), co.basic_prove(fid, raw[0, 0]),
+                         co.mle_evaluate(fid, raw[0, 1], raw[1, 0][:13]), co.mle_to_bytes(fid, raw[1, 1])))
+    finally:
+        co.set_threads(1)
+    (p1, b1, e1, y1), (p4, b4, e4, y4) = outs
+    assert all(np.array_equal(x, y) for x, y in zip(p1, p4)) and all(np.array_equal(x, y) for x, y in zip(b1, b4))
+    assert np.array_equal(e1, e4) and y1 == y4
