@@ -74,22 +74,29 @@ def cpu_prove_once(field: int, P: int, D: int, log2: int, threads: int = 1):
 
 
 def _cpu_prove_once(co, field: int, P: int, D: int, log2: int):
+    """the sample is the head of the GPU arm's own tables: entries 0 .. 2^log2 - 1 of table i under SEED, from the oracle's
+    restatement of the device generator (zko_table_generate == zk_table_generate, tests/test_oracle.py)"""
     n = 1 << log2
-    rng = np.random.default_rng(SEED)
-    if D == 1:
-        tab = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
-        tab[:, 3] &= np.uint64((1 << 58) - 1)
-        t0 = time.perf_counter()
-        co.basic_prove(field, tab)
-        return time.perf_counter() - t0
-    # the reference panics on a single product (sum_polynomial.rs:58-61): f*g is posed as f*g + 0*0
-    Pref = max(P, 2)
-    tabs = np.zeros((Pref, D, n, 4), dtype=np.uint64)
-    tabs[:P] = rng.integers(0, 1 << 62, size=(P, D, n, 4), dtype=np.uint64)
-    tabs[..., 3] &= np.uint64((1 << 58) - 1)
-    claimed = np.zeros(4, dtype=np.uint64)
+    threads = co.get_threads()
+    co.set_threads(os.cpu_count() or 1)          # generating the inputs is not part of the timed prove
+    try:
+        if D == 1:
+            tab = co.table_generate(field, SEED, 0, n)
+        else:
+            # the reference panics on a single product (sum_polynomial.rs:58-61): f*g is posed as f*g + 0*0
+            Pref = max(P, 2)
+            tabs = np.zeros((Pref, D, n, 4), dtype=np.uint64)
+            for i in range(P * D):
+                tabs[i // D, i % D] = co.table_generate(field, SEED, i, n)
+            claimed = np.zeros(4, dtype=np.uint64)
+            co.lib().zko_fe_sum(field, co._p(co.sumpoly_reduce(field, tabs)), n, co._p(claimed))    # the true claimed sum
+    finally:
+        co.set_threads(threads)
     t0 = time.perf_counter()
-    co.product_prove(field, tabs, claimed, co.Transcript())
+    if D == 1:
+        co.basic_prove(field, tab)
+    else:
+        co.product_prove(field, tabs, claimed, co.Transcript())
     return time.perf_counter() - t0
 
 
@@ -127,55 +134,74 @@ def cpu_gkr_once(field: int, depth: int):
 def wide_circuit_arrays(width_log2: int, depth: int = 16, seed: int = SEED):
     """depth layers of 2^w gates each.  Layers 1..depth-1: gate g drives output g from two seeded wires of the layer below;
     layer 0 reduces the 2^w wires below it into TWO outputs (gate g reads wire g and a seeded wire, output g mod 2), so the
-    circuit keeps the reference's output shape (one output bit -> one challenge r_a, 64 bytes absorbed).  Duplicate-free."""
+    circuit keeps the reference's output shape (one output bit -> one challenge r_a, 64 bytes absorbed).  Duplicate-free.
+    Returned in the C-ABI's own flat layout (uint64 layer offsets, uint32 indices, uint8 operators): no conversion copies."""
     rng = np.random.default_rng(seed)
     n = 1 << width_log2
-    layers = []
+    left = np.empty(depth * n, dtype=np.uint32)
+    right = np.empty(depth * n, dtype=np.uint32)
+    out = np.empty(depth * n, dtype=np.uint32)
+    op = np.empty(depth * n, dtype=np.uint8)
+    g = np.arange(n, dtype=np.uint32)
     for li in range(depth):
-        g = np.arange(n, dtype=np.int64)
-        arr = np.zeros((n, 4), dtype=np.int64)
-        arr[:, 1] = rng.integers(0, n, size=n)
-        arr[:, 3] = rng.integers(0, 2, size=n)
+        sl = slice(li * n, (li + 1) * n)
+        right[sl] = rng.integers(0, n, size=n, dtype=np.uint32)
+        op[sl] = rng.integers(0, 2, size=n, dtype=np.uint8)
         if li == 0:
-            arr[:, 0] = g
-            arr[:, 2] = g & 1
+            left[sl] = g
+            out[sl] = g & 1
         else:
-            arr[:, 0] = rng.integers(0, n, size=n)
-            arr[:, 2] = g
-        layers.append(arr)
+            left[sl] = rng.integers(0, n, size=n, dtype=np.uint32)
+            out[sl] = g
+    off = np.arange(depth + 1, dtype=np.uint64) * np.uint64(n)
     bits = [1] + [width_log2] * depth
-    return bits, layers
+    return bits, (off, left, right, out, op)
 
 
-def run_gkr_wide(args, wl):
+def keccak_digest(arrays) -> str:
+    """Keccak-256 (the transcript's own hash) of the concatenated little-endian limb bytes of the proof arrays"""
+    from zk_cryptography_research_implementations_b200.transcripts import Transcript
+    tr = Transcript()
+    for a in arrays:
+        tr.append(np.ascontiguousarray(a, dtype=np.uint64).tobytes())
+    return tr.sample_random_challenge().hex()
+
+
+def run_gkr_wide(args, wl, steps=None, warmup=None):
     field, fname, P, D, w_default, desc = wl
-    w = args.log2 or w_default
+    w = args.log2 if (args.log2 and args.workload == "gkr_wide") else w_default
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
     depth = 16
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return          # single-GPU workload: 704 latency-bound rounds over 128 MiB tables do not shard usefully (DESIGN.md)
+        return None     # single-GPU workload: 704 latency-bound rounds over 128 MiB tables do not shard usefully (DESIGN.md)
     if args.impl == "reference":
         args.workload = "gkr"
         return run_gkr(args, WORKLOADS["gkr"])
     import torch
     import zk_cryptography_research_implementations_b200 as zk
     from zk_cryptography_research_implementations_b200 import gkr
-    torch.cuda.set_device(0)
-    ctx = zk.Context(field, 0, stream=torch.cuda.current_stream().cuda_stream)
-    bits, layers = wide_circuit_arrays(w, depth)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    ctx = zk.Context(field, local_rank, stream=torch.cuda.current_stream().cuda_stream)
     t0 = time.perf_counter()
-    circuit = gkr.WideCircuit(ctx, bits, layers)
+    bits, flat = wide_circuit_arrays(w, depth)
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    circuit = gkr.WideCircuit(ctx, bits, flat=flat)      # upload + range / duplicate checks + three CSR orderings per layer, on the GPU
+    ctx.synchronize()
     setup_s = time.perf_counter() - t0
-    I = gkr_inputs(field, w)
-    dev_I = ctx.upload(I)                                # value: the input layer is resident in HBM when the clock starts
+    dev_I = ctx.generate(SEED + 1, 0, 1 << w)            # value: the input layer is resident in HBM when the clock starts
+    I = dev_I.download()
     proof = None
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         proof = gkr.prove_wide(ctx, circuit, dev_I)
     ctx.set_profiling(True)
     ctx.reset_stats()
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local_rank)
     times = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -195,7 +221,7 @@ def run_gkr_wide(args, wl):
             host_I[:] = I
             gkr.prove_wide(ctx, circuit, host_I)
             ts = []
-            for _ in range(max(1, min(args.steps, args.e2e_steps))):
+            for _ in range(max(1, min(steps, args.e2e_steps))):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 proof_e = gkr.prove_wide(ctx, circuit, host_I)
@@ -206,6 +232,11 @@ def run_gkr_wide(args, wl):
             del host_I
             ctx.lib.zk_pinned_free(pin)
     clocks = sampler.stop()
+    # after the timed region: the reference's verifier (gkr_protocol.rs:146-236) over this very proof, wiring predicates
+    # evaluated from the gate list on the GPU, the input layer's W(u), W(v) by the evaluate kernels
+    t0 = time.perf_counter()
+    verified = bool(gkr.verify_wide(ctx, circuit, proof, dev_I))
+    verify_ms = (time.perf_counter() - t0) * 1e3
     hbm_peak, peak_src = peaks()
     achieved = st["round_bytes"] / (st["round_ms"] * 1e-3) / 1e9 if st["round_ms"] > 0 else 0.0
     cpu = None
@@ -217,26 +248,36 @@ def run_gkr_wide(args, wl):
                          "express or hold a 2^%d-wide layer; oracle C restatement, 1 thread" % (d, d, (1 << d) - 1, w)}
     rounds = circuit.total_rounds()
     coeffs = np.stack([p.coefficients for sp in proof.sumcheck_proofs for p in sp.round_univariate_polynomials])
-    line = {"metric": "gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    # algorithmic HBM bytes of one prove: per layer 2 phases x 128 x 3 tables x 2^w, plus the gate passes
+    alg_bytes = depth * (2 * 128.0 * 3 * (1 << w) + 3 * 48.0 * (1 << w))
+    line = {"metric": "gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": 1, "steps": steps, "warmup": warmup,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
             "config": {"workload": "gkr_wide: " + desc, "field": fname, "depth": depth, "width_log2": w, "gates": depth << w,
                        "layer_bits": bits, "sumcheck_rounds": rounds, "prover": "sparse two-phase (csrc/gkr_wide.cu)",
-                       "circuit_setup_s": setup_s, "l2": "per phase 4 tables x %d MiB" % ((32 << w) >> 20)},
+                       "circuit_setup_s": setup_s,
+                       "circuit_setup_note": "NOT inside `value`: zk_wide_circuit_create = upload of the gate lists + range / duplicate checks + the three "
+                                             "CSR orderings of every layer, built on the GPU (the reference builds its wiring tables inside prove, "
+                                             "arithmetic_circuit.rs:126-163); generating the synthetic gate lists with numpy took %.2f s more" % gen_s,
+                       "l2": "per phase 3 tables x %d MiB" % ((32 << w) >> 20)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "fold_evals_kernel / round_evals_kernel / sumcheck_tail_kernel <%s,P=1,D=2,+1 linear table> (%d launches; most are on tables far smaller than L2: "
+                         "peak_source": peak_src, "kernel": "sumcheck round kernels <%s,P=1,D=2,+1 linear table> (%d launches; most are on tables far smaller than L2: "
                                    "latency-bound, the fraction is not a bandwidth statement)" % (fname, st["round_launches"]),
-                         "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)},
+                         "kernel_ms_per_step": st["round_ms"] / max(steps, 1),
+                         "whole_prove": {"algorithmic_bytes": alg_bytes, "hbm_floor_ms": alg_bytes / (hbm_peak * 1e9) * 1e3,
+                                         "frac": alg_bytes / (hbm_peak * 1e9) * 1e3 / ms}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(I.nbytes), "d2h_bytes_per_step": int(rounds * 4 * 32),
                     "call": "zk_gkr_prove_wide: input layer in pinned host memory -> proof on the host (the circuit's CSR lives on the GPU); "
                             "`value` is zk_gkr_prove_wide_device with the input layer already in HBM"},
             "gpu_launches": st["launches"], "clocks": clocks, "tail_log": ctx.tail_log(),
-            "proof_digest": int(np.bitwise_xor.reduce(coeffs.reshape(-1))) & 0xFFFFFFFF}
-    print(json.dumps(line), flush=True)
+            "verified": verified, "verify_ms": verify_ms,
+            "verified_by": "zk_gkr_verify_wide_device (gkr_protocol.rs:146-236) on the proof of the last timed step",
+            "proof_digest": keccak_digest([coeffs, proof.claimed_sum, proof.wb_evaluations, proof.wc_evaluations])}
     dev_I.free()
     circuit.close()
     ctx.close()
+    return line
 
 
 def run_gkr(args, wl):
@@ -245,7 +286,7 @@ def run_gkr(args, wl):
     depth = args.log2 or depth_default
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     if args.impl == "reference":
         d = min(depth, args.cpu_depth)
         times = [cpu_gkr_once(field, d) for _ in range(max(args.steps, 1))]
@@ -257,14 +298,14 @@ def run_gkr(args, wl):
                 "cpu_baseline": {"value": t * 1e3, "unit": "ms", "cores": 1, "kind": "port",
                                  "sample": "depth-%d circuit (dense 2^(3i+2) wiring tables like the reference), oracle C restatement, 1 thread" % d},
                 "e2e": {"value": t * 1e3, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
-        return
+        return line
     import torch
     import zk_cryptography_research_implementations_b200 as zk
     from zk_cryptography_research_implementations_b200 import gkr
     from zk_cryptography_research_implementations_b200.circuit import Circuit, Gate, Layer
-    torch.cuda.set_device(0)
-    ctx = zk.Context(field, 0, stream=torch.cuda.current_stream().cuda_stream)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    ctx = zk.Context(field, local_rank, stream=torch.cuda.current_stream().cuda_stream)
     layers = synthetic_circuit(depth)
     circuit = Circuit.new(field, [Layer.new([Gate.new(*g) for g in l]) for l in layers])
     I = gkr_inputs(field, depth)
@@ -272,7 +313,7 @@ def run_gkr(args, wl):
         gkr.prove(ctx, circuit, I)
     ctx.set_profiling(True)
     ctx.reset_stats()
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local_rank)
     times = []
     for _ in range(args.steps):
         torch.cuda.synchronize()
@@ -305,29 +346,32 @@ def run_gkr(args, wl):
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": int(I.nbytes), "d2h_bytes_per_step": int(rounds * 4 * 32),
                     "note": "value already is the host-to-host zk_gkr_prove call (circuit + inputs on the host, proof on the host)"},
             "gpu_launches": st["launches"], "clocks": clocks,
-            "proof_digest": int(np.bitwise_xor.reduce(np.stack([p.coefficients for sp in proof.sumcheck_proofs for p in sp.round_univariate_polynomials]).reshape(-1))) & 0xFFFFFFFF}
-    print(json.dumps(line), flush=True)
+            "verified": bool(gkr.verify(ctx, circuit, proof, I)),
+            "verified_by": "zk_gkr_verify (gkr_protocol.rs:146-236) on the proof of the last timed step",
+            "proof_digest": keccak_digest([np.stack([p.coefficients for sp in proof.sumcheck_proofs for p in sp.round_univariate_polynomials]), proof.claimed_sum])}
     ctx.close()
+    return line
 
 
-def run_mle(args, wl):
+def run_mle(args, wl, log2=None, sweep=None, steps=None, warmup=None):
     """configs[4]: MLE evaluate (all n challenges, one read of the table per 3 variables) and one partial_evaluate,
     against the HBM roofline.  N > 1: table sharded on the low index bits, zk_mle_evaluate_sharded."""
     field, fname, P, D, log2_default, desc = wl
-    log2 = args.log2 or log2_default
+    log2 = log2 or (args.log2 if args.workload == "mle" else 0) or log2_default
+    sweep_arg = args.sweep if sweep is None else sweep
+    n_steps = steps or args.steps
+    n_warm = args.warmup if warmup is None else warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         if rank != 0:
-            return
+            return None
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import coracle as co
         sl = min(log2, args.cpu_log2)
-        rng = np.random.default_rng(SEED)
-        tab = rng.integers(0, 1 << 62, size=(1 << sl, 4), dtype=np.uint64)
-        tab[:, 3] &= np.uint64((1 << 58) - 1)
-        rs = tab[:sl].copy()
+        tab = co.table_generate(field, SEED, 0, 1 << sl)
+        rs = co.table_generate(field, SEED, 99, 64)[:sl].copy()
         times = []
         for _ in range(max(args.steps, 1)):
             t0 = time.perf_counter()
@@ -335,22 +379,19 @@ def run_mle(args, wl):
             times.append(time.perf_counter() - t0)
         t = statistics.mean(times)
         v = (1 << sl) / t / MEGA
-        print(json.dumps({"impl": "reference", "metric": "mle_evaluate_Melems_per_s", "value": v, "unit": "Melems/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery limbs)", "data": "synthetic",
-                          "config": {"workload": "mle: " + desc, "field": fname, "log2_entries": log2},
-                          "cpu_baseline": {"value": v, "unit": "Melems/s", "cores": 1, "kind": "port",
-                                           "sample": "evaluate of a 2^%d-entry sample, oracle C restatement (n folds with fresh vectors), 1 thread" % sl},
-                          "e2e": {"value": v, "unit": "Melems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
-        return
+        return {"impl": "reference", "metric": "mle_evaluate_Melems_per_s", "value": v, "unit": "Melems/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery limbs)", "data": "synthetic",
+                "config": {"workload": "mle: " + desc, "field": fname, "log2_entries": log2, "cpu_sample_log2": sl},
+                "cpu_baseline": {"value": v, "unit": "Melems/s", "cores": 1, "kind": "port",
+                                 "sample": "evaluate of the first 2^%d entries of the seeded table, oracle C restatement (n folds with fresh vectors), 1 thread" % sl},
+                "e2e": {"value": v, "unit": "Melems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     import torch
     import torch.distributed as dist
     import zk_cryptography_research_implementations_b200 as zk
     from zk_cryptography_research_implementations_b200 import sharded
     from zk_cryptography_research_implementations_b200.core import _ptr
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = zk.Context(field, local_rank, stream=torch.cuda.current_stream().cuda_stream)
     if world > 1:
         sharded.init_comm(ctx)
@@ -371,11 +412,11 @@ def run_mle(args, wl):
         ctx.check(lib.zk_mle_evaluate_sharded(ctx.h, table.h, _ptr(rs), log2, _ptr(out)))
 
     def timed(fn, prep):
-        for _ in range(args.warmup):
+        for _ in range(n_warm):
             prep(); barrier(); fn(); barrier()
         ctx.reset_stats()
         ts = []
-        for _ in range(args.steps):
+        for _ in range(n_steps):
             prep(); barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); barrier()
@@ -387,7 +428,7 @@ def run_mle(args, wl):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_eval = timed(ev, lambda: None)
-    digest = int(np.bitwise_xor.reduce(out)) & 0xFFFFFFFF
+    result = out.copy()
     launches = ctx.stats()["launches"]
     # one partial_evaluate of variable 0 (in place: read N, write N/2), table refilled between steps
     r0 = np.ascontiguousarray(rs[0])
@@ -397,7 +438,7 @@ def run_mle(args, wl):
     hbm_peak, peak_src = peaks()
     # --sweep a,b,c: the same two measurements at other table sizes (BASELINE.json configs[4] is a sweep), same context
     sweep = []
-    for lg in [int(x) for x in args.sweep.split(",") if x] if args.sweep else []:
+    for lg in [int(x) for x in sweep_arg.split(",") if x] if sweep_arg else []:
         if lg == log2 or (1 << lg) < world:
             continue
         mm = (1 << lg) // world
@@ -406,56 +447,56 @@ def run_mle(args, wl):
         ms_e = timed(lambda: ctx.check(lib.zk_mle_evaluate_sharded(ctx.h, t2.h, _ptr(rs2), lg, _ptr(out))), lambda: None)
         r02 = np.ascontiguousarray(rs2[0])
         ms_f = timed(lambda: ctx.check(lib.zk_mle_partial_evaluate(ctx.h, t2.h, 0, _ptr(r02))), lambda: t2.regenerate(SEED, 0, mm, rank, world))
-        sweep.append({"log2_entries": lg, "evaluate_ms": ms_e, "evaluate_elements_per_s": (1 << lg) / (ms_e * 1e-3),
+        sweep.append({"log2_entries": lg, "evaluate_ms": ms_e, "evaluate_Melems_per_s": (1 << lg) / (ms_e * 1e-3) / MEGA,
                       "evaluate_frac_hbm": 32.0 * mm / (ms_e * 1e-3) / 1e9 / hbm_peak,
-                      "partial_evaluate_ms": ms_f, "partial_evaluate_elements_per_s": (1 << lg) / (ms_f * 1e-3),
+                      "partial_evaluate_ms": ms_f, "partial_evaluate_Melems_per_s": (1 << lg) / (ms_f * 1e-3) / MEGA,
                       "partial_evaluate_frac_hbm": 48.0 * mm / (ms_f * 1e-3) / 1e9 / hbm_peak,
                       "l2": "table larger than L2" if mm * 32 > 126e6 else "table fits L2 (timed back to back: L2-resident)"})
         t2.free()
+    line = None
     if rank == 0:
         ach_eval = 32.0 * m / (ms_eval * 1e-3) / 1e9          # algorithmic: ONE read of the table
         ach_fold = 48.0 * m / (ms_fold * 1e-3) / 1e9
         cpu = None
-        if world == 1 and not args.no_cpu:
+        verified = None
+        if not args.no_cpu:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import coracle as co
             sl = min(log2, args.cpu_log2)
-            rng = np.random.default_rng(SEED)
-            tab = rng.integers(0, 1 << 62, size=(1 << sl, 4), dtype=np.uint64)
-            tab[:, 3] &= np.uint64((1 << 58) - 1)
+            co.set_threads(os.cpu_count() or 1)
+            tab = co.table_generate(field, SEED, 0, 1 << sl)
+            co.set_threads(1)
             t0 = time.perf_counter()
-            co.mle_evaluate(field, tab, tab[:sl].copy())
+            want = co.mle_evaluate(field, tab, rs[:sl].copy())
             t = time.perf_counter() - t0
             cpu = {"value": (1 << sl) / t / MEGA, "unit": "Melems/s", "cores": 1, "kind": "port",
-                   "sample": "evaluate of a 2^%d-entry sample (%.2f s), oracle C restatement, 1 thread" % (sl, t)}
-        print(json.dumps({
+                   "sample": "evaluate of the first 2^%d entries of the seeded table (%.2f s), oracle C restatement, 1 thread" % (sl, t)}
+            if sl == log2:      # the oracle evaluated the very table the GPU did: compare the values
+                verified = bool(np.array_equal(want, result))
+        line = {
             "metric": "mle_evaluate_Melems_per_s", "value": N / (ms_eval * 1e-3) / MEGA, "unit": "Melems/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_eval, "higher_is_better": True, "scaling": "strong",
+            "steps": n_steps, "warmup": n_warm, "ms_per_step": ms_eval, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
             "config": {"workload": "mle: " + desc, "field": fname, "log2_entries": log2, "table_bytes_total": N * 32,
                        "sharding": "low index bits across %d rank(s)" % world, "l2": "table larger than L2" if m * 32 > 126e6 else "table fits L2"},
             "roofline": {"bound": "hbm", "achieved": ach_eval, "peak": hbm_peak, "unit": "GB/s", "frac": ach_eval / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "fold_multi_kernel<%s,3> passes (algorithmic bytes = 32 N: one read)" % fname,
-                         "note": "timed around the whole evaluate call (n/3 passes + host fold tables)"},
-            "integer_roofline": {"folds_per_evaluate": N - 1, "imad_wide_per_fold": 84,
-                                 "note": "evaluate is bound by the integer-multiply pipe, not HBM: (N-1) folds x 84 IMAD.WIDE against 32 N bytes; "
-                                         "at the probe's 8.86e12 IMAD.WIDE/s per GPU the floor is %.2f ms (HBM floor %.2f ms) -> %.2f of the slower roofline"
-                                         % ((m - 1) * 84 / 8.86e12 * 1e3, 32.0 * m / (hbm_peak * 1e9) * 1e3, ((m - 1) * 84 / 8.86e12 * 1e3) / ms_eval)},
-            "partial_evaluate": {"ms": ms_fold, "elements_per_s": N / (ms_fold * 1e-3), "achieved_GBps": ach_fold, "frac": ach_fold / hbm_peak,
+                         "peak_source": peak_src, "kernel": "zk_mle_evaluate passes <%s> (algorithmic bytes = 32 N: one read)" % fname,
+                         "note": "timed around the whole evaluate call (all passes + host fold tables)"},
+            "partial_evaluate": {"ms": ms_fold, "Melems_per_s": N / (ms_fold * 1e-3) / MEGA, "achieved_GBps": ach_fold, "frac": ach_fold / hbm_peak,
                                  "kernel": "fold0_kernel (read N, write N/2: 48 N bytes)"},
             "cpu_baseline": cpu, "e2e": None, "gpu_launches": launches, "clocks": clocks, "sweep": sweep,
-            "result_digest": digest}), flush=True)
+            "verified": verified, "verified_by": "oracle mle_evaluate on the same seeded table (only when the CPU sample is the whole table)",
+            "result_digest": keccak_digest([result])}
     barrier()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def run_reference(args, wl):
     field, fname, P, D, log2_default, desc = wl
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     log2 = args.log2 or log2_default
     sample_log2 = min(log2, args.cpu_log2)
     th = max(1, args.cpu_threads)
@@ -464,7 +505,7 @@ def run_reference(args, wl):
     times = [cpu_prove_once(field, P, D, sample_log2, th) for _ in range(args.steps)]
     t = statistics.mean(times)
     value = (1 << sample_log2) / t / MEGA
-    sample = "2^%d-entry sample of the 2^%d workload, oracle C restatement of the reference prover%s, %s" % (
+    sample = "the first 2^%d entries of the 2^%d workload's own seeded tables, oracle C restatement of the reference prover%s, %s" % (
         sample_log2, log2, " (posed as f*g + 0*0, the only form the reference accepts)" if (P == 1 and D > 1) else "",
         "1 thread (the reference is single-threaded)" if th == 1 else "%d OpenMP threads (--cpu-threads: stronger than the single-threaded reference)" % th)
     line = {
@@ -472,20 +513,23 @@ def run_reference(args, wl):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery limbs)",
         "data": "synthetic",
-        "config": config_dict(args.workload, wl, log2, args.gpus),
+        "config": config_dict(args.workload, wl, log2, args.gpus, sample_log2),
         "cpu_baseline": {"value": value, "unit": "Melems/s", "cores": th, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Melems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extrapolation": "the CPU prover's passes are linear in the table length: Melems/s of the 2^%d sample stands for the 2^%d workload "
+                         "(optimistic for the CPU: the sample is more cache-friendly)" % (sample_log2, log2),
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
-def config_dict(name, wl, log2, gpus):
+def config_dict(name, wl, log2, gpus, sample_log2):
+    """identical in both arms (the driver compares them); sample_log2 = size of the CPU arm's bounded sample"""
     field, fname, P, D, _, desc = wl
-    return {"workload": "%s: %s" % (name, desc), "field": fname, "log2_entries": log2, "tables": P * D, "P": P, "D": D,
+    return {"workload": "%s: %s" % (name, desc), "field": fname, "log2_entries": log2, "sample_log2": sample_log2, "tables": P * D, "P": P, "D": D,
             "table_bytes_total": (P * D) << (log2 + 5), "sharding": "low index bits across %d rank(s)" % gpus,
             "l2": "inputs regenerated in HBM between steps (untimed); tables are %s than the 126 MB L2"
                   % ("larger" if ((P * D) << (log2 + 5)) // max(gpus, 1) > 126e6 else "NOT larger"),
-            "seed": SEED}
+            "seed": SEED, "claimed_sum": "the true sum of the seeded tables (computed before the timed region)"}
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -579,7 +623,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
-def run_ours(args, wl):
+def run_ours(args, wl, name=None, log2=None, steps=None, warmup=None):
     import torch
     import torch.distributed as dist
     import zk_cryptography_research_implementations_b200 as zk
@@ -588,16 +632,14 @@ def run_ours(args, wl):
     from zk_cryptography_research_implementations_b200.transcripts import Transcript
 
     field, fname, P, D, log2_default, desc = wl
-    log2 = args.log2 or log2_default
+    name = name or args.workload
+    log2 = log2 or (args.log2 if name == args.workload else 0) or log2_default
+    n_steps = steps or args.steps
+    n_warm = args.warmup if warmup is None else warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream().cuda_stream
     ctx = zk.Context(field, local_rank, stream=stream)
     if world > 1:
@@ -632,6 +674,29 @@ def run_ours(args, wl):
     fin = np.zeros((T, 4), dtype=np.uint64)
     rpolys = np.zeros((n_rounds, 2, 4), dtype=np.uint64)
     claimed = np.zeros(4, dtype=np.uint64)
+
+    def field_sum_over_ranks(elems):
+        """sum over ranks, in the field, of an (k, 4) array of elements (host; only used outside the timed region)"""
+        acc = np.ascontiguousarray(elems, dtype=np.uint64).reshape(-1, 4).copy()
+        if world == 1:
+            return acc
+        t = torch.from_numpy(acc.view(np.int64)).cuda()
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        parts = [g.cpu().numpy().view(np.uint64) for g in gathered]
+        out = np.zeros_like(acc)
+        for part in parts:
+            for k in range(out.shape[0]):
+                out[k] = zk.fe_binop("add", field, out[k], part[k])
+        return out
+
+    if D > 1:
+        # the TRUE claimed sum of the seeded tables, so that the reference's verifier accepts the timed proofs:
+        # s(0) + s(1) of round 0 from the round-0 kernel, summed over the ranks' shards
+        ev = np.zeros((D + 1, 4), dtype=np.uint64)
+        ctx.check(lib.zk_sumcheck_round_evals(ctx.h, sp, _ptr(ev)))
+        ev = field_sum_over_ranks(ev)
+        claimed[:] = zk.fe_binop("add", field, ev[0], ev[1])
 
     def prove_resident():
         if D == 1:
@@ -675,10 +740,48 @@ def run_ours(args, wl):
         return float(t.item()), st
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms, st = timed_steps(prove_resident, regenerate, args.steps, args.warmup, True)
+    ms, st = timed_steps(prove_resident, regenerate, n_steps, n_warm, True)
     clocks = sampler.stop() if sampler else None
     value = N / (ms * 1e-3) / MEGA
-    proof_digest = int(np.bitwise_xor.reduce((coeffs if D > 1 else rpolys).reshape(-1))) & 0xFFFFFFFF
+    proof_digest = keccak_digest([coeffs, chal, fin] if D > 1 else [claimed, rpolys, chal, fin])
+
+    # ---- after the timed region: is the proof of the last timed step a proof?  (every rank holds the same one)
+    #  1. the reference's verifier accepts it (sumcheck_gkr_protocol.rs:69-106 / verifier.rs:23-65 replayed on the host);
+    #  2. the prover's final folded values are the tables' MLE evaluations at the challenges, recomputed from freshly
+    #     regenerated tables by the separate evaluate kernels (sharded over the same ranks), and
+    #  3. the verifier's last claim equals sum_p prod_d of them (the oracle check the reference's caller performs).
+    verify = {}
+    regenerate()
+    evals_at_r = np.zeros((T, 4), dtype=np.uint64)
+    for i in range(T):
+        ctx.check(lib.zk_mle_evaluate_sharded(ctx.h, lib.zk_sumpoly_table(sp, i), _ptr(chal), n_rounds, _ptr(evals_at_r[i])))
+    verify["final_values_are_mle_evaluations"] = bool(np.array_equal(evals_at_r, fin))
+    if D > 1:
+        ok = C.c_int(0)
+        ch_v = np.zeros((n_rounds, 4), dtype=np.uint64)
+        last = np.zeros(4, dtype=np.uint64)
+        tr_v = Transcript()
+        rc = lib.zk_verify_product(field, _ptr(claimed), _ptr(coeffs), n_rounds, D, tr_v.h, _ptr(ch_v), _ptr(last), C.byref(ok))
+        verify["reference_verifier_accepts"] = bool(rc == 0 and ok.value == 1 and np.array_equal(ch_v, chal))
+        total = np.zeros(4, dtype=np.uint64)
+        for pi in range(P):
+            prod = fin[pi * D]
+            for d in range(1, D):
+                prod = zk.fe_binop("mul", field, prod, fin[pi * D + d])
+            total = zk.fe_binop("add", field, total, prod)
+        verify["last_claim_matches_final_values"] = bool(np.array_equal(total, last))
+    else:
+        # plain sumcheck: the round sums telescope and the last claim is the table's evaluation (verifier.rs:44-70); the
+        # challenges themselves are only reproducible with the table absorb, which `value` leaves out (see config.note)
+        claim = claimed.copy()
+        tele = True
+        for k in range(n_rounds):
+            tele = tele and np.array_equal(zk.fe_binop("add", field, rpolys[k, 0], rpolys[k, 1]), claim)
+            diff = zk.fe_binop("sub", field, rpolys[k, 1], rpolys[k, 0])
+            claim = zk.fe_binop("add", field, rpolys[k, 0], zk.fe_binop("mul", field, chal[k], diff))
+        verify["round_sums_telescope"] = bool(tele)
+        verify["last_claim_matches_final_values"] = bool(np.array_equal(claim, fin[0]))
+    verified = all(verify.values())
 
     # ---- roofline of the dominant kernel family (round kernels), CUDA events on the launching stream
     hbm_peak, peak_src = peaks()
@@ -710,7 +813,7 @@ def run_ours(args, wl):
     # ---- integer-multiply ceiling (register-resident probe, same clocks)
     integer = {}
     if rank == 0 and not args.no_probe:
-        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced"), (7, "mul_acc_columns"), (3, "fp64_fma")):
+        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced")):
             ops, pms = C.c_double(), C.c_double()
             ctx.check(lib.zk_arith_probe(ctx.h, kind, 1500, 2, C.byref(ops), C.byref(pms)))
             integer[name + "_Gops"] = ops.value / 1e9
@@ -755,7 +858,7 @@ def run_ours(args, wl):
                 ctx.check(lib.zk_prove_product_sharded(ctx.h, sp, _ptr(claimed), tr.h, _ptr(coeffs), _ptr(chal), _ptr(fin), 0,
                                                        args.collapse_len))
 
-        e_steps = max(1, min(args.steps, args.e2e_steps))
+        e_steps = max(1, min(n_steps, args.e2e_steps))
         ms_e2e, _ = timed_steps(upload_and_prove, lambda: None, e_steps, 1, False)
         d2h = (n_rounds * (D + 1 if D > 1 else 2) + T + 1) * 32
         e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Melems/s", "h2d_bytes_per_step": T * m * 32 * world,
@@ -787,31 +890,64 @@ def run_ours(args, wl):
         except Exception as ex:   # pragma: no cover
             cpu_all = {"value": None, "unavailable": repr(ex)}
 
+    line = None
     if rank == 0:
         line = {
             "metric": "sumcheck_prove_Melems_per_s", "value": value, "unit": "Melems/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "steps": n_steps, "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
-            "config": config_dict(args.workload, wl, log2, world),
+            "config": config_dict(name, wl, log2, world, min(log2, args.cpu_log2)),
             "roofline": roofline, "integer_roofline": integer, "cpu_baseline": cpu, "cpu_baseline_all_cores": cpu_all, "e2e": e2e,
             "gpu_launches": launches,
-            "exchange": (None if world == 1 else ("ncclAllGather per round" if args.nccl_exchange else
-                                                   "shared-memory mailboxes written by the round kernels (no per-round collective)")),
-            "clocks": clocks, "proof_digest": proof_digest, "tail_log": ctx.tail_log(),
+            "exchange": (None if world == 1 else ("ncclAllGather per round" if args.nccl_exchange else ctx_exchange_name(ctx))),
+            "clocks": clocks, "tail_log": ctx.tail_log(),
+            "verified": verified, "verify": verify,
+            "verified_by": "after the timed region, on the proof of the last timed step: zk_verify_product (the reference's verifier) + "
+                           "zk_mle_evaluate_sharded of freshly regenerated tables at the challenges",
+            "proof_digest": proof_digest, "proof_digest_kind": "Keccak-256 of coefficients | challenges | final values (identical at every N)",
         }
-        if D > 1:
-            line["config"]["claimed_sum"] = ("0 -- `prove(sum_polynomial, claimed_sum, transcript)` takes the claim from its caller "
-                                             "(sumcheck_gkr_protocol.rs:24-28) and neither the reference nor this prover reads it beyond absorbing it; "
-                                             "round 0 computes s(1) directly for that reason.  Proofs of true claims are what tests/ check.")
         if D == 1:
-            line["config"]["note"] = ("value = the n fused rounds (host Fiat-Shamir per round, the last ones in the device-tail launch), table already absorbed; "
-                                      "e2e = full Prover::prove from a host table incl. the 32*N-byte serial Keccak absorb")
-        print(json.dumps(line), flush=True)
+            line["note"] = ("value = the n fused rounds, table already absorbed (ZK_FLAG_SKIP_ABSORB: measurement only); "
+                            "e2e = full Prover::prove from a host table incl. the 32*N-byte serial Keccak absorb")
     lib.zk_sumpoly_free(ctx.h, sp)
     barrier()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def ctx_exchange_name(ctx):
+    try:
+        from zk_cryptography_research_implementations_b200 import sharded
+        return sharded.exchange_kind(ctx)
+    except Exception:
+        return "shared-memory mailboxes written by the round kernels (no per-round collective)"
+
+
+def run_extras(args):
+    """The rest of BASELINE.json's metric in the driver's own record: short runs of configs[3] (GKR 16 x 2^22), configs[1]
+    (plain sumcheck 2^24) and configs[4] (MLE sweep), each a full line with its own roofline / cpu_baseline / e2e / clocks.
+    N = 1: all three; N > 1: the sharded MLE point (2^32 at N = 8).  A failing extra is reported, never fatal."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    extras = []
+
+    def attempt(label, fn):
+        try:
+            line = fn()
+            if line is not None:
+                extras.append(line)
+        except Exception as ex:   # pragma: no cover -- must never cost the headline line
+            if world > 1:
+                raise             # a rank that bails out of a collective path alone would hang the others
+            extras.append({"workload": label, "error": repr(ex)})
+
+    if world == 1:
+        attempt("gkr_wide", lambda: run_gkr_wide(args, WORKLOADS["gkr_wide"], steps=min(args.steps, 8), warmup=min(args.warmup, 3)))
+        attempt("plain24", lambda: run_ours(args, WORKLOADS["plain24"], name="plain24", steps=min(args.steps, 10), warmup=min(args.warmup, 3)))
+        attempt("mle", lambda: run_mle(args, WORKLOADS["mle"], log2=28, sweep="20,22,24,26,30", steps=min(args.steps, 5), warmup=min(args.warmup, 3)))
+    else:
+        lg = min(32, 29 + world.bit_length())       # 2^31 at 2 ranks, 2^32 at 4 and 8 (configs[4]: 2^32 sharded over 8 GPUs)
+        attempt("mle", lambda: run_mle(args, WORKLOADS["mle"], log2=lg, sweep="", steps=min(args.steps, 5), warmup=min(args.warmup, 3)))
+    return extras
 
 
 def main():
@@ -834,18 +970,38 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", dest="no_extras",
+                    help="default workload only: skip the short GKR / plain-sumcheck / MLE runs appended as `extra_workloads`")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.workload == "gkr":
-        run_gkr(args, wl)
-    elif args.workload == "gkr_wide":
-        run_gkr_wide(args, wl)
-    elif args.workload == "mle":
-        run_mle(args, wl)
-    elif args.impl == "reference":
-        run_reference(args, wl)
-    else:
-        run_ours(args, wl)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return                   # the CPU arm runs on rank 0 alone; the other ranks exit 0 without work
+        fn = {"gkr": run_gkr, "gkr_wide": run_gkr_wide, "mle": run_mle}.get(args.workload, run_reference)
+        print(json.dumps(fn(args, wl)), flush=True)
+        return
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fn = {"gkr": run_gkr, "gkr_wide": run_gkr_wide, "mle": run_mle}.get(args.workload, run_ours)
+    line = fn(args, wl)
+    if args.workload == "product30" and not args.log2 and not args.no_extras:
+        extras = run_extras(args)
+        if line is not None:
+            line["extra_workloads"] = extras
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

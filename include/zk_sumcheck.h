@@ -29,9 +29,14 @@ enum { ZK_OK = 0, ZK_ERR_ASSERT = -1, ZK_ERR_CUDA = -2, ZK_ERR_ARG = -3 };
 /* flags for the one-shot provers */
 enum {
     ZK_FLAG_DIRECT_S1 = 1,   /* compute s(1) in the kernel every round instead of claim - s(0) */
-    ZK_FLAG_SKIP_ABSORB = 2,   /* zk_prove_basic*: the caller already absorbed the table bytes */
-    ZK_FLAG_NO_CLAIM_ABSORB = 8, /* zk_prove_product: do not absorb claimed_sum first (continuation of a sumcheck whose
-                                  earlier rounds ran in a previous call -- the two phases of a sparse GKR layer) */
+    ZK_FLAG_SKIP_ABSORB = 2,   /* MEASUREMENT ONLY.  zk_prove_basic_device / zk_prove_basic: leave the 32*N-byte table absorb of
+                                  prover.rs:38-39 out of the (internal) transcript, so that the n rounds can be timed without the
+                                  serial host Keccak.  The resulting proof does NOT match the reference or verify; real proofs
+                                  pass 0.  (zk_prove_basic_sharded takes the caller's transcript instead, which carries the
+                                  absorb.)  zk_gkr_prove_wide*: do not absorb the output layer (same caveat). */
+    ZK_FLAG_NO_CLAIM_ABSORB = 8, /* zk_prove_product only: do not absorb claimed_sum first (continuation of a sumcheck whose
+                                  earlier rounds ran in a previous call -- the two phases of a sparse GKR layer).  The sharded
+                                  provers refuse it (ZK_ERR_ARG). */
     ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
     ZK_FLAG_HOST_ROUNDS = 16   /* keep every round on the host-driven path: one kernel + one host Fiat-Shamir step per
@@ -123,8 +128,9 @@ int  zk_mle_tensor_mul(zk_ctx *, const zk_table *wb, const zk_table *wc, zk_tabl
 int  zk_sum_halves(zk_ctx *, const zk_table *t, uint64_t out[8]);
 
 /* ---- SumPolynomial / ProductPolynomial (polynomials/src/composed/{sum,product}_polynomial.rs) ----
- * tables[p*D + d] is factor d of product p; the sumpoly takes ownership of the tables.
- * "different number of variables" if the lengths differ. */
+ * tables[p*D + d] is factor d of product p; the sumpoly takes ownership of the tables (on success only), which must be
+ * pairwise distinct (folds are in place).  "different number of variables" if the lengths differ.  (P, D) must be one of
+ * (1,1) (1,2) (2,2) (3,2) (4,2) (1,3) (2,3). */
 int  zk_sumpoly_create(zk_ctx *, zk_table *const *tables, uint32_t P, uint32_t D, zk_sumpoly **out);
 void zk_sumpoly_free(zk_ctx *, zk_sumpoly *);
 uint64_t zk_sumpoly_len(const zk_sumpoly *);
@@ -193,12 +199,17 @@ int  zk_gkr_verify(zk_ctx *, const zk_circuit_desc *, const uint64_t *output, ui
 /* ---- GKR for wide layers: sparse two-phase layer sumcheck over 2^m-entry tables (m = log2 width of the layer below)
  * instead of the reference's dense 2^(3i+2) / 4^(i+1) tables; identical round polynomials on reference-shaped
  * circuits.  layer_bits[li] = log2(#values of layer li), li = 0..n_layers (last = inputs); gates as in
- * zk_circuit_desc, duplicate-free.  The circuit (three CSR orderings per layer) lives on the GPU. */
+ * zk_circuit_desc, duplicate-free (checked: ZK_ERR_ARG "duplicate gate"; indices are range-checked first).  The
+ * circuit lives on the GPU as three CSR orderings per layer, built there (histogram, scan, scatter): the step the reference
+ * performs inside prove (circuit/src/arithmetic_circuit.rs:126-163 via gkr_protocol.rs:58). */
 int  zk_wide_circuit_create(zk_ctx *, uint32_t n_layers, const uint32_t *layer_bits, const uint64_t *layer_off,
                             const uint32_t *left, const uint32_t *right, const uint32_t *out, const uint8_t *op,
                             zk_wide_circuit **result);
 void zk_wide_circuit_free(zk_ctx *, zk_wide_circuit *);
 uint64_t zk_wide_circuit_total_rounds(const zk_wide_circuit *);   /* sum over layers of 2 * layer_bits[li+1] */
+/* log2 of the output layer as the prover sees it: layer_bits[0], except that a single output (layer_bits[0] == 0) is the
+ * reference's padded [out, 0] layer (gkr_protocol.rs:43-51) and reports 1 -- `output` buffers hold 2^this elements */
+uint32_t zk_wide_circuit_output_bits(const zk_wide_circuit *);
 /* gkr_protocol::prove (gkr_protocol.rs:26-143).  output (may be NULL): 2^layer_bits[0] elements; the rest as
  * zk_gkr_prove.  The output claim binds layer_bits[0] successive challenges (one in the reference's shape).
  * ZK_FLAG_SKIP_ABSORB: do not absorb the output layer into the transcript. */
@@ -209,6 +220,17 @@ int  zk_gkr_prove_wide(zk_ctx *, const zk_wide_circuit *, const uint64_t *inputs
 int  zk_gkr_prove_wide_device(zk_ctx *, const zk_wide_circuit *, const zk_table *inputs, uint64_t *output,
                               uint64_t *claimed_sum, uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges,
                               uint64_t *wb, uint64_t *wc, uint32_t flags);
+
+/* gkr_protocol::verify (gkr_protocol.rs:146-236, claim helpers gkr/src/utils.rs:84-135) of a proof laid out as
+ * zk_gkr_prove_wide writes it (output: 2^layer_bits[0] elements).  add_i / mul_i at the sumcheck point are evaluated from
+ * the gate list on the GPU (eq tables), W(u) / W(v) of the input layer by the evaluate kernels.  `flags` as given to the
+ * prover.  *ok = 1 iff the reference's verifier would return true. */
+int  zk_gkr_verify_wide(zk_ctx *, const zk_wide_circuit *, const uint64_t *output, const uint64_t *layer_claims,
+                        const uint64_t *coeffs, const uint64_t *wb, const uint64_t *wc, const uint64_t *inputs,
+                        uint64_t n_inputs, uint32_t flags, int *ok);
+int  zk_gkr_verify_wide_device(zk_ctx *, const zk_wide_circuit *, const uint64_t *output, const uint64_t *layer_claims,
+                               const uint64_t *coeffs, const uint64_t *wb, const uint64_t *wc, const zk_table *inputs,
+                               uint32_t flags, int *ok);
 
 /* ---- one process per GPU: tables sharded on the LOW index bits (rank q holds entries q, q+G, q+2G, ...) ----
  * NCCL over NVLink/NVSwitch carries one all-gather of (D+1) elements per round; folds stay local.
@@ -236,8 +258,7 @@ int  zk_prove_basic_sharded(zk_ctx *, zk_table *local, zk_transcript *, uint64_t
 int  zk_mle_evaluate_sharded(zk_ctx *, const zk_table *local, const uint64_t *values, uint32_t n_values, uint64_t out[4]);
 
 /* ---- measurement: register-resident field arithmetic, no memory traffic (the IMAD-pipe ceiling) ----
- * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate, 3: FP64 FMA,
- * 4: IMAD.WIDE.U32, 5: 32-bit IMAD, 6: carry-chained IMAD.WIDE.U32.X (raw pipe rates). */
+ * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate. */
 int  zk_arith_probe(zk_ctx *, int kind, uint32_t iters, int blocks_per_sm, double *ops_per_s, double *ms);
 
 #ifdef __cplusplus

@@ -353,3 +353,86 @@ def gkr_prove(fid: int, circuit: Circuit, inputs: np.ndarray) -> GkrProof:
 def gkr_verify(fid: int, circuit: Circuit, proof: GkrProof, inputs: np.ndarray) -> bool:
     inputs = _arr(inputs).reshape(-1, 4)
     return bool(lib().zko_gkr_verify(fid, C.byref(circuit.c), C.byref(proof.c), _p(inputs), C.c_uint64(inputs.shape[0])))
+
+
+# ------------------------------------------------------------------ GKR over explicit layer widths (gate-list form)
+class SparseCircuit:
+    """layer_bits[li] = log2(#values of layer li), li = 0..L (last = inputs); layers: per layer a list of
+    (left, right, out, op) tuples or an (n, 4) integer array with those columns."""
+
+    def __init__(self, layer_bits: Sequence[int], layers):
+        self.bits = np.array([int(b) for b in layer_bits], dtype=np.uint32)
+        self.L = len(layers)
+        assert len(self.bits) == self.L + 1
+        arrs = [np.asarray(l, dtype=np.int64).reshape(-1, 4) for l in layers]
+        off = [0]
+        for a in arrs:
+            off.append(off[-1] + a.shape[0])
+        flat = np.concatenate(arrs) if arrs else np.zeros((0, 4), dtype=np.int64)
+        self.off = np.array(off, dtype=np.uint64)
+        self.left = np.ascontiguousarray(flat[:, 0].astype(np.uint32))
+        self.right = np.ascontiguousarray(flat[:, 1].astype(np.uint32))
+        self.out = np.ascontiguousarray(flat[:, 2].astype(np.uint32))
+        self.op = np.ascontiguousarray(flat[:, 3].astype(np.uint8))
+
+    def total_rounds(self) -> int:
+        return int(sum(2 * int(b) for b in self.bits[1:]))
+
+    def _args(self):
+        return (C.c_uint32(self.L), self.bits.ctypes.data_as(u32p), self.off.ctypes.data_as(u64p), self.left.ctypes.data_as(u32p),
+                self.right.ctypes.data_as(u32p), self.out.ctypes.data_as(u32p), self.op.ctypes.data_as(u8p))
+
+
+class SparseGkrProof(GkrProof):
+    def __init__(self, circuit: SparseCircuit):
+        L, R = circuit.L, circuit.total_rounds()
+        self.L, self.R = L, R
+        self.output = np.zeros((1 << int(max(circuit.bits[0], 1)), 4), dtype=np.uint64)
+        self.layer_claims = np.zeros((L, 4), dtype=np.uint64)
+        self.coeffs = np.zeros((max(R, 1), 3, 4), dtype=np.uint64)
+        self.challenges = np.zeros((max(R, 1), 4), dtype=np.uint64)
+        self.wb = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
+        self.wc = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
+        self.c = _GkrProof(_p(self.output), 0, (C.c_uint64 * 4)(), _p(self.layer_claims), _p(self.coeffs),
+                           _p(self.challenges), _p(self.wb), _p(self.wc))
+
+
+def gkr_prove_sparse(fid: int, circuit: SparseCircuit, inputs: np.ndarray) -> SparseGkrProof:
+    """gkr_protocol::prove (gkr_protocol.rs:26-143) with the wiring predicates evaluated from the gate list"""
+    inputs = _arr(inputs).reshape(-1, 4)
+    pf = SparseGkrProof(circuit)
+    rc = lib().zko_gkr_prove_sparse(fid, *circuit._args(), _p(inputs), C.c_uint64(inputs.shape[0]), C.byref(pf.c))
+    if rc:
+        raise AssertionError("oracle gkr_prove_sparse failed (%d)" % rc)
+    return pf
+
+
+def gkr_verify_sparse(fid: int, circuit: SparseCircuit, proof, inputs: np.ndarray) -> bool:
+    """gkr_protocol::verify (gkr_protocol.rs:146-236); `proof` is anything with a `.c` _GkrProof (see make_gkr_proof)"""
+    inputs = _arr(inputs).reshape(-1, 4)
+    return bool(lib().zko_gkr_verify_sparse(fid, *circuit._args(), C.byref(proof.c), _p(inputs), C.c_uint64(inputs.shape[0])))
+
+
+def make_gkr_proof(circuit: SparseCircuit, output, claimed_sum, layer_claims, coeffs, wb, wc) -> SparseGkrProof:
+    """wrap proof arrays (e.g. what the CUDA prover returned) for gkr_verify_sparse"""
+    pf = SparseGkrProof(circuit)
+    out = _arr(output).reshape(-1, 4)
+    pf.output[: out.shape[0]] = out
+    pf.c.n_output = out.shape[0]
+    pf.layer_claims[:] = _arr(layer_claims).reshape(-1, 4)
+    c = _arr(coeffs).reshape(-1, 3, 4)
+    pf.coeffs[: c.shape[0]] = c
+    for name, src in (("wb", wb), ("wc", wc)):
+        a = _arr(src).reshape(-1, 4)
+        getattr(pf, name)[: a.shape[0]] = a
+    cs = _arr(claimed_sum).reshape(4)
+    for k in range(4):
+        pf.c.claimed_sum[k] = int(cs[k])
+    return pf
+
+
+def table_generate(fid: int, seed: int, table_id: int, n: int, first: int = 0, step: int = 1) -> np.ndarray:
+    """the bench workload's seeded table, identical to the CUDA generator's (zk_table_generate)"""
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().zko_table_generate(fid, C.c_uint64(seed), C.c_uint64(table_id), C.c_uint64(n), C.c_uint64(first), C.c_uint64(step), _p(out))
+    return out

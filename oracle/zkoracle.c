@@ -895,3 +895,312 @@ int zko_gkr_verify(int fid, const zko_circuit *c, const zko_gkr_proof *pf, const
     zko_transcript_free(t);
     return ok;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * GKR over layers of EXPLICIT width, wiring predicates evaluated from the gate list
+ * (gkr/src/gkr_protocol.rs:26-143 prove, :146-236 verify; gkr/src/utils.rs:8-135).
+ *
+ * The reference stores add_i / mul_i as dense 2^(3i+2) tables (arithmetic_circuit.rs:126-163) and W(b)+W(c),
+ * W(b)W(c) as 4^(i+1) tensors (utils.rs:8-21), which caps it at widths of ~2^7.  The functions of the protocol are
+ * the same whatever their storage: with f(b,c) = add(b,c)(W(b)+W(c)) + mul(b,c)W(b)W(c) the round polynomial of
+ * round k is  s_k(X) = sum over boolean x of f(r_0..r_{k-1}, X, x)  (sumcheck_gkr_protocol.rs:113-143), and since
+ * add/mul are sums of indicators -- one per gate -- every term of that sum belongs to exactly one gate:
+ *
+ *   s_k(X) = sum_g w(out_g) . eq(prefix of (l_g, r_g), r_0..r_{k-1}) . eq1(bit k of (l_g, r_g), X)
+ *                  . op_g( W~(b-part at (r.., X, rest of l_g)), W~(c-part ...) )
+ *
+ * where w(a) binds the `a` variables: eq(r_a, a) at the output layer (gkr_protocol.rs:60-72), and
+ * alpha eq(r_b, a) + beta eq(r_c, a) below (utils.rs:23-68).  That is O(gates) per round with no dense table, and it
+ * is a DIFFERENT algorithm from the product's two-phase bucketed tables (csrc/gkr_wide.cu): per-gate running prefix
+ * weights here, per-wire h tables there.  Pinned to zko_gkr_prove (the dense restatement) on reference-shaped
+ * circuits by tests/test_oracle.py; generalisation of the reference's single output challenge r_a to layer_bits[0]
+ * successive challenges as in the product.  Gate lists must be duplicate-free (the dense indicator stores `= one`).
+ * ------------------------------------------------------------------------------------------ */
+static void eq_at_index(int fid, fe *out, const uint64_t *rs, uint32_t k, uint64_t idx) {
+    /* eq(r, idx) = prod_v (bit_v ? r_v : 1 - r_v), variable 0 = most significant bit of idx */
+    fe acc = f_one(fid), one = f_one(fid);
+    for (uint32_t v = 0; v < k; ++v) {
+        fe r, t;
+        memcpy(r.l, rs + 4 * v, 32);
+        if ((idx >> (k - 1 - v)) & 1) t = r;
+        else f_sub(fid, &t, &one, &r);
+        f_mul(fid, &acc, &acc, &t);
+    }
+    *out = acc;
+}
+/* value at X of the line through (0 -> a0) and (1 -> a1), X a small integer given as a field element */
+static inline void line_at(int fid, fe *out, const fe *a0, const fe *a1, const fe *x) {
+    fe d, t;
+    f_sub(fid, &d, a1, a0);
+    f_mul(fid, &t, x, &d);
+    f_add(fid, out, a0, &t);
+}
+/* eq1(bit, X) = bit ? X : 1 - X */
+static inline void eq1_at(int fid, fe *out, int bit, const fe *x) {
+    if (bit) { *out = *x; return; }
+    fe one = f_one(fid);
+    f_sub(fid, out, &one, x);
+}
+static int sparse_layer_values(int fid, uint32_t L, const uint32_t *bits, const uint64_t *layer_off, const uint32_t *left,
+                               const uint32_t *right, const uint32_t *out, const uint8_t *op, const uint64_t *inputs,
+                               uint64_t n_inputs, fe **W) {
+    /* Circuit::evaluate, arithmetic_circuit.rs:65-109: input side first, gate results accumulate (`+=`, :96) */
+    if (n_inputs != (1ull << bits[L])) return -1;
+    W[L] = (fe *)malloc(n_inputs * sizeof(fe));
+    memcpy(W[L], inputs, n_inputs * 32);
+    for (uint32_t li = L; li-- > 0;) {
+        uint64_t n_out = 1ull << bits[li], n_in = 1ull << bits[li + 1];
+        W[li] = (fe *)calloc(n_out, sizeof(fe));
+        for (uint64_t g = layer_off[li]; g < layer_off[li + 1]; ++g) {
+            if (out[g] >= n_out || left[g] >= n_in || right[g] >= n_in) return -2;
+            fe v;
+            if (op[g] == 0) f_add(fid, &v, &W[li + 1][left[g]], &W[li + 1][right[g]]);
+            else f_mul(fid, &v, &W[li + 1][left[g]], &W[li + 1][right[g]]);
+            f_add(fid, &W[li][out[g]], &W[li][out[g]], &v);
+        }
+    }
+    return 0;
+}
+/* proof layout as zko_gkr_proof: output = 2^layer_bits[0] elements, rounds of layer li = 2 layer_bits[li+1].
+ * layer_bits[0] == 0 (a single output) is the reference's padded case: [out, 0], one challenge (gkr_protocol.rs:43-47). */
+int zko_gkr_prove_sparse(int fid, uint32_t L, const uint32_t *layer_bits, const uint64_t *layer_off, const uint32_t *left,
+                         const uint32_t *right, const uint32_t *out, const uint8_t *op, const uint64_t *inputs,
+                         uint64_t n_inputs, zko_gkr_proof *pf) {
+    if (L == 0) return -1;
+    uint32_t *bits = (uint32_t *)malloc((L + 1) * sizeof(uint32_t));
+    memcpy(bits, layer_bits, (L + 1) * sizeof(uint32_t));
+    const int padded = bits[0] == 0;
+    if (padded) bits[0] = 1;                                        /* [out, 0]: index 1 holds the zero no gate drives */
+    for (uint32_t li = 1; li <= L; ++li) if (bits[li] == 0) { free(bits); return -1; }
+    fe **W = (fe **)calloc(L + 1, sizeof(fe *));
+    int rc = sparse_layer_values(fid, L, bits, layer_off, left, right, out, op, inputs, n_inputs, W);
+    if (rc) return rc;
+    const fe one = f_one(fid);
+    fe xs[3];
+    for (int i = 0; i < 3; ++i) xs[i] = f_from_u64(fid, (uint64_t)i);
+    zko_transcript *t = zko_transcript_new();
+    /* output layer -- gkr_protocol.rs:39-51 */
+    const uint64_t n0 = 1ull << bits[0];
+    memcpy(pf->output, W[0], (padded ? 1 : n0) * 32);
+    pf->n_output = padded ? 1 : n0;
+    {
+        uint8_t *bytes = (uint8_t *)malloc(n0 * 32);
+        zko_mle_to_bytes(fid, (const uint64_t *)W[0], n0, bytes);
+        zko_transcript_append(t, bytes, n0 * 32);                                          /* :49 */
+        free(bytes);
+    }
+    uint64_t *ra = (uint64_t *)malloc(bits[0] * 32);
+    for (uint32_t v = 0; v < bits[0]; ++v) zko_transcript_challenge(t, fid, ra + 4 * v);   /* :50 */
+    fe claimed;
+    if (zko_mle_evaluate(fid, (const uint64_t *)W[0], n0, ra, bits[0], claimed.l)) return -1;   /* :51 */
+    fe alpha = f_zero(), beta = f_zero();
+    const uint64_t *rb = NULL, *rcv = NULL;
+    uint64_t round_off = 0;
+    for (uint32_t li = 0; li < L; ++li) {                                                  /* :57 */
+        const uint32_t m = bits[li + 1], ka = bits[li];
+        const uint64_t g0 = layer_off[li], ng = layer_off[li + 1] - g0, nm = 1ull << m;
+        /* per-gate weight w(out_g): the `a` variables bound -- :60-82, utils.rs:23-68 */
+        fe *pw = (fe *)malloc((ng ? ng : 1) * sizeof(fe));
+        for (uint64_t g = 0; g < ng; ++g) {
+            if (li == 0) eq_at_index(fid, &pw[g], ra, ka, out[g0 + g]);
+            else {
+                fe eb, ec, x, y;
+                eq_at_index(fid, &eb, rb, ka, out[g0 + g]);
+                eq_at_index(fid, &ec, rcv, ka, out[g0 + g]);
+                f_mul(fid, &x, &alpha, &eb);
+                f_mul(fid, &y, &beta, &ec);
+                f_add(fid, &pw[g], &x, &y);
+            }
+        }
+        memcpy(pf->layer_claims + 4 * li, claimed.l, 32);
+        uint64_t *chal = pf->challenges + 4 * round_off;
+        uint64_t *coeffs = pf->coeffs + 12 * round_off;
+        /* sumcheck over (b, c): prove -- sumcheck_gkr_protocol.rs:24-67 */
+        uint8_t by[96];
+        zko_fe_to_bytes_be(fid, claimed.l, by);
+        zko_transcript_append(t, by, 32);                                                  /* :35 */
+        fe *Wb = (fe *)malloc(nm * sizeof(fe));     /* W over the not-yet-bound b variables */
+        fe *Wc = (fe *)malloc(nm * sizeof(fe));     /* W over the not-yet-bound c variables */
+        memcpy(Wb, W[li + 1], nm * sizeof(fe));
+        memcpy(Wc, W[li + 1], nm * sizeof(fe));
+        const fe *Wfull = W[li + 1];
+        fe Wu = f_zero();
+        for (uint32_t k = 0; k < 2 * m; ++k) {                                             /* :37 */
+            const int phase_c = k >= m;
+            const uint32_t kk = phase_c ? k - m : k;           /* variable inside its half */
+            const uint32_t rest = m - kk - 1;                  /* unbound variables after it */
+            const fe *tab = phase_c ? Wc : Wb;
+            fe ev[3] = {f_zero(), f_zero(), f_zero()};
+            for (uint64_t g = 0; g < ng; ++g) {
+                const uint32_t idx = phase_c ? right[g0 + g] : left[g0 + g];
+                const int bit = (idx >> rest) & 1;
+                const uint64_t low = idx & ((1ull << rest) - 1);
+                for (int X = 0; X < 3; ++X) {                                              /* :127-137, X = 0..d */
+                    fe e1, wv, other, val, term;
+                    eq1_at(fid, &e1, bit, &xs[X]);
+                    line_at(fid, &wv, &tab[low], &tab[(1ull << rest) + low], &xs[X]);
+                    other = phase_c ? Wu : Wfull[right[g0 + g]];   /* the factor the sum over boolean c pins to W(r_g) */
+                    if (op[g0 + g] == 0) f_add(fid, &val, &wv, &other);
+                    else f_mul(fid, &val, &wv, &other);
+                    f_mul(fid, &term, &pw[g], &e1);
+                    f_mul(fid, &term, &term, &val);
+                    f_add(fid, &ev[X], &ev[X], &term);
+                }
+            }
+            uint64_t *c = coeffs + 12ull * k;
+            zko_lagrange_interpolate(fid, (const uint64_t *)xs, (const uint64_t *)ev, 3, c);   /* :46-50 */
+            for (int i = 0; i < 3; ++i) zko_fe_to_bytes_le(fid, c + 4 * i, by + 32 * i);   /* :145-150 */
+            zko_transcript_append(t, by, 96);                                              /* :52 */
+            fe r;
+            zko_transcript_challenge(t, fid, r.l);                                         /* :55 */
+            memcpy(chal + 4 * k, r.l, 32);                                                 /* :59 */
+            /* bind the variable -- :57: prefix weights, then the W table of this half */
+            for (uint64_t g = 0; g < ng; ++g) {
+                const uint32_t idx = phase_c ? right[g0 + g] : left[g0 + g];
+                fe e1;
+                eq1_at(fid, &e1, (idx >> rest) & 1, &r);
+                f_mul(fid, &pw[g], &pw[g], &e1);
+            }
+            fe *tw = phase_c ? Wc : Wb;
+            for (uint64_t j = 0; j < (1ull << rest); ++j) line_at(fid, &tw[j], &tw[j], &tw[(1ull << rest) + j], &r);
+            if (!phase_c && rest == 0) Wu = Wb[0];                                         /* W(r_b) */
+        }
+        const fe Wv = Wc[0];                                                               /* W(r_c) */
+        (void)one;
+        free(Wb); free(Wc); free(pw);
+        if (li + 1 < L) {                                                                  /* :109-132 */
+            memcpy(pf->wb + 4 * li, Wu.l, 32);                                             /* utils.rs:70-82 */
+            memcpy(pf->wc + 4 * li, Wv.l, 32);
+            rb = chal; rcv = chal + 4 * m;                                                 /* :120-123 */
+            zko_fe_to_bytes_be(fid, Wu.l, by);
+            zko_transcript_append(t, by, 32);
+            zko_transcript_challenge(t, fid, alpha.l);                                     /* :125-126 */
+            zko_fe_to_bytes_be(fid, Wv.l, by);
+            zko_transcript_append(t, by, 32);
+            zko_transcript_challenge(t, fid, beta.l);                                      /* :128-129 */
+            fe x, y;
+            f_mul(fid, &x, &alpha, &Wu);
+            f_mul(fid, &y, &beta, &Wv);
+            f_add(fid, &claimed, &x, &y);                                                  /* :132 */
+        }
+        round_off += 2ull * m;
+    }
+    memcpy(pf->claimed_sum, claimed.l, 32);
+    zko_transcript_free(t);
+    for (uint32_t li = 0; li <= L; ++li) free(W[li]);
+    free(W); free(ra); free(bits);
+    return 0;
+}
+/* verify -- gkr_protocol.rs:146-236 with the claim helpers of utils.rs:84-135 evaluated from the gate list:
+ * add_i(r_a.., r_b, r_c) = sum over add gates of w(out_g) eq(r_b, l_g) eq(r_c, r_g).  Returns 1 iff accepted. */
+int zko_gkr_verify_sparse(int fid, uint32_t L, const uint32_t *layer_bits, const uint64_t *layer_off, const uint32_t *left,
+                          const uint32_t *right, const uint32_t *out, const uint8_t *op, const zko_gkr_proof *pf,
+                          const uint64_t *inputs, uint64_t n_inputs) {
+    if (L == 0) return 0;
+    uint32_t *bits = (uint32_t *)malloc((L + 1) * sizeof(uint32_t));
+    memcpy(bits, layer_bits, (L + 1) * sizeof(uint32_t));
+    const int padded = bits[0] == 0;
+    if (padded) bits[0] = 1;
+    zko_transcript *t = zko_transcript_new();
+    const uint64_t n0 = 1ull << bits[0];
+    if (pf->n_output != (padded ? 1 : n0)) { free(bits); zko_transcript_free(t); return 0; }
+    uint64_t *w0 = (uint64_t *)calloc(n0, 32);
+    memcpy(w0, pf->output, pf->n_output * 32);                                             /* :153-159 */
+    uint8_t *bytes = (uint8_t *)malloc(n0 * 32);
+    zko_mle_to_bytes(fid, w0, n0, bytes);
+    zko_transcript_append(t, bytes, n0 * 32);                                              /* :161 */
+    free(bytes);
+    uint64_t *ra = (uint64_t *)malloc(bits[0] * 32);
+    for (uint32_t v = 0; v < bits[0]; ++v) zko_transcript_challenge(t, fid, ra + 4 * v);
+    fe claimed, alpha = f_zero(), beta = f_zero();
+    zko_mle_evaluate(fid, w0, n0, ra, bits[0], claimed.l);                                 /* :164 */
+    free(w0);
+    uint64_t round_off = 0;
+    uint64_t *prev = NULL;
+    int ok = 1;
+    for (uint32_t li = 0; li < L && ok; ++li) {
+        const uint32_t m = bits[li + 1], ka = bits[li], rounds = 2 * m;
+        const uint64_t g0 = layer_off[li], ng = layer_off[li + 1] - g0;
+        if (memcmp(claimed.l, pf->layer_claims + 4 * li, 32)) { ok = 0; break; }           /* :167-169 */
+        uint64_t *chal = (uint64_t *)malloc(rounds * 32);
+        fe last;
+        if (!zko_product_verify(fid, pf->layer_claims + 4 * li, pf->coeffs + 12 * round_off, rounds, 2, t, chal, last.l)) {
+            free(chal); ok = 0; break;                                                     /* :172-176 */
+        }
+        fe wbv, wcv;
+        if (li + 1 < L) {                                                                  /* :183-187 */
+            memcpy(wbv.l, pf->wb + 4 * li, 32);
+            memcpy(wcv.l, pf->wc + 4 * li, 32);
+        } else {                                                                           /* :188-194 */
+            if (n_inputs != (1ull << m)) { free(chal); ok = 0; break; }
+            zko_mle_evaluate(fid, inputs, n_inputs, chal, m, wbv.l);
+            zko_mle_evaluate(fid, inputs, n_inputs, chal + 4 * m, m, wcv.l);
+        }
+        fe addr = f_zero(), mulr = f_zero();
+        for (uint64_t g = 0; g < ng; ++g) {                                                /* utils.rs:84-135 */
+            fe w, eb, ec, term;
+            if (li == 0) eq_at_index(fid, &w, ra, ka, out[g0 + g]);
+            else {
+                fe x, y, e1, e2;
+                eq_at_index(fid, &e1, prev, ka, out[g0 + g]);
+                eq_at_index(fid, &e2, prev + 4 * ka, ka, out[g0 + g]);
+                f_mul(fid, &x, &alpha, &e1);
+                f_mul(fid, &y, &beta, &e2);
+                f_add(fid, &w, &x, &y);
+            }
+            eq_at_index(fid, &eb, chal, m, left[g0 + g]);
+            eq_at_index(fid, &ec, chal + 4 * m, m, right[g0 + g]);
+            f_mul(fid, &term, &eb, &ec);
+            f_mul(fid, &term, &term, &w);
+            if (op[g0 + g] == 0) f_add(fid, &addr, &addr, &term);
+            else f_add(fid, &mulr, &mulr, &term);
+        }
+        fe s, pr, x, y, expect;
+        f_add(fid, &s, &wbv, &wcv);
+        f_mul(fid, &pr, &wbv, &wcv);
+        f_mul(fid, &x, &addr, &s);
+        f_mul(fid, &y, &mulr, &pr);
+        f_add(fid, &expect, &x, &y);                                                       /* utils.rs:110,134 */
+        if (!f_eq(&expect, &last)) { free(chal); ok = 0; break; }                          /* :220-222 */
+        free(prev);
+        prev = chal;                                                                       /* :224 */
+        uint8_t b[32];
+        zko_fe_to_bytes_be(fid, wbv.l, b);
+        zko_transcript_append(t, b, 32);
+        zko_transcript_challenge(t, fid, alpha.l);                                         /* :226-227 */
+        zko_fe_to_bytes_be(fid, wcv.l, b);
+        zko_transcript_append(t, b, 32);
+        zko_transcript_challenge(t, fid, beta.l);                                          /* :229-230 */
+        f_mul(fid, &x, &alpha, &wbv);
+        f_mul(fid, &y, &beta, &wcv);
+        f_add(fid, &claimed, &x, &y);                                                      /* :232 */
+        round_off += rounds;
+    }
+    free(prev); free(ra); free(bits);
+    zko_transcript_free(t);
+    return ok;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic tables -- the bench workload's inputs, regenerated on the host exactly as the
+ * CUDA generator makes them: entry i of table `table_id` under `seed` = from_le_bytes_mod_order of the 32 bytes
+ * le64(w0) | le64(w1) | le64(w2) | le64(w3), w_l = splitmix64 stream of (seed ^ table_id * GOLDEN) at counter 4 i + l.
+ * Local entry j is global entry first + j * step (a shard).  Not part of the reference: it turns bytes into elements
+ * the way the reference does (fiat_shamir_transcript.rs:42 `from_le_bytes_mod_order`).
+ * ------------------------------------------------------------------------------------------ */
+static inline uint64_t splitmix64_at(uint64_t base, uint64_t ctr) {
+    uint64_t z = base + (ctr + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void zko_table_generate(int fid, uint64_t seed, uint64_t table_id, uint64_t n, uint64_t first, uint64_t step, uint64_t *out) {
+    const uint64_t base = seed ^ (table_id * 0x9E3779B97F4A7C15ull);
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && n >= 4096)
+    for (uint64_t j = 0; j < n; ++j) {
+        const uint64_t g = first + j * step;
+        uint64_t w[4];
+        for (int l = 0; l < 4; ++l) w[l] = splitmix64_at(base, 4 * g + (uint64_t)l);
+        zko_fe_from_le_bytes_mod_order(fid, (const uint8_t *)w, 32, out + 4 * j);   /* little-endian host */
+    }
+}

@@ -132,6 +132,22 @@ uint64_t zko_gkr_total_rounds(uint32_t n_layers);
 int  zko_gkr_prove(int fid, const zko_circuit *c, const uint64_t *inputs, uint64_t n_inputs, zko_gkr_proof *proof);
 int  zko_gkr_verify(int fid, const zko_circuit *c, const zko_gkr_proof *proof, const uint64_t *inputs, uint64_t n_inputs);
 
+/* ---- GKR over layers of explicit width, add_i / mul_i evaluated from the gate list (O(gates) per round, no dense
+ * 2^(3i+2) tables): gkr_protocol.rs:26-143 / :146-236 for circuits the reference's dense storage cannot hold.
+ * layer_bits[li] = log2(#values of layer li), li = 0..n_layers; rounds of layer li = 2 * layer_bits[li + 1];
+ * the output claim binds layer_bits[0] successive challenges (one in the reference's shape; layer_bits[0] == 0 is the
+ * reference's padded single output).  Identical to zko_gkr_prove on reference-shaped circuits (tests/test_oracle.py).
+ * proof->output must hold 2^layer_bits[0] elements.  Gate lists duplicate-free. */
+int  zko_gkr_prove_sparse(int fid, uint32_t n_layers, const uint32_t *layer_bits, const uint64_t *layer_off,
+                          const uint32_t *left, const uint32_t *right, const uint32_t *out, const uint8_t *op,
+                          const uint64_t *inputs, uint64_t n_inputs, zko_gkr_proof *proof);
+int  zko_gkr_verify_sparse(int fid, uint32_t n_layers, const uint32_t *layer_bits, const uint64_t *layer_off,
+                           const uint32_t *left, const uint32_t *right, const uint32_t *out, const uint8_t *op,
+                           const zko_gkr_proof *proof, const uint64_t *inputs, uint64_t n_inputs);
+
+/* ---- the bench workload's seeded tables, as the CUDA generator makes them ---- */
+void zko_table_generate(int fid, uint64_t seed, uint64_t table_id, uint64_t n, uint64_t first, uint64_t step, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,46 +50,6 @@ template <int FID> static int run() {
             P::redc_wide(R, acc);
             if (!eq(R, s)) { ++bad; printf("redc_wide mismatch\n"); }
         }
-        // the same sums through the carry-chain-free column accumulator
-        {
-            typename P::ColAcc ca; P::cols_init(ca);
-            P::mul_acc_cols(ca, A, B); P::mul_acc_cols(ca, to_fe(c), A); P::mul_acc_cols(ca, B, to_fe(c));
-            uint64_t t1[4], t2[4], t3[4], s[4];
-            zko_fe_mul(FID, a, b, t1); zko_fe_mul(FID, c, a, t2); zko_fe_mul(FID, b, c, t3);
-            zko_fe_add(FID, t1, t2, s); zko_fe_add(FID, s, t3, s);
-            if (it % 50 == 0) {
-                for (int k = 0; k < 3000; ++k) { P::mul_acc_cols(ca, A, B); zko_fe_add(FID, s, t1, s); }
-            }
-            uint32_t limbs[17]; P::cols_to_limbs(limbs, ca);
-            P::redc_wide(R, limbs);
-            if (!eq(R, s)) { ++bad; printf("mul_acc_cols mismatch\n"); }
-            // and limb for limb against the chained accumulator
-            uint32_t acc[17] = {0};
-            P::mul_acc(acc, A, B); P::mul_acc(acc, to_fe(c), A); P::mul_acc(acc, B, to_fe(c));
-            if (it % 50 == 0) for (int k = 0; k < 3000; ++k) P::mul_acc(acc, A, B);
-            if (memcmp(acc, limbs, sizeof acc)) { ++bad; printf("column accumulator differs from the chained accumulator\n"); }
-        }
-        // the same sums through flag-free radix-2^29 columns (six multiplications per flush)
-        {
-            typename P::Cols29 cc; P::cols29_init(cc);
-            uint32_t acc29[17] = {0}, accw[17] = {0};
-            int pending = 0;
-            int reps = (it % 50 == 0) ? 500 : 1;
-            for (int rep = 0; rep < reps; ++rep) {
-                const zk::Fe* xs[3] = {&A, &B, &A};
-                zk::Fe Cc = to_fe(c);
-                const zk::Fe* ys[3] = {&B, &Cc, &Cc};
-                for (int q = 0; q < 3; ++q) {
-                    typename P::Digits29 da, db;
-                    P::to_digits29(da, *xs[q]); P::to_digits29(db, *ys[q]);
-                    P::mul_cols29(cc, da, db);
-                    if (++pending == P::kCols29Budget) { P::cols29_flush(acc29, cc); pending = 0; }
-                    P::mul_acc(accw, *xs[q], *ys[q]);
-                }
-            }
-            P::cols29_flush(acc29, cc);
-            if (memcmp(acc29, accw, sizeof accw)) { ++bad; printf("radix-2^29 accumulator differs from the chained accumulator (it=%d)\n", it); }
-        }
         // fold by scalar table: out = lo + r*(hi-lo); r = b, lo = a, hi = c
         {
             zk::FoldTable tab;
@@ -131,8 +91,8 @@ template <int FID> static int run() {
 // RoundAcc (round_acc.cuh): several "threads" accumulate pairs, their 32-bit columns are summed as exact
 // 64-bit integers (what the kernels' REDUX / RED stages do) and finalize() must return the reference's
 // generate_round_univariate evaluations (oracle: zko_generate_round_univariate on the same tables).
-template <int FID, int P, int D, bool SKIP1, int NLIN, bool COLS = false> static int run_round_acc(int n_threads, int pairs_per_thread, int edge) {
-    typedef zk::RoundAcc<FID, P, D, SKIP1, NLIN, COLS> RA;
+template <int FID, int P, int D, bool SKIP1, int NLIN> static int run_round_acc(int n_threads, int pairs_per_thread, int edge) {
+    typedef zk::RoundAcc<FID, P, D, SKIP1, NLIN> RA;
     constexpr int T = P * D + NLIN;
     const uint64_t half = (uint64_t)n_threads * pairs_per_thread, len = 2 * half;   // must be a power of two
     // oracle layout: P' products of D factors; a linear table l enters as the product (l, ones, ones...)
@@ -184,11 +144,6 @@ template <int FID> static int run_round_accs() {
         bad += run_round_acc<FID, 1, 2, true, 1>(1, 1, edge);
         bad += run_round_acc<FID, 2, 3, false, 0>(4, 2, edge);
         bad += run_round_acc<FID, 4, 2, true, 0>(2, 2, edge);
-        // column accumulators (the round-0 kernels)
-        bad += run_round_acc<FID, 1, 2, false, 0, true>(16, 8, edge);
-        bad += run_round_acc<FID, 2, 2, false, 0, true>(4, 4, edge);
-        bad += run_round_acc<FID, 1, 2, false, 1, true>(8, 2, edge);
-        bad += run_round_acc<FID, 4, 2, false, 0, true>(2, 2, edge);
     }
     printf("round_acc field %d: %s\n", FID, bad ? "FAIL" : "ok");
     return bad;

@@ -27,3 +27,20 @@ def test_gpu_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 2 * (1 << 20) * 32 and d["e2e"]["value"] > 0 and d["e2e"]["value"] != d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["gpu_launches"] > 0
+    # the proof of the last timed step is checked after the timed region: reference verifier + evaluate kernels
+    assert d["verified"] is True and all(d["verify"].values()), d["verify"]
+    assert len(d["proof_digest"]) == 64
+    assert d["config"]["sample_log2"] == 12 and "extra_workloads" not in d      # --log2 given: no extras
+
+
+def test_gpu_arm_other_workloads_verify_their_proofs():
+    for args in (["--workload", "plain24", "--log2", "18"], ["--workload", "gkr_wide", "--log2", "12", "--cpu-depth", "3"],
+                 ["--workload", "mle", "--log2", "18", "--cpu-log2", "18", "--sweep", "16"]):
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), *args, "--steps", "2", "--warmup", "1"]
+        if "--cpu-log2" not in args:
+            cmd += ["--cpu-log2", "12"]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-2000:]
+        d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+        assert d["verified"] is True, (args, d.get("verify"))
+        assert d["roofline"]["frac"] > 0 and d["clocks"] is not None

@@ -216,39 +216,118 @@ def test_wide_prover_reduction_layer_with_heavy_fan_in(zk, co, ctx_for):
         assert zk.fe_to_ints(fid, proof.circuit_output) == want.circuit_output
 
 
-def test_wide_prover_row_form_eq_tables_match_entry_wise_form(zk, co, ctx_for):
-    """layers wide enough (2^16) for the row-form eq tables (one fold table per row, 84 multiplies per entry) and the
-    multi-block round kernels: the proof must equal the one built with the entry-wise Montgomery products"""
-    import os
-    from zk_cryptography_research_implementations_b200 import gkr
-    fid = 0
-    ctx = ctx_for(fid)
-    rng = np.random.default_rng(99)
-    w = 16
-    bits = [1, w, w]
+def _wide_arrays(rng, w, depth):
+    """bench.py's synthetic wide circuit in miniature: layer 0 reduces 2^w wires to two outputs, the others are full width"""
     n = 1 << w
     g = np.arange(n, dtype=np.int64)
-    layer0 = np.stack([g, rng.integers(0, n, size=n), g & 1, rng.integers(0, 2, size=n)], axis=1)
-    layer1 = np.stack([rng.integers(0, n, size=n), rng.integers(0, n, size=n), g, rng.integers(0, 2, size=n)], axis=1)
-    inputs = ctx.generate(11, 0, n).download()
-    proofs = []
+    layers = [np.stack([g, rng.integers(0, n, size=n), g & 1, rng.integers(0, 2, size=n)], axis=1)]
+    for _ in range(depth - 1):
+        layers.append(np.stack([rng.integers(0, n, size=n), rng.integers(0, n, size=n), g, rng.integers(0, 2, size=n)], axis=1))
+    return [1] + [w] * depth, layers
+
+
+def _assert_equals_sparse_oracle(proof, want):
+    got_coeffs = np.concatenate([np.stack([p.coefficients for p in sp.round_univariate_polynomials]) for sp in proof.sumcheck_proofs])
+    assert np.array_equal(got_coeffs, want.coeffs[: got_coeffs.shape[0]]), "round polynomials differ from the gate-list oracle"
+    assert np.array_equal(np.concatenate([sp.random_challenges for sp in proof.sumcheck_proofs]), want.challenges[: got_coeffs.shape[0]])
+    assert np.array_equal(np.stack([sp.claimed_sum for sp in proof.sumcheck_proofs]), want.layer_claims)
+    L = len(proof.sumcheck_proofs)
+    assert np.array_equal(proof.wb_evaluations, want.wb[: L - 1]) and np.array_equal(proof.wc_evaluations, want.wc[: L - 1])
+    assert np.array_equal(proof.claimed_sum, want.claimed_sum)
+    assert np.array_equal(proof.circuit_output[: want.circuit_output.shape[0]], want.circuit_output)
+
+
+@pytest.mark.parametrize("w,depth,fid", [(12, 4, 0), (12, 3, 2), (16, 3, 0)])
+def test_wide_prover_limb_for_limb_against_the_gate_list_oracle(zk, co, ctx_for, w, depth, fid):
+    """widths the dense oracles cannot reach (2^12, 2^16: multi-block round kernels, the row-form eq tables, the sliced
+    evaluation of the reduction layer, the CSR orderings built on the GPU): every limb of the proof against
+    oracle/zkoracle.c zko_gkr_prove_sparse -- gkr_protocol.rs:57-134 with add_i / mul_i evaluated from the gate list --
+    which is itself pinned to the dense restatement on reference shapes (tests/test_oracle.py).  Both eq-table forms
+    (ZKB200_EQ_ROWS) must give that proof, and both verifiers (the CUDA one and the oracle's) must accept it."""
+    import os
+    from zk_cryptography_research_implementations_b200 import gkr
+    ctx = ctx_for(fid)
+    rng = np.random.default_rng(1000 * w + 10 * depth + fid)
+    bits, layers = _wide_arrays(rng, w, depth)
+    inputs = ctx.generate(11, 0, 1 << w).download()
+    sc = co.SparseCircuit(bits, layers)
+    want = co.gkr_prove_sparse(fid, sc, inputs)
+    assert co.gkr_verify_sparse(fid, sc, want, inputs)
     for knob in ("1", "0"):
         os.environ["ZKB200_EQ_ROWS"] = knob
         try:
-            wc = gkr.WideCircuit(ctx, bits, [layer0, layer1])
-            proofs.append(gkr.prove_wide(ctx, wc, inputs))
+            wc = gkr.WideCircuit(ctx, bits, layers)
+            proof = gkr.prove_wide(ctx, wc, inputs)
+            _assert_equals_sparse_oracle(proof, want)
+            assert gkr.verify_wide(ctx, wc, proof, inputs)
             wc.close()
         finally:
             del os.environ["ZKB200_EQ_ROWS"]
-    a, b = proofs
-    assert np.array_equal(a.claimed_sum, b.claimed_sum) and np.array_equal(a.circuit_output, b.circuit_output)
-    assert np.array_equal(a.wb_evaluations, b.wb_evaluations) and np.array_equal(a.wc_evaluations, b.wc_evaluations)
-    for x, y in zip(a.sumcheck_proofs, b.sumcheck_proofs):
-        assert np.array_equal(x.random_challenges, y.random_challenges)
-        assert all(np.array_equal(p.coefficients, q.coefficients) for p, q in zip(x.round_univariate_polynomials, y.round_univariate_polynomials))
-    # the circuit output against a plain host evaluation with the oracle's field (2^15 gates per output: the sliced
-    # evaluation kernels at scale)
-    assert np.array_equal(_host_layer(co, fid, layer0, 2, _host_layer(co, fid, layer1, n, inputs)), a.circuit_output)
+
+
+def test_wide_verifier_accepts_honest_and_rejects_tampered_proofs(zk, co, ctx_for):
+    """zk_gkr_verify_wide (gkr_protocol.rs:146-236 with utils.rs:84-135 evaluated from the gate list on the GPU): decision
+    parity with the oracle's gate-list verifier on honest and tampered proofs, inputs from the host and from HBM"""
+    import copy
+    from zk_cryptography_research_implementations_b200 import gkr
+    fid = 0
+    ctx = ctx_for(fid)
+    rng = np.random.default_rng(77)
+    bits, layers = _wide_arrays(rng, 10, 3)
+    dev_inputs = ctx.generate(5, 1, 1 << 10)
+    inputs = dev_inputs.download()
+    wc = gkr.WideCircuit(ctx, bits, layers)
+    sc = co.SparseCircuit(bits, layers)
+    proof = gkr.prove_wide(ctx, wc, dev_inputs)
+
+    def both(pf, inp=inputs):
+        got = gkr.verify_wide(ctx, wc, pf, inp)
+        coeffs = np.concatenate([np.stack([p.coefficients for p in sp.round_univariate_polynomials]) for sp in pf.sumcheck_proofs])
+        want = co.gkr_verify_sparse(fid, sc, co.make_gkr_proof(sc, pf.circuit_output, pf.claimed_sum, np.stack([sp.claimed_sum for sp in pf.sumcheck_proofs]),
+                                                                coeffs, pf.wb_evaluations, pf.wc_evaluations), inp)
+        assert got == want
+        return got
+
+    assert both(proof)
+    assert gkr.verify_wide(ctx, wc, proof, dev_inputs)
+    one = zk.fe_from_int(fid, 1)
+    t = copy.deepcopy(proof); t.circuit_output[0] = zk.fe_binop("add", fid, t.circuit_output[0], one); assert not both(t)
+    t = copy.deepcopy(proof); t.wb_evaluations[1] = zk.fe_binop("add", fid, t.wb_evaluations[1], one); assert not both(t)
+    t = copy.deepcopy(proof); c = t.sumcheck_proofs[2].round_univariate_polynomials[7].coefficients; c[1] = zk.fe_binop("add", fid, c[1], one); assert not both(t)
+    t = copy.deepcopy(proof); t.sumcheck_proofs[1].claimed_sum[:] = zk.fe_binop("add", fid, t.sumcheck_proofs[1].claimed_sum, one); assert not both(t)
+    bad_inputs = inputs.copy(); bad_inputs[3] = zk.fe_binop("add", fid, bad_inputs[3], one)
+    assert not both(proof, bad_inputs)
+    wc.close()
+
+
+def test_wide_circuit_single_output_is_the_reference_padding_and_bad_gate_lists_are_refused(zk, co, ctx_for):
+    from zk_cryptography_research_implementations_b200 import gkr
+    import pyoracle as po
+    fid = 0
+    ctx = ctx_for(fid)
+    rng = random.Random(31)
+    depth = 4
+    layers = _random_layers(rng, [0] + list(range(1, depth + 1)))
+    inputs = zk.fe_from_ints(fid, [rng.randrange(po.P["BN254_FQ"]) for _ in range(1 << depth)])
+    # layer_bits[0] == 0: one output, padded to [out, 0] with one challenge exactly like gkr_protocol.rs:43-51
+    wc = gkr.WideCircuit(ctx, [0] + list(range(1, depth + 1)), layers)
+    assert wc.layer_bits[0] == 1
+    proof = gkr.prove_wide(ctx, wc, inputs)
+    want = co.gkr_prove(fid, co.Circuit(layers), inputs)
+    assert np.array_equal(np.concatenate([np.stack([q.coefficients for q in sp.round_univariate_polynomials]) for sp in proof.sumcheck_proofs]), want.coeffs)
+    assert np.array_equal(proof.claimed_sum, want.claimed_sum)
+    assert np.array_equal(proof.circuit_output[0], want.circuit_output[0]) and not proof.circuit_output[1].any()
+    assert gkr.verify_wide(ctx, wc, proof, inputs)
+    # a duplicated gate, an index outside its layer, an operator that is neither add nor mul: refused at construction
+    with pytest.raises(zk.ZkError, match="duplicate gate"):
+        gkr.WideCircuit(ctx, [1, 2], [[(0, 1, 0, 1), (2, 3, 1, 0), (0, 1, 0, 1)]])
+    gkr.WideCircuit(ctx, [1, 2], [[(0, 1, 0, 1), (2, 3, 1, 0), (0, 1, 0, 0)]]).close()      # same wires, other operator: distinct
+    with pytest.raises(zk.ZkError, match="does not fit its layer width"):
+        gkr.WideCircuit(ctx, [1, 2], [[(0, 4, 0, 1)]])
+    with pytest.raises(zk.ZkError, match="does not fit its layer width"):
+        gkr.WideCircuit(ctx, [0, 2], [[(0, 1, 1, 1)]])
+    with pytest.raises(zk.ZkError, match="operator"):
+        gkr.WideCircuit(ctx, [1, 2], [[(0, 1, 0, 2)]])
 
 
 def _host_layer(co, fid, layer, n_out, values):

@@ -11,10 +11,9 @@ import pytest
 from conftest import ROOT
 
 
-@pytest.mark.parametrize("defines", [[], ["-DZK_FOLD_COLS=1"]], ids=["product", "column-form fold (experiment)"])
-def test_fp_cuh_host_emulation(tmp_path, defines):
+def test_fp_cuh_host_emulation(tmp_path):
     exe = str(tmp_path / "emu")
-    cmd = ["g++", "-O1", "-std=c++17", "-DZK_HOST_EMU", *defines, "-x", "c++",
+    cmd = ["g++", "-O1", "-std=c++17", "-DZK_HOST_EMU", "-x", "c++",
            "-I", os.path.join(ROOT, "zk_cryptography_research_implementations_b200", "csrc"),
            os.path.join(ROOT, "tests", "host_emu", "emu_main.cpp"), os.path.join(ROOT, "oracle", "zkoracle.c"),
            "-o", exe]

@@ -241,3 +241,71 @@ def test_all_core_mode_gives_the_same_proofs(co):
     (p1, b1, e1, y1), (p4, b4, e4, y4) = outs
     assert all(np.array_equal(x, y) for x, y in zip(p1, p4)) and all(np.array_equal(x, y) for x, y in zip(b1, b4))
     assert np.array_equal(e1, e4) and y1 == y4
+
+
+@pytest.mark.parametrize("fid", [0, 2])
+def test_gate_list_gkr_oracle_equals_the_dense_restatement_on_reference_shapes(co, fid):
+    """zko_gkr_prove_sparse / zko_gkr_verify_sparse (gkr_protocol.rs:26-236 with add_i / mul_i evaluated from the gate list,
+    O(gates) per round) are the checkers of the wide CUDA prover; here they are pinned to the dense line-by-line restatement
+    zko_gkr_prove / zko_gkr_verify on circuits the reference's storage can hold, and to the Python model beyond."""
+    import random
+    import pyoracle as po
+    name = {0: "BN254_FQ", 2: "BLS12_381_FR"}[fid]
+    p = po.P[name]
+    for depth in (1, 2, 3, 5, 6):
+        rng = random.Random(7 * fid + depth)
+        layers = []
+        for i in range(depth):
+            gates, seen = [], set()
+            for o in range(1 if i == 0 else 1 << i):
+                for _ in range(rng.choice([1, 1, 2, 3])):
+                    g = (rng.randrange(1 << (i + 1)), rng.randrange(1 << (i + 1)), o, rng.randrange(2))
+                    if g not in seen:
+                        seen.add(g)
+                        gates.append(g)
+            layers.append(gates)
+        I = co.from_ints(fid, [rng.randrange(p) for _ in range(1 << depth)])
+        want = co.gkr_prove(fid, co.Circuit(layers), I)
+        sc = co.SparseCircuit([0] + list(range(1, depth + 1)), layers)       # one output: the reference's padded layer 0
+        got = co.gkr_prove_sparse(fid, sc, I)
+        for f in ("coeffs", "challenges", "layer_claims", "wb", "wc", "claimed_sum", "circuit_output"):
+            assert np.array_equal(getattr(got, f), getattr(want, f)), (depth, f)
+        assert co.gkr_verify_sparse(fid, sc, got, I) and co.gkr_verify_sparse(fid, sc, want, I)
+        got.coeffs[0, 0, 0] ^= np.uint64(1)
+        assert not co.gkr_verify_sparse(fid, sc, got, I)
+    if fid == 0:
+        for bits in ([2, 3, 3, 2], [1, 4, 2, 5], [4, 1, 3]):
+            rng = random.Random(sum(b * 7 ** i for i, b in enumerate(bits)))
+            layers = []
+            for li in range(len(bits) - 1):
+                gates, seen = [], set()
+                for o in range(1 << bits[li]):
+                    for _ in range(rng.choice((1, 1, 2))):
+                        g = (rng.randrange(1 << bits[li + 1]), rng.randrange(1 << bits[li + 1]), o, rng.randrange(2))
+                        if g not in seen:
+                            seen.add(g)
+                            gates.append(g)
+                layers.append(gates)
+            inputs = [rng.randrange(p) for _ in range(1 << bits[-1])]
+            want = po.gkr_prove_general([[po.Gate(*g) for g in l] for l in layers], bits, inputs, p)
+            sc = co.SparseCircuit(bits, layers)
+            got = co.gkr_prove_sparse(fid, sc, co.from_ints(fid, inputs))
+            assert co.to_ints(fid, got.coeffs) == [c for (_, polys, _) in want.sumcheck_proofs for poly in polys for c in poly]
+            assert co.to_ints(fid, got.challenges) == [c for (_, _, ch) in want.sumcheck_proofs for c in ch]
+            assert co.to_ints(fid, got.claimed_sum) == [want.claimed_sum]
+            assert co.gkr_verify_sparse(fid, sc, got, co.from_ints(fid, inputs))
+
+
+def test_seeded_table_generator_matches_the_python_restatement(co):
+    """zko_table_generate (the CPU arm's inputs in bench.py) against the pure-Python statement of SURVEY.md 8d that the
+    GPU tests use to check zk_table_generate: all three agree, so both bench arms prove the same tables."""
+    from zk_cryptography_research_implementations_b200.core import synthetic_table_ints
+    for fid in (0, 1, 2):
+        for first, step in ((0, 1), (5, 8)):
+            assert co.to_ints(fid, co.table_generate(fid, 0xB200, 3, 64, first, step)) == synthetic_table_ints(fid, 0xB200, 3, 64, first, step)
+    co.set_threads(4)
+    try:
+        a = co.table_generate(0, 7, 1, 1 << 13)
+    finally:
+        co.set_threads(1)
+    assert np.array_equal(a, co.table_generate(0, 7, 1, 1 << 13))

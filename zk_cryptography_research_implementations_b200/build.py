@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs = list(ex.map(lambda s: _compile(s, force, hdr), srcs))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = ["nvcc", "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
-               "-ldl"]
+               "-ldl", "-lrt"]
         subprocess.check_call(cmd)
         if verbose:
             print("linked", LIB)

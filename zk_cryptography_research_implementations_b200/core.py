@@ -156,12 +156,23 @@ class Context:
 
 
 class DeviceTable:
-    """A table of field elements resident in HBM (zk_table)."""
+    """A table of field elements resident in HBM (zk_table).  `h` raises once the table has been moved into a
+    sumpoly / consumed by a prover / freed, so a stale Python object can never hand a dangling handle to the library."""
 
     def __init__(self, ctx: Context, handle, owned: bool = True):
         self.ctx = ctx
-        self.h = handle
+        self._h = handle
         self.owned = owned
+
+    @property
+    def h(self):
+        if self._h is None:
+            raise ReferencePanic("use of a moved table (consumed by a prover, given to a sumpoly, or freed)")
+        return self._h
+
+    @property
+    def alive(self) -> bool:
+        return self._h is not None
 
     def __len__(self) -> int:
         return int(self.ctx.lib.zk_table_len(self.h))
@@ -184,14 +195,16 @@ class DeviceTable:
         self.ctx.check(self.ctx.lib.zk_table_regenerate(self.ctx.h, self.h, seed, table_id, n, first, step))
 
     def release(self):
-        """give up ownership (the handle now belongs to a sumpoly)"""
+        """give up ownership: returns the raw handle (it now belongs to the caller, e.g. to a sumpoly) and kills this object"""
+        h = self.h
         self.owned = False
-        return self.h
+        self._h = None
+        return h
 
     def free(self) -> None:
-        if self.owned and self.h and self.ctx.h:
-            self.ctx.lib.zk_table_free(self.ctx.h, self.h)
-        self.h = None
+        if self.owned and self._h and self.ctx.h:
+            self.ctx.lib.zk_table_free(self.ctx.h, self._h)
+        self._h = None
 
     def __del__(self):
         try:

@@ -232,6 +232,7 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
     if (ctx->world == 1) return zk_prove_product(ctx, sp, claimed_sum, tr, coeffs_out, challenges_out, final_values, flags);
     if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_ARG, "zk_comm_init has not been called");
     if (!is_pow2(sp->len)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
+    if (flags & ZK_FLAG_NO_CLAIM_ABSORB) return fail(ctx, ZK_ERR_ARG, "ZK_FLAG_NO_CLAIM_ABSORB is not supported by the sharded prover");
     if (collapse_len < 1) collapse_len = 1;
     const HostField& f = ctx->field;
     const int D = sp->D, P = sp->P, NE = D + 1, G = ctx->world;

@@ -371,6 +371,8 @@ extern "C" void zk_table_free(zk_ctx* ctx, zk_table* t) {
 }
 
 // =================================================================================== kernel launchers
+static bool supported_pd(uint32_t P, uint32_t D);
+extern const char* const kUnsupportedPdMsg;
 namespace zk {
 
 int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own) { return wait_seq(ctx, &box->seq, seq, own); }
@@ -437,6 +439,8 @@ bool tail_applies(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags) {
 int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
              uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals) {
     const int NE = D + 1, T = P * D + nlin;
+    if (P < 1 || D < 1 || NE > kMaxEvals || T > kMaxTables || !supported_pd((uint32_t)P, (uint32_t)D) || (nlin != 0 && !(P == 1 && D == 2 && nlin == 1)))
+        return fail(ctx, ZK_ERR_ARG, kUnsupportedPdMsg);
     if (!is_pow2(len) || len < 2 || ilog2(len) > (uint32_t)kTailMaxLog) return fail(ctx, ZK_ERR_ARG, "internal: table too long for the device tail");
     TailArgs a;
     memset(&a, 0, sizeof a);
@@ -446,7 +450,8 @@ int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode,
     a.mode = (uint32_t)mode;
     a.seq = ++ctx->tail_seq;
     if (pending_r) a.ft = make_fold_table(ctx->field, *pending_r);
-    memcpy(a.interp, interp_for(ctx, D).matrix(), (size_t)NE * NE * sizeof(Fe));
+    static_assert(sizeof(a.interp) == sizeof(Fe) * kMaxEvals * kMaxEvals, "TailArgs::interp holds kMaxEvals^2 elements");
+    memcpy(a.interp, interp_for(ctx, D).matrix(), (size_t)NE * NE * sizeof(Fe));   // NE <= kMaxEvals checked above
     memcpy(a.pow32, ctx->pow32, sizeof a.pow32);
     tr.export_state(a.sponge.s, &a.sponge.pos);
     a.out = ctx->tail_dev;
@@ -610,10 +615,24 @@ extern "C" int zk_sum_halves(zk_ctx* ctx, const zk_table* t, uint64_t out[8]) {
 }
 
 // =================================================================================== SumPolynomial
+// the (P, D) shapes the round kernels and the device tail are instantiated for (round_launch.cuh ZK_PD_CASES); anything
+// else is refused at the boundary, before any buffer sized by kMaxEvals / kMaxTables is filled
+static bool supported_pd(uint32_t P, uint32_t D) {
+#define ZK_CASE(PP, DD) if (P == PP && D == DD) return true;
+    ZK_PD_CASES
+#undef ZK_CASE
+    return false;
+}
+static_assert(kMaxEvals >= 4, "ZK_PD_CASES goes up to D = 3");
+const char* const kUnsupportedPdMsg = "unsupported (P, D): supported are (1,1) (1,2) (2,2) (3,2) (4,2) (1,3) (2,3)";
+
 extern "C" int zk_sumpoly_create(zk_ctx* ctx, zk_table* const* tables, uint32_t P, uint32_t D, zk_sumpoly** out) {
-    if (P == 0 || D == 0 || P * D > (uint32_t)kMaxTables) return fail(ctx, ZK_ERR_ARG, "P*D must be in 1..8");
+    if (!supported_pd(P, D)) return fail(ctx, ZK_ERR_ARG, kUnsupportedPdMsg);
     for (uint32_t i = 0; i < P * D; ++i)
         if (tables[i]->len != tables[0]->len) return fail(ctx, ZK_ERR_ASSERT, "different number of variables");
+    for (uint32_t i = 0; i < P * D; ++i)   // folds are in place: one table in two slots would be folded twice per round (and freed twice)
+        for (uint32_t j = 0; j < i; ++j)
+            if (tables[i] == tables[j] || tables[i]->d == tables[j]->d) return fail(ctx, ZK_ERR_ARG, "the tables of a sumpoly must be distinct (clone a repeated factor)");
     zk_sumpoly* sp = new zk_sumpoly();
     sp->P = P;
     sp->D = D;
@@ -836,7 +855,7 @@ extern "C" int zk_prove_basic(zk_ctx* ctx, const uint64_t* host_table, uint64_t 
 extern "C" int zk_prove_product_host(zk_ctx* ctx, const uint64_t* host_tables, uint32_t P, uint32_t D, uint64_t n,
                                      const uint64_t claimed_sum[4], zk_transcript* tr, uint64_t* coeffs, uint64_t* challenges,
                                      uint64_t* final_values, uint32_t flags) {
-    if (P == 0 || D == 0 || P * D > (uint32_t)kMaxTables) return fail(ctx, ZK_ERR_ARG, "P*D must be in 1..8");
+    if (!supported_pd(P, D)) return fail(ctx, ZK_ERR_ARG, kUnsupportedPdMsg);
     if (!is_pow2(n)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
     std::vector<zk_table*> tabs(P * D, nullptr);
     int rc = ZK_OK;
@@ -860,13 +879,10 @@ extern "C" int zk_prove_product_host(zk_ctx* ctx, const uint64_t* host_tables, u
 
 // =================================================================================== arithmetic probe
 // Times `iters` x 4 field operations per thread on a full grid (blocks_per_sm x SMs x 256 threads);
-// returns operations per second.  kind: 0 mont_mul, 1 fold-by-scalar, 2 unreduced multiply-accumulate,
-// 3: double-precision FMA, 4: IMAD.WIDE.U32, 5: IMAD (32-bit), 6: carry-chained IMAD.WIDE.U32.X (8 x iters per thread each),
-// 7: unreduced product through the carry-chain-free column accumulator, 8: through flag-free radix-2^29 columns, operand
-// conversion and flushes included, 9: the chained mul_acc on the same fully varying operand stream as 8 (2 x iters per
-// thread each; iters a multiple of 6 for kinds 8 and 9).
+// returns operations per second.  kind: 0 mont_mul, 1 fold-by-scalar, 2 unreduced multiply-accumulate.
+// (The raw pipe-rate probes of round 1 -- DFMA, IMAD.WIDE forms, column accumulators -- live in experiments/.)
 extern "C" int zk_arith_probe(zk_ctx* ctx, int kind, uint32_t iters, int blocks_per_sm, double* ops_per_s, double* ms_out) {
-    if (kind < 0 || kind > 9 || blocks_per_sm < 1 || blocks_per_sm > 8) return fail(ctx, ZK_ERR_ARG, "bad probe arguments");
+    if (kind < 0 || kind > 2 || blocks_per_sm < 1 || blocks_per_sm > 8) return fail(ctx, ZK_ERR_ARG, "bad probe arguments");
     int grid = ctx->sm_count * blocks_per_sm;
     int rc = ensure_scratch(ctx, (size_t)grid * kThreads * sizeof(Fe));
     if (rc) return rc;
@@ -876,14 +892,7 @@ extern "C" int zk_arith_probe(zk_ctx* ctx, int kind, uint32_t iters, int blocks_
     ZK_CUDA(cudaEventCreate(&e1));
     for (int pass = 0; pass < 2; ++pass) {  // first pass warms up
         ZK_CUDA(cudaEventRecord(e0, ctx->stream));
-        if (kind == 3) { dfma_probe_kernel<0><<<grid, kThreads, 0, ctx->stream>>>((double*)ctx->scratch, iters); }
-        else if (kind == 4) { imad_probe_kernel<4><<<grid, kThreads, 0, ctx->stream>>>((uint64_t*)ctx->scratch, iters); }
-        else if (kind == 5) { imad_probe_kernel<5><<<grid, kThreads, 0, ctx->stream>>>((uint64_t*)ctx->scratch, iters); }
-        else if (kind == 6) { imad_probe_kernel<6><<<grid, kThreads, 0, ctx->stream>>>((uint64_t*)ctx->scratch, iters); }
-        else if (kind == 7) { ZK_DISPATCH_FID(ctx, (cols_probe_kernel<FID><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters))); }
-        else if (kind == 8) { ZK_DISPATCH_FID(ctx, (cols29_probe_kernel<FID, 0><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters))); }
-        else if (kind == 9) { ZK_DISPATCH_FID(ctx, (cols29_probe_kernel<FID, 1><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters))); }
-        else if (kind == 0) { ZK_DISPATCH_FID(ctx, (arith_probe_kernel<FID, 0><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters, ft))); }
+        if (kind == 0) { ZK_DISPATCH_FID(ctx, (arith_probe_kernel<FID, 0><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters, ft))); }
         else if (kind == 1) { ZK_DISPATCH_FID(ctx, (arith_probe_kernel<FID, 1><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters, ft))); }
         else { ZK_DISPATCH_FID(ctx, (arith_probe_kernel<FID, 2><<<grid, kThreads, 0, ctx->stream>>>((Fe*)ctx->scratch, iters, ft))); }
         rc = post_launch(ctx);
@@ -896,6 +905,6 @@ extern "C" int zk_arith_probe(zk_ctx* ctx, int kind, uint32_t iters, int blocks_
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_out) *ms_out = ms;
-    if (ops_per_s) *ops_per_s = (double)grid * kThreads * (kind >= 7 ? 2.0 : kind >= 3 ? 8.0 : 4.0) * iters / (ms * 1e-3);
+    if (ops_per_s) *ops_per_s = (double)grid * kThreads * 4.0 * iters / (ms * 1e-3);
     return ZK_OK;
 }

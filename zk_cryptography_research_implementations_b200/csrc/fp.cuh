@@ -234,104 +234,6 @@ template <int FID> struct Fp {
         acc[16] = ptx::addc(acc[16], 0u);
     }
 
-    // ---------------------------------------------------------------- unreduced products without carry chains
-    // Column accumulator: slot k collects every limb product a_i b_j with i + j == k as a 96-bit integer
-    // (lo, hi, top) at weight 2^(32 k).  A product costs one carry-OUT-only IMAD.WIDE.U32 plus half an IADD3.X (ptxas
-    // feeds two carry predicates into one IADD3.X), and the 64 products of a multiplication are independent of each
-    // other -- no IMAD.WIDE.U32.X.  Up to 2^29 products per slot fit (8 x 2^29 x 2^64 < 2^96).  Measured on B200
-    // (zk_arith_probe kind 7): 122 G products/s against 102 G/s for the chained mul_acc -- the carry-OUT form is not
-    // the full-rate instruction either -- and 45 registers per accumulator instead of 17; the round kernels that
-    // tried it (ZK_ROUND0_COLS) lost more to the halved occupancy than they gained.  Kept as a tested experiment.
-    struct ColAcc {
-        uint32_t lo[15], hi[15], top[15];
-    };
-    ZK_DEV static void cols_init(ColAcc& c) {
-#pragma unroll
-        for (int k = 0; k < 15; ++k) c.lo[k] = c.hi[k] = c.top[k] = 0;
-    }
-    ZK_DEV static void mul_acc_cols(ColAcc& c, const Fe& a, const Fe& b) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ptx::mad_wide_top(c.lo[i + j], c.hi[i + j], c.top[i + j], a.v[i], b.v[j]);
-    }
-    // the slots as one 17-limb integer (the sum of < 2^32 products of canonical elements fits: < 2^542)
-    ZK_DEV static void cols_to_limbs(uint32_t t[17], const ColAcc& c) {
-        // limb p collects lo[p] + hi[p-1] + top[p-2]: three carry chains added one after the other
-        t[0] = c.lo[0];
-#pragma unroll
-        for (int p = 1; p < 15; ++p) t[p] = c.lo[p];
-        t[15] = t[16] = 0;
-        t[1] = ptx::add_cc(t[1], c.hi[0]);
-#pragma unroll
-        for (int p = 2; p < 16; ++p) t[p] = ptx::addc_cc(t[p], c.hi[p - 1]);
-        t[16] = ptx::addc(t[16], 0u);
-        t[2] = ptx::add_cc(t[2], c.top[0]);
-#pragma unroll
-        for (int p = 3; p < 16; ++p) t[p] = ptx::addc_cc(t[p], c.top[p - 2]);
-        t[16] = ptx::addc(t[16], c.top[14]);
-    }
-
-    // ---------------------------------------------------------------- flag-free products in radix 2^29 (EXPERIMENT)
-    // Nine 29-bit digits per operand: a digit product is < 2^58 and a column collects at most 9 of them per
-    // multiplication, so SIX multiplications accumulate in 64-bit columns with the flag-free IMAD.WIDE.U32 -- the one
-    // form of the instruction that issues at full rate -- before the columns are carried out into the 32-bit-limb
-    // accumulator.  81 multiplies instead of 64, none of them carry-chained.
-    struct Digits29 {
-        uint32_t v[9];
-    };
-    struct Cols29 {
-        uint64_t c[17];   // sum_k c[k] 2^(29 k)
-    };
-    static constexpr int kCols29Budget = 6;   // multiplications per flush: 6 x 9 x 2^58 < 2^64
-    ZK_DEV static void to_digits29(Digits29& o, const Fe& a) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int bit = 29 * k, w = bit >> 5, sh = bit & 31;
-            const uint32_t lo = a.v[w], hi = (w + 1 < 8) ? a.v[w + 1] : 0u;
-            o.v[k] = ptx::funnel_r(lo, hi, sh) & 0x1fffffffu;
-        }
-    }
-    ZK_DEV static void cols29_init(Cols29& c) {
-#pragma unroll
-        for (int k = 0; k < 17; ++k) c.c[k] = 0;
-    }
-    ZK_DEV static void mul_cols29(Cols29& c, const Digits29& a, const Digits29& b) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i)
-#pragma unroll
-            for (int j = 0; j < 9; ++j) ptx::mad_wide_noflags(c.c[i + j], a.v[i], b.v[j]);
-    }
-    // acc (17 x 32-bit limbs) += sum_k c[k] 2^(29 k); c = 0
-    ZK_DEV static void cols29_flush(uint32_t acc[17], Cols29& c) {
-        // radix-2^29 carry propagation: 18 exact digits + what is left above
-        uint32_t dg[19];
-        uint64_t carry = 0;
-#pragma unroll
-        for (int k = 0; k < 17; ++k) {
-            const uint64_t t = c.c[k] + carry;
-            dg[k] = (uint32_t)t & 0x1fffffffu;
-            carry = t >> 29;
-            c.c[k] = 0;
-        }
-        dg[17] = (uint32_t)carry & 0x1fffffffu;
-        dg[18] = (uint32_t)(carry >> 29);
-        // repack into 32-bit limbs: limb p = bits [32 p, 32 p + 32) of sum_k dg[k] 2^(29 k)
-        uint32_t t[17];
-#pragma unroll
-        for (int p = 0; p < 17; ++p) {
-            const int bit = 32 * p, k = bit / 29, off = bit - 29 * k;   // limb p starts `off` bits into digit k
-            uint32_t v = dg[k] >> off;
-            if (k + 1 < 19) v |= dg[k + 1] << (29 - off);
-            if (29 - off + 29 < 32 && k + 2 < 19) v |= dg[k + 2] << (58 - off);
-            t[p] = v;
-        }
-        acc[0] = ptx::add_cc(acc[0], t[0]);
-#pragma unroll
-        for (int p = 1; p < 16; ++p) acc[p] = ptx::addc_cc(acc[p], t[p]);
-        acc[16] = ptx::addc(acc[16], t[16]);
-    }
-
     // ---------------------------------------------------------------- Barrett step
     // s[0..9] < 2^291  ->  r = s mod p (canonical).
     //   x = s >> 232 (< 2^59);  q = (x * floor(2^296/p)) >> 64  in {floor(s/p)-1, floor(s/p)};
@@ -442,43 +344,6 @@ template <int FID> struct FoldScalar {
         const uint32_t* v;
         ZK_DEV uint32_t operator()(int i) const { return v[i]; }
     };
-#ifndef ZK_FOLD_COLS
-#define ZK_FOLD_COLS 0   // 0: the chained even/odd rows (product); 1: the carry-chain-free column form (measured slower)
-#endif
-#if ZK_FOLD_COLS
-    // Column form (EXPERIMENT, off by default): limb j of every table row lands in slot j, so the 64 limb products fall
-    // into 8 independent 96-bit slots -- 64 carry-OUT-only IMAD.WIDE.U32 and ~33 IADD3.X that collect two carries each,
-    // instead of 19 + 45 carry-chained IMAD.WIDE.U32.X.  Same integer S, same Barrett step, bit-identical results;
-    // on B200 the carry-out form issues no faster than the carry-in form (fold probe 86 vs 91 G/s).
-    ZK_DEV static void fold(Fe& out, const Fe& lo, const Fe& hi, const FoldTable& tab) {
-        Fe d;
-        P::sub_lazy(d, hi, lo);  // hi - lo + p in (0, 2p)
-        uint32_t cl[8], ch[8], ct[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            cl[j] = lo.v[j];
-            ch[j] = ct[j] = 0;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ptx::mad_wide_top(cl[j], ch[j], ct[j], d.v[i], tab.w[i][j]);
-        // S = sum_j (cl[j] + ch[j] 2^32 + ct[j] 2^64) 2^(32 j) < p (1 + 2^35) < 2^291
-        uint32_t s[10];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] = cl[k];
-        s[8] = s[9] = 0;
-        s[1] = ptx::add_cc(s[1], ch[0]);
-#pragma unroll
-        for (int k = 2; k < 9; ++k) s[k] = ptx::addc_cc(s[k], ch[k - 1]);
-        s[9] = ptx::addc(s[9], 0u);
-        s[2] = ptx::add_cc(s[2], ct[0]);
-#pragma unroll
-        for (int k = 3; k < 9; ++k) s[k] = ptx::addc_cc(s[k], ct[k - 2]);
-        s[9] = ptx::addc(s[9], ct[7]);
-        P::barrett(out.v, s);
-    }
-#else
     ZK_DEV static void fold(Fe& out, const Fe& lo, const Fe& hi, const FoldTable& tab) {
         Fe d;
         P::sub_lazy(d, hi, lo);  // hi - lo + p in (0, 2p)
@@ -510,7 +375,6 @@ template <int FID> struct FoldScalar {
         s[9] = ptx::addc(E[9], O[8]);
         P::barrett(out.v, s);
     }
-#endif
 };
 
 }  // namespace zk

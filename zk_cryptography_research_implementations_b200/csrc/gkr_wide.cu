@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "gkr_wide.h"
 
 using namespace zk;
 
@@ -48,38 +49,6 @@ using namespace zk;
         case 1: { constexpr int FID = 1; EXPR; } break;       \
         default: { constexpr int FID = 2; EXPR; } break;      \
     }
-
-// ---------------------------------------------------------------- device-resident circuit
-struct GateCsr {            // gates of one layer grouped by a key (left / right / out index)
-    uint64_t* off = nullptr;    // [n_keys + 1]
-    uint32_t* x = nullptr;      // first other index per gate (see users)
-    uint32_t* y = nullptr;      // second other index per gate
-    uint8_t* op = nullptr;      // 0 add, 1 mul
-};
-struct WideLayer {
-    uint64_t n_gates = 0;
-    GateCsr by_left;    // x = out,  y = right
-    GateCsr by_right;   // x = out,  y = left
-    GateCsr by_out;     // x = left, y = right
-};
-struct DevBuf {   // RAII device allocation
-    Fe* p = nullptr;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p) { o.p = nullptr; }
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(uint64_t n) { return cudaMalloc(&p, (size_t)(n ? n : 1) * sizeof(Fe)); }
-};
-struct zk_wide_circuit {
-    uint32_t L = 0;
-    std::vector<uint32_t> bits;   // bits[li] = log2(#values of layer li), li = 0..L (L = inputs)
-    std::vector<WideLayer> layers;
-    int device = 0;
-    // prover workspace, allocated with the circuit so a prove never calls cudaMalloc/cudaFree:
-    std::vector<DevBuf> W;        // all layer values (Circuit::evaluate result), resident
-    DevBuf wtab, eqa, h1, h2, Wc, half_hi, half_lo, half_hi2, half_lo2;
-};
 
 namespace {
 inline int grid_of(const zk_ctx* ctx, uint64_t work, int bps) {
@@ -212,37 +181,36 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-// counting sort of one layer's gates by `key`; uploads the CSR
-int build_csr(zk_ctx* ctx, uint64_t n_keys, uint64_t n, const uint32_t* key, const uint32_t* x, const uint32_t* y, const uint8_t* op,
-              GateCsr* out) {
-    std::vector<uint64_t> off(n_keys + 1, 0);
-    for (uint64_t i = 0; i < n; ++i) {
-        if (key[i] >= n_keys) return fail(ctx, ZK_ERR_ARG, "gate index does not fit its layer width");
-        off[key[i] + 1]++;
+// verifier: add_i / mul_i at the sumcheck point with `a` bound (gkr/src/utils.rs:84-135) from the gate list,
+//   add_r = sum over add gates of w(out_g) eq(u, left_g) eq(v, right_g),   mul_r likewise,
+// one thread per b = left index (by_left CSR: x = out, y = right); per-block partial sums, added on the host.
+template <int FID>
+__global__ void __launch_bounds__(kThreads) wiring_eval_kernel(GateCsr g, const Fe* w, const Fe* equ, const Fe* eqv, Fe* partial /* [gridDim.x][2] */, uint64_t nb) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    Fe acc[2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[0].v[k] = acc[1].v[k] = 0;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += stride) {
+        Fe sa, sm;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sa.v[k] = sm.v[k] = 0;
+        for (uint64_t i = g.off[b]; i < g.off[b + 1]; ++i) {
+            Fe wv = ld256(w + g.x[i]), ev = ld256(eqv + g.y[i]), t;
+            Fp<FID>::mont_mul(t, wv, ev);
+            if (g.op[i] == 0) Fp<FID>::add(sa, sa, t);
+            else Fp<FID>::add(sm, sm, t);
+        }
+        Fe eu = ld256(equ + b), t;
+        Fp<FID>::mont_mul(t, sa, eu);
+        Fp<FID>::add(acc[0], acc[0], t);
+        Fp<FID>::mont_mul(t, sm, eu);
+        Fp<FID>::add(acc[1], acc[1], t);
     }
-    for (uint64_t k = 0; k < n_keys; ++k) off[k + 1] += off[k];
-    std::vector<uint64_t> cur(off.begin(), off.end() - 1);
-    std::vector<uint32_t> sx(n), sy(n);
-    std::vector<uint8_t> so(n);
-    for (uint64_t i = 0; i < n; ++i) {
-        uint64_t p = cur[key[i]]++;
-        sx[p] = x[i];
-        sy[p] = y[i];
-        so[p] = op[i];
+    block_sum<FID, 2>(acc);
+    if (threadIdx.x == 0) {
+        st256(partial + 2 * blockIdx.x, acc[0]);
+        st256(partial + 2 * blockIdx.x + 1, acc[1]);
     }
-    ZK_CUDA(cudaMalloc(&out->off, (n_keys + 1) * sizeof(uint64_t)));
-    ZK_CUDA(cudaMalloc(&out->x, (n ? n : 1) * sizeof(uint32_t)));
-    ZK_CUDA(cudaMalloc(&out->y, (n ? n : 1) * sizeof(uint32_t)));
-    ZK_CUDA(cudaMalloc(&out->op, (n ? n : 1)));
-    ZK_CUDA(cudaMemcpy(out->off, off.data(), (n_keys + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    ZK_CUDA(cudaMemcpy(out->x, sx.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    ZK_CUDA(cudaMemcpy(out->y, sy.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    ZK_CUDA(cudaMemcpy(out->op, so.data(), n, cudaMemcpyHostToDevice));
-    return ZK_OK;
-}
-void free_csr(GateCsr* g) {
-    cudaFree(g->off); cudaFree(g->x); cudaFree(g->y); cudaFree(g->op);
-    *g = GateCsr();
 }
 
 // ---- eq tables.  w(a) = s1 eq(r1, a) [+ s2 eq(r2, a)] over k variables is built from half-width tables
@@ -389,69 +357,6 @@ int build_eq2(zk_ctx* ctx, zk_wide_circuit* wc, const std::vector<HFe>& r1, cons
     return ZK_OK;
 }
 }  // namespace
-
-extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint32_t* layer_bits, const uint64_t* layer_off,
-                                      const uint32_t* left, const uint32_t* right, const uint32_t* out, const uint8_t* op,
-                                      zk_wide_circuit** result) {
-    if (n_layers == 0) return fail(ctx, ZK_ERR_ARG, "circuit has no layers");
-    for (uint32_t i = 0; i <= n_layers; ++i)
-        if (layer_bits[i] > 30) return fail(ctx, ZK_ERR_ARG, "layer wider than 2^30");
-    ZK_CUDA(cudaSetDevice(ctx->device));
-    zk_wide_circuit* wc = new zk_wide_circuit();
-    wc->L = n_layers;
-    wc->device = ctx->device;
-    wc->bits.assign(layer_bits, layer_bits + n_layers + 1);
-    wc->layers.resize(n_layers);
-    for (uint32_t li = 0; li < n_layers; ++li) {
-        const uint64_t g0 = layer_off[li], n = layer_off[li + 1] - g0;
-        const uint64_t n_out = 1ull << wc->bits[li], n_in = 1ull << wc->bits[li + 1];
-        WideLayer& wl = wc->layers[li];
-        wl.n_gates = n;
-        int rc = build_csr(ctx, n_in, n, left + g0, out + g0, right + g0, op + g0, &wl.by_left);
-        if (!rc) rc = build_csr(ctx, n_in, n, right + g0, out + g0, left + g0, op + g0, &wl.by_right);
-        if (!rc) rc = build_csr(ctx, n_out, n, out + g0, left + g0, right + g0, op + g0, &wl.by_out);
-        if (!rc) {
-            for (uint64_t i = 0; i < n; ++i)
-                if (out[g0 + i] >= n_out || left[g0 + i] >= n_in || right[g0 + i] >= n_in) { rc = fail(ctx, ZK_ERR_ARG, "gate index does not fit its layer width"); break; }
-        }
-        if (rc) { zk_wide_circuit_free(ctx, wc); return rc; }
-    }
-    {   // workspace
-        uint32_t maxbits = 0;
-        for (uint32_t b : wc->bits) maxbits = std::max(maxbits, b);
-        const uint64_t maxn = 1ull << maxbits;
-        wc->W.resize(n_layers + 1);
-        cudaError_t e = cudaSuccess;
-        for (uint32_t li = 0; li <= n_layers && e == cudaSuccess; ++li) e = wc->W[li].alloc(1ull << wc->bits[li]);
-        DevBuf* bufs[] = {&wc->wtab, &wc->eqa, &wc->h1, &wc->h2, &wc->Wc};
-        for (DevBuf* b : bufs)
-            if (e == cudaSuccess) e = b->alloc(maxn);
-        DevBuf* halves[] = {&wc->half_hi, &wc->half_lo, &wc->half_hi2, &wc->half_lo2};   // half_hi doubles as the slice scratch of evaluate
-        for (DevBuf* b : halves)
-            if (e == cudaSuccess) e = b->alloc(1ull << 16);
-        if (e != cudaSuccess) {
-            ctx->err = std::string("cudaMalloc (GKR workspace): ") + cudaGetErrorString(e);
-            zk_wide_circuit_free(ctx, wc);
-            return ZK_ERR_CUDA;
-        }
-    }
-    *result = wc;
-    return ZK_OK;
-}
-
-extern "C" void zk_wide_circuit_free(zk_ctx* ctx, zk_wide_circuit* wc) {
-    if (!wc) return;
-    cudaSetDevice(wc->device);
-    cudaStreamSynchronize(ctx->stream);
-    for (WideLayer& wl : wc->layers) { free_csr(&wl.by_left); free_csr(&wl.by_right); free_csr(&wl.by_out); }
-    delete wc;
-}
-
-extern "C" uint64_t zk_wide_circuit_total_rounds(const zk_wide_circuit* wc) {
-    uint64_t s = 0;
-    for (uint32_t li = 0; li < wc->L; ++li) s += 2ull * wc->bits[li + 1];
-    return s;
-}
 
 // gkr_protocol::prove (gkr_protocol.rs:26-143), sparse two-phase layers.  Outputs as zk_gkr_prove; `output` may be
 // NULL (wide output layers).  flags: ZK_FLAG_SKIP_ABSORB leaves the output layer out of the transcript (its absorb
@@ -624,4 +529,115 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         fprintf(stderr, "zk_gkr_prove_wide ms: upload+evaluate %.2f | w tables %.2f | phase-1 build %.2f | phase-1 sumcheck %.2f | eq(u)+phase-2 build %.2f | phase-2 sumcheck %.2f\n",
                 t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4], t_acc[5]);
     return ZK_OK;
+}
+
+// gkr_protocol::verify (gkr_protocol.rs:146-236) for circuits of explicit layer widths; the proof laid out as
+// zk_gkr_prove_wide writes it.  The transcript replay and the per-round checks of the layer sumchecks are host work
+// (sumcheck_gkr_protocol.rs:69-106); the claim helpers (utils.rs:84-135) evaluate add_i / mul_i at the sumcheck point from
+// the gate list on the GPU (eq tables of u, v and the bound `a` weights, one pass over the layer's gates), and the input
+// layer's W(u), W(v) (gkr_protocol.rs:188-194, utils.rs:70-82) are the evaluate kernels.  *ok = 1 iff the reference would
+// return true.  `flags` must match the prover's (ZK_FLAG_SKIP_ABSORB).
+static int gkr_verify_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* output, const uint64_t* layer_claims,
+                                const uint64_t* coeffs, const uint64_t* wb, const uint64_t* wcv_in, const uint64_t* inputs,
+                                const zk_table* device_inputs, uint64_t n_inputs, uint32_t flags, int* ok) {
+    zk_wide_circuit* wc = const_cast<zk_wide_circuit*>(wc_);
+    const HostField& f = ctx->field;
+    const uint32_t L = wc->L;
+    *ok = 0;
+    for (uint32_t li = 0; li < L; ++li)
+        if (wc->bits[li + 1] == 0) return fail(ctx, ZK_ERR_ARG, "every layer must read at least two wires");
+    HostTranscript tr;
+    const uint64_t n0 = 1ull << wc->bits[0];
+    std::vector<HFe> w0(reinterpret_cast<const HFe*>(output), reinterpret_cast<const HFe*>(output) + n0);   // :153-159
+    if (!(flags & ZK_FLAG_SKIP_ABSORB))
+        for (const HFe& x : w0) tr.append_be(f, x);                                                          // :161
+    std::vector<HFe> ra(wc->bits[0]);
+    for (HFe& r : ra) r = tr.challenge(f);
+    for (const HFe& r : ra) {                                                                                // :164
+        size_t half = w0.size() / 2;
+        for (size_t j = 0; j < half; ++j) w0[j] = f.add(w0[j], f.mul(r, f.sub(w0[j + half], w0[j])));
+        w0.resize(half);
+    }
+    HFe claimed = w0[0], alpha = f.zero(), beta = f.zero();
+    std::vector<HFe> prev_b, prev_c;
+    uint64_t round_off = 0;
+    const int grid_cap = ctx->sm_count * 4;
+    int rc = ensure_scratch(ctx, (size_t)grid_cap * 2 * sizeof(Fe));
+    if (rc) return rc;
+    std::vector<HFe> partial((size_t)grid_cap * 2);
+    zk_table* in_tab = nullptr;
+    for (uint32_t li = 0; li < L; ++li) {
+        const uint32_t m = wc->bits[li + 1], rounds = 2 * m;
+        const uint64_t nm = 1ull << m;
+        HFe layer_claim;
+        memcpy(layer_claim.l, layer_claims + 4 * li, 32);
+        if (claimed != layer_claim) return ZK_OK;                                                            // :167-169
+        std::vector<HFe> chal(rounds);
+        HFe last;
+        int valid = 0;
+        zk_transcript wrap;
+        wrap.t = tr;
+        rc = zk_verify_product(ctx->fid, layer_claim.l, coeffs + 12 * round_off, rounds, 2, &wrap, chal[0].l, last.l, &valid);
+        tr = wrap.t;
+        if (rc) return rc;
+        if (!valid) return ZK_OK;                                                                            // :172-176
+        std::vector<HFe> u(chal.begin(), chal.begin() + m), v(chal.begin() + m, chal.end());
+        HFe wbv, wcv;
+        if (li + 1 < L) {                                                                                    // :183-187
+            memcpy(wbv.l, wb + 4 * li, 32);
+            memcpy(wcv.l, wcv_in + 4 * li, 32);
+        } else {                                                                                             // :188-194
+            if (n_inputs != nm) return ZK_OK;
+            const zk_table* t = device_inputs;
+            if (!t) {
+                rc = zk_table_upload(ctx, inputs, n_inputs, &in_tab);
+                if (rc) return rc;
+                t = in_tab;
+            }
+            rc = zk_mle_evaluate(ctx, t, u[0].l, m, wbv.l);                                                  // utils.rs:70-82
+            if (!rc) rc = zk_mle_evaluate(ctx, t, v[0].l, m, wcv.l);
+            if (in_tab) { zk_table_free(ctx, in_tab); in_tab = nullptr; }
+            if (rc) return rc;
+        }
+        // bound `a` weights, eq(u, .), eq(v, .) -- utils.rs:84-135 without the dense 2^(3i+2) tables
+        if (li == 0) rc = build_eq2(ctx, wc, ra, f.one(), nullptr, f.one(), wc->wtab.p);
+        else rc = build_eq2(ctx, wc, prev_b, alpha, &prev_c, beta, wc->wtab.p);
+        if (!rc) rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), wc->eqa.p);
+        if (!rc) rc = build_eq2(ctx, wc, v, f.one(), nullptr, f.one(), wc->h1.p);
+        if (rc) return rc;
+        const int grid = grid_of(ctx, nm, 4);
+        ZK_FID_SWITCH(ctx, (wiring_eval_kernel<FID><<<grid, kThreads, 0, ctx->stream>>>(wc->layers[li].by_left, wc->wtab.p, wc->eqa.p, wc->h1.p, (Fe*)ctx->scratch, nm)));
+        ctx->launches++;
+        ZK_CUDA(cudaGetLastError());
+        ZK_CUDA(cudaMemcpyAsync(partial.data(), ctx->scratch, (size_t)grid * 2 * sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        HFe add_r = f.zero(), mul_r = f.zero();
+        for (int b = 0; b < grid; ++b) {
+            add_r = f.add(add_r, partial[2 * b]);
+            mul_r = f.add(mul_r, partial[2 * b + 1]);
+        }
+        const HFe expected = f.add(f.mul(add_r, f.add(wbv, wcv)), f.mul(mul_r, f.mul(wbv, wcv)));           // utils.rs:110,134
+        if (expected != last) return ZK_OK;                                                                  // :220-222
+        prev_b = u;                                                                                          // :224
+        prev_c = v;
+        tr.append_be(f, wbv);
+        alpha = tr.challenge(f);                                                                             // :226-227
+        tr.append_be(f, wcv);
+        beta = tr.challenge(f);                                                                              // :229-230
+        claimed = f.add(f.mul(alpha, wbv), f.mul(beta, wcv));                                                // :232
+        round_off += rounds;
+    }
+    *ok = 1;
+    return ZK_OK;
+}
+
+extern "C" int zk_gkr_verify_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const uint64_t* output, const uint64_t* layer_claims,
+                                  const uint64_t* coeffs, const uint64_t* wb, const uint64_t* wcv, const uint64_t* inputs,
+                                  uint64_t n_inputs, uint32_t flags, int* ok) {
+    return gkr_verify_wide_impl(ctx, wc, output, layer_claims, coeffs, wb, wcv, inputs, nullptr, n_inputs, flags, ok);
+}
+extern "C" int zk_gkr_verify_wide_device(zk_ctx* ctx, const zk_wide_circuit* wc, const uint64_t* output, const uint64_t* layer_claims,
+                                         const uint64_t* coeffs, const uint64_t* wb, const uint64_t* wcv, const zk_table* inputs,
+                                         uint32_t flags, int* ok) {
+    return gkr_verify_wide_impl(ctx, wc, output, layer_claims, coeffs, wb, wcv, nullptr, inputs, inputs->len, flags, ok);
 }

@@ -35,12 +35,6 @@ inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c)    { return addc(mul
 inline void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b)     { lo = mul_lo(a, b); hi = mul_hi(a, b); }
 inline void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b)  { lo = mad_lo_cc(a, b, lo); hi = madc_hi_cc(a, b, hi); }
 inline void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = madc_lo_cc(a, b, lo); hi = madc_hi_cc(a, b, hi); }
-// 96-bit slot: (lo, hi) += a * b, the carry out of the slot lands in `top` -- no carry enters, no chain leaves
-inline void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t& top, uint32_t a, uint32_t b) { mad_wide_cc(lo, hi, a, b); top = addc(top, 0u); }
-// c += a * b as a 64-bit integer, no flags (the caller guarantees no overflow)
-inline void mad_wide_noflags(uint64_t& c, uint32_t a, uint32_t b) { c += (uint64_t)a * b; }
-// bits [s, s + 32) of the 64-bit value hi:lo, s in [0, 31]
-inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return s ? (lo >> s) | (hi << (32 - s)) : lo; }
 }}  // namespace zk::ptx
 #else
 #define ZK_DEV __device__ __forceinline__
@@ -83,19 +77,6 @@ ZK_DEV void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
 }
 ZK_DEV void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
-}
-// 96-bit slot: (lo, hi) += a * b with the carry out of the slot caught in `top`: IMAD.WIDE.U32 with a carry-OUT
-// predicate + an IADD3.X on the alu pipe (measured: the carry-out form issues at about the rate of the carry-in form
-// IMAD.WIDE.U32.X, half the rate of a plain IMAD.WIDE.U32).
-// (volatile like every statement that touches the condition code: the front end must not move it into another chain;
-// ptxas turns the flag into predicates and then schedules the independent slots freely)
-// c += a * b as a 64-bit integer: plain IMAD.WIDE.U32, no carry flag in or out -- the only full-rate form of the
-// instruction on B200 (59 lanes / clk / SM against 27 with a flag).  The caller guarantees the sum fits 64 bits.
-// (volatile: keeps the front end from splitting it into a multiply and 64-bit adds or hoisting it; ptxas still schedules)
-ZK_DEV void mad_wide_noflags(uint64_t& c, uint32_t a, uint32_t b) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c) : "r"(a), "r"(b)); }
-ZK_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
-ZK_DEV void mad_wide_top(uint32_t& lo, uint32_t& hi, uint32_t& top, uint32_t a, uint32_t b) {
-    asm volatile("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(top) : "r"(a), "r"(b));
 }
 }}  // namespace zk::ptx
 #endif

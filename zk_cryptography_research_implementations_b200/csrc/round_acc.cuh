@@ -29,27 +29,18 @@ struct TablePtrs {
 // NLIN extra tables enter the sum LINEARLY (a product with the all-ones table, which is then neither stored, folded
 // nor multiplied): s(X) += sum_l (lo_l + X (hi_l - lo_l)).  The sparse GKR layer prover's phases have exactly that
 // shape, h1*W + h2*1 (gkr_wide.cu).  Only the two half sums are accumulated; finalize() spreads them over the s(X).
-// COLS: the products are accumulated in carry-chain-free column accumulators (Fp::ColAcc, 45 registers per evaluation
-// instead of 17, no half-rate IMAD.WIDE.U32.X) -- for the launch that is bound by the products alone: round 0.
-template <int FID, int P, int D, bool SKIP1, int NLIN = 0, bool COLS = false> struct RoundAcc {
-    static_assert(!COLS || D == 2, "column accumulators are wired for degree 2");
+template <int FID, int P, int D, bool SKIP1, int NLIN = 0> struct RoundAcc {
     static constexpr int NE = D + 1;
     static constexpr int W = (D == 1) ? 9 : 17;
     static constexpr int T = P * D + NLIN;
     static constexpr int NC = NE * W + (NLIN > 0 ? 18 : 0);   // 32-bit columns a thread contributes
-    uint32_t acc[COLS ? 1 : NE][W];
-    typename Fp<FID>::ColAcc cacc[COLS ? NE : 1];
+    uint32_t acc[NE][W];
     uint32_t lin[NLIN > 0 ? 2 : 1][9];
     ZK_DEV void init() {
-        if (COLS) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) Fp<FID>::cols_init(cacc[e]);
-        } else {
+        for (int e = 0; e < NE; ++e)
 #pragma unroll
-            for (int e = 0; e < NE; ++e)
-#pragma unroll
-                for (int k = 0; k < W; ++k) acc[e][k] = 0;
-        }
+            for (int k = 0; k < W; ++k) acc[e][k] = 0;
 #pragma unroll
         for (int e = 0; e < (NLIN > 0 ? 2 : 1); ++e)
 #pragma unroll
@@ -58,15 +49,14 @@ template <int FID, int P, int D, bool SKIP1, int NLIN = 0, bool COLS = false> st
     ZK_DEV void add_point(int e, const Fe (&v)[T]) {
         if (D == 1) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) Fp<FID>::acc9_add(acc[COLS ? 0 : e], v[p]);
+            for (int p = 0; p < P; ++p) Fp<FID>::acc9_add(acc[e], v[p]);
         } else {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 Fe prod = v[p * D];
 #pragma unroll
                 for (int d = 1; d < D - 1; ++d) Fp<FID>::mont_mul(prod, prod, v[p * D + d]);
-                if (COLS) Fp<FID>::mul_acc_cols(cacc[COLS ? e : 0], prod, v[p * D + D - 1]);
-                else Fp<FID>::mul_acc(acc[COLS ? 0 : e], prod, v[p * D + D - 1]);
+                Fp<FID>::mul_acc(acc[e], prod, v[p * D + D - 1]);
             }
         }
     }
@@ -98,15 +88,8 @@ template <int FID, int P, int D, bool SKIP1, int NLIN = 0, bool COLS = false> st
     ZK_DEV void columns(uint32_t (&col)[NC]) const {
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-            if (COLS) {
-                uint32_t t[17];
-                Fp<FID>::cols_to_limbs(t, cacc[COLS ? e : 0]);
 #pragma unroll
-                for (int k = 0; k < W && k < 17; ++k) col[e * W + k] = t[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < W; ++k) col[e * W + k] = acc[COLS ? 0 : e][k];
-            }
+            for (int k = 0; k < W; ++k) col[e * W + k] = acc[e][k];
         }
         if (NLIN > 0) {
 #pragma unroll

@@ -55,8 +55,7 @@ template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, in
 template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t half, bool shared) {
     if (nlin != 0 && !(P == 1 && D == 2 && nlin == 1)) return unsupported_pd(ctx);
     ReduceScratch rs = reduce_scratch(ctx, shared);
-    // the column-accumulator form (D == 2) keeps one block per SM resident: two blocks' worth of grid per SM
-    int grid = launch_grid(ctx, half, (D == 2 && ZK_ROUND0_COLS) ? 2 : round_blocks_per_sm(P * D + nlin));
+    int grid = launch_grid(ctx, half, round_blocks_per_sm(P * D + nlin));
     if (nlin == 1) {
         round_evals_kernel<FID, 1, 2, 1><<<grid, kThreads, 0, ctx->stream>>>(tp, half, rs);
         return launch_check(ctx);

@@ -69,20 +69,29 @@ class WideCircuit:
     gates) for the sparse two-phase layer prover (csrc/gkr_wide.cu).  layer_bits[li] = log2(#values of layer li),
     li = 0..L (last entry = inputs).  `layers` as for `Circuit`: lists of (left, right, out, op)."""
 
-    def __init__(self, ctx: Context, layer_bits, layers):
+    def __init__(self, ctx: Context, layer_bits, layers=None, *, flat=None):
+        """`layers`: per layer a list of (left, right, out, op) or an (n, 4) array.  `flat=(layer_off, left, right, out, op)`:
+        the C-ABI's own layout (uint64 offsets, uint32 indices, uint8 operators) handed through without a copy."""
         self.ctx = ctx
         self.layer_bits = [int(b) for b in layer_bits]
-        self.n_layers = len(layers)
+        if flat is not None:
+            self._off, left, right, out, op = flat
+            self._off = np.ascontiguousarray(self._off, dtype=np.uint64)
+            left, right, out = (np.ascontiguousarray(a, dtype=np.uint32) for a in (left, right, out))
+            op = np.ascontiguousarray(op, dtype=np.uint8)
+            self.n_layers = len(self._off) - 1
+        else:
+            self.n_layers = len(layers)
+            off = [0]
+            for l in layers:
+                off.append(off[-1] + len(l))
+            def col(k, dt):
+                if isinstance(layers[0], np.ndarray):
+                    return np.ascontiguousarray(np.concatenate([l[:, k] for l in layers]).astype(dt))
+                return np.array([g[k] for l in layers for g in l], dtype=dt)
+            self._off = np.array(off, dtype=np.uint64)
+            left, right, out, op = col(0, np.uint32), col(1, np.uint32), col(2, np.uint32), col(3, np.uint8)
         assert len(self.layer_bits) == self.n_layers + 1
-        off = [0]
-        for l in layers:
-            off.append(off[-1] + len(l))
-        def col(k, dt):
-            if isinstance(layers[0], np.ndarray):
-                return np.ascontiguousarray(np.concatenate([l[:, k] for l in layers]).astype(dt))
-            return np.array([g[k] for l in layers for g in l], dtype=dt)
-        self._off = np.array(off, dtype=np.uint64)
-        left, right, out, op = col(0, np.uint32), col(1, np.uint32), col(2, np.uint32), col(3, np.uint8)
         bits = np.array(self.layer_bits, dtype=np.uint32)
         h = C.c_void_p()
         u32p = C.POINTER(C.c_uint32)
@@ -90,6 +99,8 @@ class WideCircuit:
                                                  left.ctypes.data_as(u32p), right.ctypes.data_as(u32p), out.ctypes.data_as(u32p),
                                                  op.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(h)))
         self.h = h
+        # a single output is the reference's padded [out, 0] layer (gkr_protocol.rs:43-51): the prover sees one output bit
+        self.layer_bits[0] = int(ctx.lib.zk_wide_circuit_output_bits(h))
 
     @classmethod
     def reference_shaped(cls, ctx: Context, layers):
@@ -142,3 +153,28 @@ def prove_wide(ctx: Context, circuit: WideCircuit, inputs, flags: int = 0, want_
         proofs.append(SumcheckProverProof(claims[i].copy(), polys, chal[o:o + r].copy()))
         o += r
     return Proof(output, claimed, proofs, wb[: L - 1].copy(), wc[: L - 1].copy())
+
+
+def verify_wide(ctx: Context, circuit: WideCircuit, proof: Proof, inputs, flags: int = 0) -> bool:
+    """gkr_protocol::verify (gkr_protocol.rs:146-236) for explicit layer widths; wiring predicates from the gate list"""
+    lib = ctx.lib
+    from .core import DeviceTable
+    L = circuit.n_layers
+    out = np.ascontiguousarray(as_elems(proof.circuit_output).reshape(-1, 4))
+    if out.shape[0] != (1 << circuit.layer_bits[0]):
+        return False
+    claims = np.ascontiguousarray(np.stack([sp.claimed_sum for sp in proof.sumcheck_proofs]))
+    coeffs = np.ascontiguousarray(np.concatenate([np.stack([p.coefficients for p in sp.round_univariate_polynomials])
+                                                  for sp in proof.sumcheck_proofs]))
+    pad = np.zeros((1, 4), dtype=np.uint64)
+    wb = np.ascontiguousarray(np.concatenate([as_elems(proof.wb_evaluations).reshape(-1, 4), pad]))
+    wc = np.ascontiguousarray(np.concatenate([as_elems(proof.wc_evaluations).reshape(-1, 4), pad]))
+    ok = C.c_int(0)
+    if isinstance(inputs, DeviceTable):
+        ctx.check(lib.zk_gkr_verify_wide_device(ctx.h, circuit.h, _ptr(out), _ptr(claims), _ptr(coeffs), _ptr(wb), _ptr(wc),
+                                                inputs.h, flags, C.byref(ok)))
+    else:
+        inputs = as_elems(inputs).reshape(-1, 4)
+        ctx.check(lib.zk_gkr_verify_wide(ctx.h, circuit.h, _ptr(out), _ptr(claims), _ptr(coeffs), _ptr(wb), _ptr(wc),
+                                         _ptr(inputs), inputs.shape[0], flags, C.byref(ok)))
+    return bool(ok.value)

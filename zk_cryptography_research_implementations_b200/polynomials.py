@@ -196,15 +196,35 @@ class SumPolynomial:
 
     # ---- device handle (zk_sumpoly); the handle owns its tables
     def _device_sumpoly(self, clone: bool):
+        """clone=True: the sumpoly gets copies (the reference clones: `self` stays usable).  clone=False: the tables of
+        `self` are MOVED into the sumpoly -- a table that sits in two slots (f*f, W_b == W_c) is cloned for its second
+        slot, and afterwards every MultilinearPolynomial of `self` holds a dead handle (any later use raises instead of
+        touching freed memory)."""
         ctx = self.ctx
         D = self.degree()
         if any(len(prod.polynomials) != D for prod in self.product_polynomials):
             raise ValueError("all products must have the same number of factors on the device path")
         polys = [p for prod in self.product_polynomials for p in prod.polynomials]
-        tabs = [(p.table.clone() if clone else p.table) for p in polys]
-        arr = (vp * len(tabs))(*[t.release() for t in tabs])
+        tabs, made, seen = [], [], set()
+        for p in polys:
+            p.table.h               # raises if the table was consumed by an earlier prove
+            if clone or id(p.table) in seen:
+                t = p.table.clone()
+                made.append(t)
+            else:
+                t = p.table
+                seen.add(id(t))
+            tabs.append(t)
+        arr = (vp * len(tabs))(*[t.h for t in tabs])
         h = vp()
-        ctx.check(ctx.lib.zk_sumpoly_create(ctx.h, arr, len(self.product_polynomials), D, C.byref(h)))
+        try:
+            ctx.check(ctx.lib.zk_sumpoly_create(ctx.h, arr, len(self.product_polynomials), D, C.byref(h)))
+        except Exception:
+            for t in made:          # nothing was transferred: drop the copies, the caller keeps its own tables
+                t.free()
+            raise
+        for t in tabs:              # ownership is now the sumpoly's: the copies and (clone=False) the caller's tables die here
+            t.release()
         return h
 
 

@@ -116,9 +116,11 @@ def generate_round_univariate(current_polynomial: SumPolynomial) -> np.ndarray: 
         ctx.lib.zk_sumpoly_free(ctx.h, sp)
 
 
-def prove(sum_polynomial: SumPolynomial, claimed_sum, transcript: Transcript, flags: int = 0) -> SumcheckProverProof:
-    """`prove` (sumcheck_gkr_protocol.rs:24-67).  Takes the polynomial by value like the reference
-    (its tables are consumed); the transcript is borrowed and advanced."""
+def prove(sum_polynomial: SumPolynomial, claimed_sum, transcript: Transcript, flags: int = 0, consume: bool = False) -> SumcheckProverProof:
+    """`prove` (sumcheck_gkr_protocol.rs:24-67).  The transcript is borrowed and advanced.  By default the tables are
+    copied on the device and `sum_polynomial` stays usable (a Rust caller that wants to keep its polynomial clones it
+    before the by-value call).  consume=True is the reference's by-value move without the copy: the tables are folded
+    in place and every polynomial of `sum_polynomial` is dead afterwards (use raises)."""
     ctx = sum_polynomial.ctx
     P, D = len(sum_polynomial.product_polynomials), sum_polynomial.degree()
     if P < 2:
@@ -126,7 +128,7 @@ def prove(sum_polynomial: SumPolynomial, claimed_sum, transcript: Transcript, fl
     if D < 2:
         raise ReferencePanic("more than one polynomial required for mul operation")
     n = sum_polynomial.number_of_variables()
-    sp = sum_polynomial._device_sumpoly(clone=False)
+    sp = sum_polynomial._device_sumpoly(clone=not consume)
     try:
         coeffs = np.zeros((max(n, 1), D + 1, 4), dtype=np.uint64)
         chal = np.zeros((max(n, 1), 4), dtype=np.uint64)
