@@ -813,10 +813,10 @@ def run_ours(args, wl, name=None, log2=None, steps=None, warmup=None):
     # ---- integer-multiply ceiling (register-resident probe, same clocks)
     integer = {}
     if rank == 0 and not args.no_probe:
-        for kind, name in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced")):
+        for kind, probe in ((0, "mont_mul"), (1, "fold_by_scalar"), (2, "mul_acc_unreduced")):
             ops, pms = C.c_double(), C.c_double()
             ctx.check(lib.zk_arith_probe(ctx.h, kind, 1500, 2, C.byref(ops), C.byref(pms)))
-            integer[name + "_Gops"] = ops.value / 1e9
+            integer[probe + "_Gops"] = ops.value / 1e9
         # IMAD.WIDE budget of one prove (per rank): round 0 evaluates (D+1) P products per pair (64 IMAD.WIDE each, D = 2)
         # or none (D = 1); each later round folds 2T entries per new pair (84 each) and evaluates D P products (s(1) is
         # derived) -- summed over the rounds: N/2 pairs in round 0, N/2 new pairs in all later rounds together.

@@ -40,10 +40,10 @@ enum {
     ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
     ZK_FLAG_HOST_ROUNDS = 16   /* keep every round on the host-driven path: one kernel + one host Fiat-Shamir step per
-                                  round.  Default: once tables x entries <= 2^tail_log (zk_ctx_set_tail_log, default 13)
-                                  ONE single-block launch runs all remaining rounds with the transcript on the
-                                  device (transcripts/.../fiat_shamir_transcript.rs:12-43 restated in csrc/dev_transcript.cuh);
-                                  the proof is identical either way */
+                                  round.  Default: once tables x entries <= 2^tail_log (zk_ctx_set_tail_log, default 24)
+                                  ONE persistent launch runs all remaining rounds with the transcript on the device
+                                  (transcripts/.../fiat_shamir_transcript.rs:12-43 restated in csrc/dev_transcript.cuh,
+                                  the round loop in csrc/devrounds.cuh); the proof is identical either way */
 };
 
 typedef struct zk_ctx zk_ctx;
@@ -65,11 +65,13 @@ int  zk_ctx_synchronize(zk_ctx *);
 int  zk_ctx_set_profiling(zk_ctx *, int on);
 int  zk_ctx_reset_stats(zk_ctx *);
 int  zk_ctx_get_stats(zk_ctx *, uint64_t *launches, uint64_t *round_launches, double *round_ms, double *round_bytes);
-/* Device tail: a sumcheck whose tables together hold at most 2^tail_log entries (one table: 2^tail_log; the three
- * tables of a GKR phase: 2^(tail_log-2) each, rounded down) finishes in ONE single-block launch that runs
- * every remaining round -- sums, fold, Lagrange coefficients (dense_univariate.rs:74-127), transcript absorb and
- * challenge (fiat_shamir_transcript.rs:22-43) -- on the GPU.  Default 13 (env ZKB200_TAIL_LOG); 0 keeps every round
- * host-driven; at most 16.  Proofs are bit-identical for every setting. */
+/* Device-resident rounds: a sumcheck whose tables together hold at most 2^tail_log entries (one table: 2^tail_log; the
+ * three tables of a GKR phase: 2^(tail_log-2) each, rounded down) finishes in ONE persistent cooperative launch that runs
+ * every remaining round -- sums, fold, grid barrier, Lagrange coefficients (dense_univariate.rs:74-127), transcript absorb
+ * and challenge (fiat_shamir_transcript.rs:22-43) -- on the GPU; blocks leave the loop as the tables shrink, so the last
+ * rounds run on one block.  Sharded provers exchange the per-round partial evaluations between the ranks' kernels over
+ * peer memory (zk_comm_peer_exchange).  Default 24 (env ZKB200_TAIL_LOG); 0 keeps every round host-driven; at most 32.
+ * Proofs are bit-identical for every setting. */
 int  zk_ctx_set_tail_log(zk_ctx *, int tail_log);
 int  zk_ctx_get_tail_log(const zk_ctx *);
 
@@ -242,6 +244,10 @@ int  zk_comm_init(zk_ctx *, int rank, int world, const uint8_t id[128]);   /* wo
  * on the per-round path.  Rank 0: create = 1 before the others attach; unlink after all have attached. */
 int  zk_comm_attach_mailboxes(zk_ctx *, const char *shm_name, int create);
 int  zk_comm_unlink_mailboxes(const char *shm_name);
+/* 1 if zk_comm_init could map every rank's exchange slots into every other rank (cudaIpc peer access): the sharded provers
+ * then run their sharded rounds in ONE persistent launch per rank and the per-round (d+1) x 32 B partial evaluations go from
+ * kernel to kernel over NVLink; 0: host-mediated exchange (mailboxes / ncclAllGather).  ZKB200_PEER_EXCHANGE=0 forces 0. */
+int  zk_comm_peer_exchange(const zk_ctx *);
 int  zk_comm_destroy(zk_ctx *);
 int  zk_comm_rank(const zk_ctx *);
 int  zk_comm_world(const zk_ctx *);

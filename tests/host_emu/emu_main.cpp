@@ -6,7 +6,7 @@
 #include <vector>
 #include "fp.cuh"
 #include "round_acc.cuh"
-#include "tail.cuh"
+#include "devrounds.cuh"
 #include "host_field.h"
 #include "../../oracle/zkoracle.h"
 
@@ -174,7 +174,8 @@ static void lanes_permute(uint64_t a[25]) {   // what CudaExec::permute does, on
     for (int i = 0; i < 25; ++i) a[i] = (uint64_t)lo.v[i] | ((uint64_t)hi.v[i] << 32);
 }
 
-struct HostExec {
+struct HostExec {   // one "thread" per block; blocks (and ranks) are stepped in an order that satisfies every wait
+    uint32_t bid_ = 0, nblocks_ = 1;
     int lane() const { return 0; }
     int warp() const { return 0; }
     void permute(uint64_t* s) const { lanes_permute(s); }
@@ -188,12 +189,55 @@ struct HostExec {
     }
     int tid() const { return 0; }
     int nthreads() const { return 1; }
+    uint32_t bid() const { return bid_; }
+    uint32_t nblocks() const { return nblocks_; }
+    uint32_t failure() const { return 9; }
     void sync() const {}
     template <int NC> void column_sums(const uint32_t (&col)[NC], unsigned long long* tot) const { for (int c = 0; c < NC; ++c) tot[c] = col[c]; }
     zk::Fe load(const zk::Fe* p) const { return *p; }
     void store(zk::Fe* p, const zk::Fe& v) const { *p = v; }
+    void prefetch(const zk::Fe*) const {}
+    uint32_t load_word(const uint32_t* p) const { return *p; }
+    void store_word(uint32_t* p, uint32_t v) const { *p = v; }
+    void grid_add(unsigned long long* p, unsigned long long v) const { *p += v; }
+    unsigned long long grid_take(unsigned long long* p) const { unsigned long long v = *p; *p = 0; return v; }
+    void arrive(zk::DevGlobal* g) const { g->arrive += 1; }
+    // the stepping order makes every wait already satisfied; anything else is a bug in the round bookkeeping
+    bool wait_arrivals(zk::DevGlobal* g, uint32_t target) const { return g->arrive == target; }
+    void release(zk::DevGlobal* g, uint32_t round) const { g->release = round; }
+    bool wait_release(zk::DevGlobal* g, uint32_t round) const { return g->release >= round; }
+    void store_peer(zk::Fe* p, const zk::Fe& v) const { *p = v; }
+    void publish_peer(uint32_t* seq, uint32_t v) const { *seq = v; }
+    bool wait_peers(zk::PeerSlot* mine, uint32_t world, uint32_t xs) const {
+        for (uint32_t q = 0; q < world; ++q) if (mine[q].seq != xs) return false;
+        return true;
+    }
+    zk::Fe load_peer(const zk::Fe* p) const { return *p; }
+    void rearm(zk::DevGlobal* g, bool failed) const { if (failed) g->abort_ = 1; else { g->arrive = 0; g->release = 0; } }
     void publish(uint32_t* seq, uint32_t v) const { *seq = v; }
 };
+
+// Runs one launch of the device-resident round loop on `nblocks` emulated blocks (one thread each, so a table of a few
+// entries already spreads over several blocks).  Blocks are stepped round by round, highest block first: a non-leader's
+// wait for the previous challenge and the leader's wait for the arrivals are then always satisfied.
+template <int FID, int P, int D, int NLIN> static int emu_launch(zk::DevArgs& a, int nblocks) {
+    typedef zk::DevRounds<FID, P, D, NLIN, HostExec> Blk;
+    zk::DevGlobal g; memset(&g, 0, sizeof g);
+    a.g = &g;
+    std::vector<zk::DevShared> sh(nblocks);
+    std::vector<HostExec> ex(nblocks);
+    std::vector<Blk*> blk(nblocks);
+    std::vector<char> alive(nblocks, 1);
+    for (int b = 0; b < nblocks; ++b) { ex[b].bid_ = b; ex[b].nblocks_ = nblocks; blk[b] = new Blk(a, sh[b], ex[b]); blk[b]->init(); }
+    for (int guard = 0; guard < 100 && alive[0]; ++guard)
+        for (int b = nblocks - 1; b >= 0; --b)
+            if (alive[b]) alive[b] = blk[b]->step();
+    int bad = 0;
+    for (int b = 0; b < nblocks; ++b) { if (alive[b] || blk[b]->failed) { ++bad; printf("emulated block %d did not finish cleanly\n", b); } delete blk[b]; }
+    if (g.arrive != 0 || g.release != 0 || g.abort_ != 0) { ++bad; printf("the launch did not re-arm its global state\n"); }
+    for (int c = 0; c < zk::kMaxCols; ++c) if (g.gacc[c] != 0) { ++bad; printf("grid accumulator column %d left non-zero\n", c); break; }
+    return bad;
+}
 
 static int test_dev_sponge() {
     int bad = 0;
@@ -258,7 +302,7 @@ static zk::FoldTable host_fold_table(const zk::HostField& f, const zk::HFe& r_mo
     for (int i = 0; i < 8; ++i) { memcpy(ft.w[i], cur.l, 32); cur = f.mul(cur, m232); }
     return ft;
 }
-template <int FID> static void fill_tail_consts(zk::TailArgs& a, const zk::HostField& f, int D) {
+template <int FID> static void fill_tail_consts(zk::DevArgs& a, const zk::HostField& f, int D) {
     zk::Interpolator ip(f, D);
     memcpy(a.interp, ip.matrix(), (size_t)(D + 1) * (D + 1) * 32);
     zk::HFe cur = f.one(), m232 = f.from_u64(1ull << 32);
@@ -266,7 +310,7 @@ template <int FID> static void fill_tail_consts(zk::TailArgs& a, const zk::HostF
 }
 
 // product sumcheck: `host_rounds` rounds are run the way the host driver runs them, the rest by the tail body
-template <int FID, int P, int D, int NLIN> static int run_tail_product(int n, int host_rounds, int prefix_bytes) {
+template <int FID, int P, int D, int NLIN> static int run_tail_product(int n, int host_rounds, int prefix_bytes, int nblocks = 1) {
     constexpr int T = P * D + NLIN, PO = P + NLIN + (P + NLIN < 2 ? 1 : 0), NE = D + 1;
     const uint64_t len = 1ull << n;
     zk::HostField f(FID);
@@ -322,19 +366,18 @@ template <int FID, int P, int D, int NLIN> static int run_tail_product(int n, in
         tabs[t].resize(cur_len);
         for (uint64_t i = 0; i < cur_len; ++i) tabs[t][i] = to_fe(&cur_ot[(((size_t)p * D + d) * cur_len + i) * 4]);
     }
-    zk::TailArgs a; memset(&a, 0, sizeof a);
-    zk::TailOut out; memset(&out, 0, sizeof out);
-    zk::TailShared sh;
+    zk::DevArgs a; memset(&a, 0, sizeof a);
+    zk::DevOut out; memset(&out, 0, sizeof out);
     for (int t = 0; t < T; ++t) a.tp.t[t] = tabs[t].data();
     a.log_len = 0; while ((1ull << a.log_len) < cur_len) ++a.log_len;
-    a.pending = host_rounds > 0; a.mode = zk::kTailProduct; a.seq = 77;
+    a.pending = host_rounds > 0; a.mode = zk::kDevProduct; a.seq = 77; a.world = 1;
+    a.max_rounds = a.log_len - (a.pending ? 1 : 0);
     if (a.pending) a.ft = host_fold_table(f, r);
     fill_tail_consts<FID>(a, f, D);
     tr.export_state(a.sponge.s, &a.sponge.pos);
     a.out = &out;
-    HostExec ex;
-    zk::sumcheck_tail_body<FID, P, D, NLIN>(a, sh, ex);
-    if (out.seq != 77 || (int)out.rounds != n - host_rounds) { ++bad; printf("tail rounds %u (want %d)\n", out.rounds, n - host_rounds); }
+    bad += emu_launch<FID, P, D, NLIN>(a, nblocks);
+    if (out.seq != 77 || out.status != zk::kDevOk || (int)out.rounds != n - host_rounds) { ++bad; printf("tail rounds %u status %u (want %d)\n", out.rounds, out.status, n - host_rounds); }
     for (int k = host_rounds; k < n; ++k) {
         if (memcmp(out.round_vals[k - host_rounds], &wc[(size_t)k * NE * 4], 32 * NE)) { ++bad; printf("tail<%d,%d,%d,%d> n=%d coeffs of round %d mismatch\n", FID, P, D, NLIN, n, k); }
         if (memcmp(&out.challenges[k - host_rounds], &wch[(size_t)k * 4], 32)) { ++bad; printf("tail challenge of round %d mismatch\n", k); }
@@ -352,7 +395,7 @@ template <int FID, int P, int D, int NLIN> static int run_tail_product(int n, in
 }
 
 // plain sumcheck (basic_sumcheck::Prover): the table absorb and the claimed sum on the host, the rounds in the tail
-template <int FID> static int run_tail_plain(int n, int host_rounds) {
+template <int FID> static int run_tail_plain(int n, int host_rounds, int nblocks = 1) {
     const uint64_t len = 1ull << n;
     zk::HostField f(FID);
     std::vector<uint64_t> table(len * 4);
@@ -381,24 +424,124 @@ template <int FID> static int run_tail_plain(int n, int host_rounds) {
     }
     std::vector<zk::Fe> tab(cur_len);
     for (uint64_t i = 0; i < cur_len; ++i) tab[i] = to_fe(&cur[4 * i]);
-    zk::TailArgs a; memset(&a, 0, sizeof a);
-    zk::TailOut out; memset(&out, 0, sizeof out);
-    zk::TailShared sh;
+    zk::DevArgs a; memset(&a, 0, sizeof a);
+    zk::DevOut out; memset(&out, 0, sizeof out);
     a.tp.t[0] = tab.data();
     a.log_len = 0; while ((1ull << a.log_len) < cur_len) ++a.log_len;
-    a.pending = host_rounds > 0; a.mode = zk::kTailPlain; a.seq = 5;
+    a.pending = host_rounds > 0; a.mode = zk::kDevPlain; a.seq = 5; a.world = 1;
+    a.max_rounds = a.log_len - (a.pending ? 1 : 0);
     if (a.pending) a.ft = host_fold_table(f, r);
     fill_tail_consts<FID>(a, f, 1);
     tr.export_state(a.sponge.s, &a.sponge.pos);
     a.out = &out;
-    HostExec ex;
-    zk::sumcheck_tail_body<FID, 1, 1, 0>(a, sh, ex);
-    if (out.seq != 5 || (int)out.rounds != n - host_rounds) { ++bad; printf("plain tail rounds %u (want %d)\n", out.rounds, n - host_rounds); }
+    bad += emu_launch<FID, 1, 1, 0>(a, nblocks);
+    if (out.seq != 5 || out.status != zk::kDevOk || (int)out.rounds != n - host_rounds) { ++bad; printf("plain tail rounds %u (want %d)\n", out.rounds, n - host_rounds); }
     for (int k = host_rounds; k < n; ++k) {
         if (memcmp(out.round_vals[k - host_rounds], &rp[(size_t)k * 8], 64)) { ++bad; printf("plain tail n=%d round %d sums mismatch\n", n, k); }
         if (memcmp(&out.challenges[k - host_rounds], &ch[(size_t)k * 4], 32)) { ++bad; printf("plain tail challenge %d mismatch\n", k); }
     }
     if (memcmp(&out.finals[0], fin, 32)) { ++bad; printf("plain tail final evaluation mismatch\n"); }
+    return bad;
+}
+
+// Sharded product sumcheck: G ranks hold the low-index-bit shards of the tables (comm.cu), every rank runs the round loop
+// on `nblocks` blocks and the leaders exchange their partial evaluations through each other's slot arrays; after
+// `sharded_rounds` rounds the launch stops with the last challenge pending, the shards are folded, gathered and
+// interleaved (what zk_prove_product_sharded's collapse does) and one more launch finishes on the full table.
+template <int FID, int P, int D> static int run_sharded_product(int n, int g, int sharded_rounds, int nblocks) {
+    constexpr int T = P * D, PO = P < 2 ? 2 : P, NE = D + 1;
+    typedef zk::DevRounds<FID, P, D, 0, HostExec> Blk;
+    const int G = 1 << g;
+    const uint64_t len = 1ull << n, m = len >> g;
+    zk::HostField f(FID);
+    std::vector<uint64_t> ot((size_t)PO * D * len * 4, 0);
+    for (int t = 0; t < T; ++t)
+        for (uint64_t i = 0; i < len; ++i) rand_fe(FID, &ot[((size_t)t * len + i) * 4], (rnd() % 16 == 0) ? (int)(rnd() % 6) : 0);
+    std::vector<uint64_t> red(len * 4); uint64_t claim[4];
+    zko_sumpoly_reduce(FID, ot.data(), PO, D, len, red.data()); zko_fe_sum(FID, red.data(), len, claim);
+    zko_transcript* otr = zko_transcript_new();
+    std::vector<uint64_t> wc((size_t)n * NE * 4), wch((size_t)n * 4), wfin((size_t)PO * D * 4);
+    if (zko_product_prove(FID, ot.data(), PO, D, len, claim, otr, wc.data(), wch.data(), wfin.data())) { printf("oracle refused\n"); return 1; }
+    int bad = 0;
+    // ---- stage 1: G ranks x nblocks blocks
+    std::vector<std::vector<std::vector<zk::Fe>>> shard(G, std::vector<std::vector<zk::Fe>>(T, std::vector<zk::Fe>(m)));
+    for (int q = 0; q < G; ++q)
+        for (int t = 0; t < T; ++t)
+            for (uint64_t j = 0; j < m; ++j) shard[q][t][j] = to_fe(&ot[((size_t)t * len + (j * G + q)) * 4]);
+    std::vector<std::vector<zk::PeerSlot>> slots(G, std::vector<zk::PeerSlot>(2 * G));
+    for (auto& v : slots) memset(v.data(), 0, v.size() * sizeof(zk::PeerSlot));
+    std::vector<zk::DevArgs> args(G);
+    std::vector<zk::DevOut> outs(G);
+    std::vector<zk::DevGlobal> glob(G);
+    std::vector<std::vector<zk::DevShared>> sh(G, std::vector<zk::DevShared>(nblocks));
+    std::vector<std::vector<HostExec>> ex(G, std::vector<HostExec>(nblocks));
+    std::vector<std::vector<Blk*>> blk(G, std::vector<Blk*>(nblocks));
+    std::vector<std::vector<char>> alive(G, std::vector<char>(nblocks, 1));
+    zk::HostTranscript tr0;
+    zk::HFe hclaim; memcpy(hclaim.l, claim, 32); tr0.append_be(f, hclaim);
+    for (int q = 0; q < G; ++q) {
+        zk::DevArgs& a = args[q];
+        memset(&a, 0, sizeof a); memset(&outs[q], 0, sizeof(zk::DevOut)); memset(&glob[q], 0, sizeof(zk::DevGlobal));
+        for (int t = 0; t < T; ++t) a.tp.t[t] = shard[q][t].data();
+        a.log_len = n - g; a.pending = 0; a.mode = zk::kDevProduct; a.seq = 11; a.max_rounds = sharded_rounds;
+        a.world = G; a.rank = q; a.xseq = 1000;
+        for (int r = 0; r < G; ++r) a.peers[r] = slots[r].data();
+        fill_tail_consts<FID>(a, f, D);
+        tr0.export_state(a.sponge.s, &a.sponge.pos);
+        a.out = &outs[q]; a.g = &glob[q];
+        for (int b = 0; b < nblocks; ++b) { ex[q][b].bid_ = b; ex[q][b].nblocks_ = nblocks; blk[q][b] = new Blk(a, sh[q][b], ex[q][b]); blk[q][b]->init(); }
+    }
+    for (int round = 0; round <= sharded_rounds; ++round) {
+        for (int q = 0; q < G; ++q)
+            for (int b = nblocks - 1; b >= 1; --b)
+                if (alive[q][b]) alive[q][b] = blk[q][b]->step();
+        if (!blk[0][0]->rounds_left()) {
+            for (int q = 0; q < G; ++q) alive[q][0] = blk[q][0]->step();   // finish_launch
+            break;
+        }
+        bool ok = true;
+        for (int q = 0; q < G; ++q) ok = ok && blk[q][0]->step_compute();
+        for (int q = 0; q < G; ++q) ok = ok && blk[q][0]->step_post();
+        for (int q = 0; q < G; ++q) ok = ok && blk[q][0]->step_finish();
+        if (!ok) { ++bad; printf("sharded emulation: a wait was not satisfied in round %d\n", round); break; }
+        for (int q = 0; q < G; ++q) blk[q][0]->advance();
+    }
+    for (int q = 0; q < G; ++q) {
+        for (int b = 0; b < nblocks; ++b) { if (alive[q][b]) { ++bad; printf("rank %d block %d still alive\n", q, b); } delete blk[q][b]; }
+        if (outs[q].seq != 11 || outs[q].status != zk::kDevOk || (int)outs[q].rounds != sharded_rounds) { ++bad; printf("rank %d: rounds %u status %u\n", q, outs[q].rounds, outs[q].status); }
+        for (int k = 0; k < sharded_rounds; ++k) {
+            if (memcmp(outs[q].round_vals[k], &wc[(size_t)k * NE * 4], 32 * NE)) { ++bad; printf("sharded<%d,%d,%d> n=%d G=%d rank %d round %d coefficients mismatch\n", FID, P, D, n, G, q, k); }
+            if (memcmp(&outs[q].challenges[k], &wch[(size_t)k * 4], 32)) { ++bad; printf("sharded rank %d round %d challenge mismatch\n", q, k); }
+        }
+    }
+    // ---- collapse: fold the shards by the pending challenge, gather, interleave; stage 2 on one rank
+    zk::HFe r; memcpy(r.l, &outs[0].challenges[sharded_rounds - 1], 32);
+    uint64_t cur = m >> (sharded_rounds - 1);           // local length before the pending fold
+    const zk::FoldTable ft = host_fold_table(f, r);
+    std::vector<std::vector<zk::Fe>> full(T, std::vector<zk::Fe>((cur / 2) * G));
+    for (int q = 0; q < G; ++q)
+        for (int t = 0; t < T; ++t)
+            for (uint64_t j = 0; j < cur / 2; ++j) {
+                zk::Fe o;
+                zk::FoldScalar<FID>::fold(o, shard[q][t][j], shard[q][t][j + cur / 2], ft);
+                full[t][j * G + q] = o;
+            }
+    zk::DevArgs a; memset(&a, 0, sizeof a);
+    zk::DevOut out; memset(&out, 0, sizeof out);
+    for (int t = 0; t < T; ++t) a.tp.t[t] = full[t].data();
+    const uint64_t flen = (cur / 2) * G;
+    a.log_len = 0; while ((1ull << a.log_len) < flen) ++a.log_len;
+    a.pending = 0; a.mode = zk::kDevProduct; a.seq = 12; a.world = 1; a.max_rounds = a.log_len;
+    fill_tail_consts<FID>(a, f, D);
+    memcpy(&a.sponge, &outs[G - 1].sponge, sizeof a.sponge);
+    a.out = &out;
+    bad += emu_launch<FID, P, D, 0>(a, nblocks);
+    if ((int)out.rounds != n - sharded_rounds) { ++bad; printf("stage 2 rounds %u (want %d)\n", out.rounds, n - sharded_rounds); }
+    for (int k = sharded_rounds; k < n; ++k)
+        if (memcmp(out.round_vals[k - sharded_rounds], &wc[(size_t)k * NE * 4], 32 * NE) || memcmp(&out.challenges[k - sharded_rounds], &wch[(size_t)k * 4], 32)) { ++bad; printf("sharded stage 2 round %d mismatch\n", k); }
+    for (int t = 0; t < T; ++t)
+        if (memcmp(&out.finals[t], &wfin[(size_t)t * 4], 32)) { ++bad; printf("sharded final value %d mismatch\n", t); }
+    zko_transcript_free(otr);
     return bad;
 }
 
@@ -415,6 +558,23 @@ template <int FID> static int run_tails() {
     bad += run_tail_product<FID, 1, 3, 0>(3, 0, 2);
     bad += run_tail_product<FID, 4, 2, 0>(3, 2, 135);
     bad += run_tail_product<FID, 3, 2, 0>(5, 5, 136);
+    // several blocks: the grid accumulator, arrivals / release, blocks leaving as the tables shrink
+    for (int nb : {2, 3, 5, 8, 64})
+        for (int n = 1; n <= 7; n += 2)
+            for (int h = 0; h <= 2 && h <= n; ++h) {
+                bad += run_tail_product<FID, 1, 2, 0>(n, h, n + h, nb);
+                bad += run_tail_product<FID, 1, 2, 1>(n, h, 7, nb);
+                bad += run_tail_plain<FID>(n, h, nb);
+            }
+    bad += run_tail_product<FID, 2, 2, 0>(6, 0, 0, 7);
+    bad += run_tail_product<FID, 2, 3, 0>(5, 1, 1, 4);
+    // several ranks exchanging partial evaluations through peer slots, then the collapse
+    for (int g = 1; g <= 3; ++g)
+        for (int nb : {1, 3})
+            for (int sr = 1; sr <= 3; ++sr) {
+                bad += run_sharded_product<FID, 1, 2>(g + 4, g, sr, nb);
+                if (g < 3) bad += run_sharded_product<FID, 2, 2>(g + 3, g, sr > 2 ? 2 : sr, nb);
+            }
     printf("tail field %d: %s\n", FID, bad ? "FAIL" : "ok");
     return bad;
 }

@@ -203,12 +203,12 @@ def test_wide_prover_reduction_layer_with_heavy_fan_in(zk, co, ctx_for):
     inputs = [rng.randrange(p) for _ in range(1 << w)]
     want = po.gkr_prove_general([[po.Gate(*g) for g in l] for l in layers], bits, inputs, p)
     ctx = ctx_for(fid)
-    for tail_log in (13, 0):
+    for tail_log in (24, 13, 0):
         ctx.set_tail_log(tail_log)
         try:
             proof = gkr.prove_wide(ctx, gkr.WideCircuit(ctx, bits, layers), zk.fe_from_ints(fid, inputs))
         finally:
-            ctx.set_tail_log(13)
+            ctx.set_tail_log(24)
         _compare_wide(zk, fid, proof,
                       [c for (_, polys, _) in want.sumcheck_proofs for poly in polys for c in poly],
                       [c for (_, _, ch) in want.sumcheck_proofs for c in ch],

@@ -43,8 +43,17 @@ def _gpu_product_prove(zk, ctx, tabs_dev, P, D, claimed, flags=0):
     return coeffs, ch, fin, tr
 
 
+@pytest.fixture
+def tail_logs(ctx_for):
+    """both regimes of the round loop: 13 = host-driven per-round kernels (592-block grids, HBM streaming) down to 2^12
+    entries, then a single-block device launch; 24 = the whole prove in ONE persistent multi-block launch"""
+    yield (13, 24)
+    for fid in (0, 1, 2):
+        ctx_for(fid).set_tail_log(24)
+
+
 @pytest.mark.parametrize("n", [20, 22])
-def test_f_times_g_limb_for_limb_at_hbm_sizes(zk, co, ctx_for, all_cores, n):
+def test_f_times_g_limb_for_limb_at_hbm_sizes(zk, co, ctx_for, all_cores, tail_logs, n):
     """BASELINE configs[2] in miniature (f*g on BN254 Fq, the bench's own seeded tables): every coefficient, challenge and
     folded value of the GPU proof equals the oracle's, which proves the reference's form f*g + 0*0."""
     fid = 0
@@ -57,17 +66,19 @@ def test_f_times_g_limb_for_limb_at_hbm_sizes(zk, co, ctx_for, all_cores, n):
     claimed = np.zeros(4, dtype=np.uint64)
     co.lib().zko_fe_sum(fid, co._p(co.sumpoly_reduce(fid, host)), N, co._p(claimed))
     want_coeffs, want_ch, want_fin = co.product_prove(fid, host, claimed, co.Transcript())
-    for flags in (0, 1):     # s(1) derived from the running claim / summed directly
-        tabs = dev if flags == 0 else [ctx.generate(SEED, i, N) for i in range(2)]
-        coeffs, ch, fin, _ = _gpu_product_prove(zk, ctx, tabs, 1, 2, claimed, flags)
-        assert np.array_equal(coeffs, want_coeffs), "round polynomials differ from the oracle (flags=%d)" % flags
-        assert np.array_equal(ch, want_ch)
-        assert np.array_equal(fin, want_fin[0])
+    for tl in tail_logs:
+        ctx.set_tail_log(tl)
+        for flags in (0, 1):     # s(1) derived from the running claim / summed directly
+            tabs = [ctx.generate(SEED, i, N) for i in range(2)]
+            coeffs, ch, fin, _ = _gpu_product_prove(zk, ctx, tabs, 1, 2, claimed, flags)
+            assert np.array_equal(coeffs, want_coeffs), "round polynomials differ from the oracle (tail_log=%d flags=%d)" % (tl, flags)
+            assert np.array_equal(ch, want_ch)
+            assert np.array_equal(fin, want_fin[0])
     ok, _, _ = co.product_verify(fid, claimed, want_coeffs, co.Transcript())
     assert ok
 
 
-def test_gkr_shaped_2x2_limb_for_limb_at_2p20(zk, co, ctx_for, all_cores):
+def test_gkr_shaped_2x2_limb_for_limb_at_2p20(zk, co, ctx_for, all_cores, tail_logs):
     """(P, D) = (2, 2) -- add*(Wb+Wc) + mul*(Wb*Wc), the GKR layer shape -- over four 2^20-entry tables, BLS12-381 Fr"""
     fid = 2
     ctx = ctx_for(fid)
@@ -78,38 +89,43 @@ def test_gkr_shaped_2x2_limb_for_limb_at_2p20(zk, co, ctx_for, all_cores):
     co.lib().zko_fe_sum(fid, co._p(co.sumpoly_reduce(fid, host)), N, co._p(claimed))
     tr_o = co.Transcript()
     want_coeffs, want_ch, want_fin = co.product_prove(fid, host, claimed, tr_o)
-    coeffs, ch, fin, tr = _gpu_product_prove(zk, ctx, dev, 2, 2, claimed)
-    assert np.array_equal(coeffs, want_coeffs) and np.array_equal(ch, want_ch)
-    assert np.array_equal(fin.reshape(2, 2, 4), want_fin)
-    assert tr.sample_random_challenge() == tr_o.sample_random_challenge()      # transcripts end in the same state
+    want_next = tr_o.sample_random_challenge()
+    for tl in tail_logs:
+        ctx.set_tail_log(tl)
+        coeffs, ch, fin, tr = _gpu_product_prove(zk, ctx, [ctx.generate(SEED + 1, i, N) for i in range(4)], 2, 2, claimed)
+        assert np.array_equal(coeffs, want_coeffs) and np.array_equal(ch, want_ch), tl
+        assert np.array_equal(fin.reshape(2, 2, 4), want_fin)
+        assert tr.sample_random_challenge() == want_next      # transcripts end in the same state
 
 
-def _plain_limb_for_limb(zk, co, ctx, fid, table):
+def _plain_limb_for_limb(zk, co, ctx, fid, table, tail_logs=(24,)):
     from zk_cryptography_research_implementations_b200.sumcheck_protocol import Prover
-    proof = Prover.init(ctx, table).prove()
     c, rp, ch, fin = co.basic_prove(fid, table)
-    assert np.array_equal(proof.initial_claimed_sum, c)
-    assert np.array_equal(proof.round_univariate_polynomials, rp)
-    assert np.array_equal(proof.challenges, ch)
-    assert np.array_equal(proof.final_evaluation, fin)
+    for tl in tail_logs:
+        ctx.set_tail_log(tl)
+        proof = Prover.init(ctx, table).prove()
+        assert np.array_equal(proof.initial_claimed_sum, c)
+        assert np.array_equal(proof.round_univariate_polynomials, rp), tl
+        assert np.array_equal(proof.challenges, ch)
+        assert np.array_equal(proof.final_evaluation, fin)
     assert co.basic_verify(fid, table, proof.initial_claimed_sum, proof.round_univariate_polynomials)
 
 
-def test_plain_sumcheck_limb_for_limb_at_2p20(zk, co, ctx_for, all_cores):
+def test_plain_sumcheck_limb_for_limb_at_2p20(zk, co, ctx_for, all_cores, tail_logs):
     """the reference's own largest test input, vec![Fr::from(3); 1 << 20] (protocol.rs:41-55), and a seeded random table"""
     fid = 2
     ctx = ctx_for(fid)
     N = 1 << 20
-    _plain_limb_for_limb(zk, co, ctx, fid, np.tile(zk.fe_from_ints(fid, [3]), (N, 1)))
-    _plain_limb_for_limb(zk, co, ctx, fid, ctx.generate(SEED, 0, N).download())
+    _plain_limb_for_limb(zk, co, ctx, fid, np.tile(zk.fe_from_ints(fid, [3]), (N, 1)), tail_logs)
+    _plain_limb_for_limb(zk, co, ctx, fid, ctx.generate(SEED, 0, N).download(), tail_logs)
 
 
-def test_plain_sumcheck_limb_for_limb_at_2p24(zk, co, ctx_for, all_cores):
+def test_plain_sumcheck_limb_for_limb_at_2p24(zk, co, ctx_for, all_cores, tail_logs):
     """BASELINE configs[1] at full size (2^24 entries, BLS12-381 Fr, 512 MiB), the whole Prover::prove including the
     reference-mandated Keccak absorb of the table on both sides"""
     fid = 2
     ctx = ctx_for(fid)
-    _plain_limb_for_limb(zk, co, ctx, fid, ctx.generate(SEED, 0, 1 << 24).download())
+    _plain_limb_for_limb(zk, co, ctx, fid, ctx.generate(SEED, 0, 1 << 24).download(), tail_logs)
 
 
 @pytest.mark.parametrize("n", [20, 23])

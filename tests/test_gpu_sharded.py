@@ -1,5 +1,6 @@
-"""Two ranks on two GPUs (skipped with fewer): the native sharded prover (NCCL all-gather per round,
-csrc/comm.cu) and the Python round loop over torch.distributed, both against the unsharded oracle."""
+"""2, 4 and 8 ranks, one GPU each (skipped with fewer devices): the native sharded provers (csrc/comm.cu) with every
+exchange path -- in-kernel over peer memory (the device-resident round loop, default), host mailboxes, ncclAllGather --
+and the Python round loop over torch.distributed, all against the unsharded oracle, limb for limb."""
 import os
 import socket
 import sys
@@ -35,28 +36,42 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     ok = True
+    notes = []
     try:
         fid = 0
         ctx = zk.Context(fid, rank)
         sharded.init_comm(ctx)
-        for (P, D, n, collapse) in [(2, 2, 9, 1), (2, 2, 12, 64), (1, 2, 14, 256), (2, 3, 8, 4)]:
+        peer = bool(ctx.lib.zk_comm_peer_exchange(ctx.h))
+        for (P, D, n, collapse) in [(2, 2, 9, 1), (2, 2, 12, 64), (1, 2, 14, 256), (2, 3, 8, 4), (1, 2, 20, 4096), (1, 2, 18, 1)]:
             N = 1 << n
-            full = np.stack([np.stack([np.array(zk.fe_from_ints(fid, zk.synthetic_table_ints(fid, 5, p * D + d, N))) for d in range(D)]) for p in range(P)])
+            if N // world < 2:
+                continue
+            co.set_threads(os.cpu_count() or 1)
+            full = np.stack([np.stack([co.table_generate(fid, 5, p * D + d, N) for d in range(D)]) for p in range(P)])
             Pref = max(P, 2)
             ref_tabs = np.zeros((Pref, D, N, 4), dtype=np.uint64)
             ref_tabs[:P] = full
             claimed = np.zeros(4, dtype=np.uint64)
             co.lib().zko_fe_sum(fid, co._p(co.sumpoly_reduce(fid, ref_tabs)), N, co._p(claimed))
             want = co.product_prove(fid, ref_tabs, claimed, co.Transcript())
-            # native driver, shard generated on the device
-            tabs = [ctx.generate(5, i, N // world, first=rank, step=world) for i in range(P * D)]
-            arr = (C.c_void_p * (P * D))(*[t.release() for t in tabs])
-            sp = C.c_void_p()
-            ctx.check(ctx.lib.zk_sumpoly_create(ctx.h, arr, P, D, C.byref(sp)))
-            tr = Transcript()
-            got = sharded.prove_product_native(ctx, sp, P, D, n, claimed, tr, collapse_len=collapse)
-            ctx.lib.zk_sumpoly_free(ctx.h, sp)
-            ok &= np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2].reshape(P, D, 4), want[2][:P])
+            co.set_threads(1)
+            # native driver, shard generated on the device; flags: 0 = default exchange (in-kernel over peer memory when the
+            # peers could be mapped), 16 = host-driven rounds with the shared mailboxes, 4 = ncclAllGather per round,
+            # 1 = s(1) summed directly
+            for flags in (0, 16, 4, 1):
+                tabs = [ctx.generate(5, i, N // world, first=rank, step=world) for i in range(P * D)]
+                arr = (C.c_void_p * (P * D))(*[t.release() for t in tabs])
+                sp = C.c_void_p()
+                ctx.check(ctx.lib.zk_sumpoly_create(ctx.h, arr, P, D, C.byref(sp)))
+                tr = Transcript()
+                got = sharded.prove_product_native(ctx, sp, P, D, n, claimed, tr, flags=flags, collapse_len=collapse)
+                ctx.lib.zk_sumpoly_free(ctx.h, sp)
+                same = np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2].reshape(P, D, 4), want[2][:P])
+                if not same:
+                    notes.append("product (P,D,n,collapse)=%s flags=%d differs from the oracle" % ((P, D, n, collapse), flags))
+                ok &= same
+            if n > 14:
+                continue
             # Python round loop over torch.distributed (NCCL), CUDA engine
             shard = np.stack([np.stack([sharded.shard_of(full[p, d], rank, world) for d in range(D)]) for p in range(P)])
             eng = sharded.CudaShardEngine(ctx, shard)
@@ -69,37 +84,43 @@ def _worker(rank, world, port, q):
             ctx.check(ctx.lib.zk_mle_evaluate_sharded(ctx.h, local.h, _ptr(np.ascontiguousarray(want[1])), n, _ptr(out)))
             ok &= np.array_equal(out, co.mle_evaluate(fid, full[0, 0], want[1]))
         # plain sumcheck over a sharded table: the caller absorbs the table, the rest must equal the reference proof
-        for (n, collapse) in [(11, 1), (13, 128)]:
+        for (n, collapse) in [(11, 1), (13, 128), (19, 2048)]:
             N = 1 << n
-            full = np.array(zk.fe_from_ints(fid, zk.synthetic_table_ints(fid, 6, 0, N)))
+            full = co.table_generate(fid, 6, 0, N)
             claimed_w, rp_w, ch_w, fin_w = co.basic_prove(fid, full)
-            local = ctx.generate(6, 0, N // world, first=rank, step=world)
-            tr = Transcript()
-            tr.append(co.mle_to_bytes(fid, full))
-            claimed = np.zeros(4, dtype=np.uint64); rp = np.zeros((n, 2, 4), dtype=np.uint64)
-            ch = np.zeros((n, 4), dtype=np.uint64); fin = np.zeros(4, dtype=np.uint64)
-            ctx.check(ctx.lib.zk_prove_basic_sharded(ctx.h, local.h, tr.h, _ptr(claimed), _ptr(rp), _ptr(ch), _ptr(fin), 0, collapse))
-            ok &= np.array_equal(claimed, claimed_w) and np.array_equal(rp, rp_w) and np.array_equal(ch, ch_w) and np.array_equal(fin, fin_w)
-        q.put((rank, bool(ok)))
+            for flags in (0, 16, 4):
+                local = ctx.generate(6, 0, N // world, first=rank, step=world)
+                tr = Transcript()
+                tr.append(co.mle_to_bytes(fid, full))
+                claimed = np.zeros(4, dtype=np.uint64); rp = np.zeros((n, 2, 4), dtype=np.uint64)
+                ch = np.zeros((n, 4), dtype=np.uint64); fin = np.zeros(4, dtype=np.uint64)
+                ctx.check(ctx.lib.zk_prove_basic_sharded(ctx.h, local.h, tr.h, _ptr(claimed), _ptr(rp), _ptr(ch), _ptr(fin), flags, collapse))
+                same = np.array_equal(claimed, claimed_w) and np.array_equal(rp, rp_w) and np.array_equal(ch, ch_w) and np.array_equal(fin, fin_w)
+                if not same:
+                    notes.append("plain (n,collapse)=%s flags=%d differs from the oracle" % ((n, collapse), flags))
+                ok &= same
+        q.put((rank, bool(ok), peer, notes))
     except Exception as e:  # pragma: no cover
-        q.put((rank, repr(e)))
+        import traceback
+        q.put((rank, False, None, [repr(e), traceback.format_exc()[-1500:]]))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_sharded_prover_matches_oracle():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_provers_match_the_oracle(world):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
+    res = [q.get(timeout=900) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(r, True) for r in range(world)]
+    assert sorted((r[0], r[1]) for r in res) == [(r, True) for r in range(world)], [r[3] for r in res]
+    print("peer-memory exchange attached:", [r[2] for r in res])

@@ -96,6 +96,7 @@ SIGNATURES = {
     "zk_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
     "zk_comm_attach_mailboxes": (C.c_int, [vp, C.c_char_p, C.c_int]),
     "zk_comm_unlink_mailboxes": (C.c_int, [C.c_char_p]),
+    "zk_comm_peer_exchange": (C.c_int, [vp]),
     "zk_comm_destroy": (C.c_int, [vp]),
     "zk_comm_rank": (C.c_int, [vp]),
     "zk_comm_world": (C.c_int, [vp]),

@@ -16,6 +16,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -90,6 +91,96 @@ __global__ void __launch_bounds__(kThreads) interleave_kernel(const Fe* gathered
 }
 }  // namespace
 
+// In-kernel exchange of the device-resident rounds (devrounds.cuh): every rank owns a PeerSlot[2][world] array in its
+// HBM; the other ranks map it (cudaIpc, peer access over NVLink) and their round-loop kernels write their partial
+// evaluations straight into it.  Collective over the communicator; leaves peers_attached false (and the host-mailbox
+// exchange in charge) if any rank cannot map any peer.  ZKB200_PEER_EXCHANGE=0 skips it.
+static int attach_peers(zk_ctx* ctx) {
+    const int G = ctx->world;
+    ctx->peers_attached = false;
+    if (G < 2 || G > kMaxRanks) return ZK_OK;
+    if (const char* knob = getenv("ZKB200_PEER_EXCHANGE"))
+        if (knob[0] == '0') return ZK_OK;
+    PeerSlot* own = nullptr;
+    ZK_CUDA(cudaMalloc(&own, sizeof(PeerSlot) * 2 * (size_t)G));
+    ZK_CUDA(cudaMemset(own, 0, sizeof(PeerSlot) * 2 * (size_t)G));
+    ctx->peer_slots[ctx->rank] = own;
+    cudaIpcMemHandle_t mine;
+    int ok = cudaIpcGetMemHandle(&mine, own) == cudaSuccess ? 1 : 0;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    // all-gather {handle, ok} through NCCL (device staging buffers)
+    const size_t rec = 64 + 8;
+    uint8_t *d_send = nullptr, *d_recv = nullptr;
+    ZK_CUDA(cudaMalloc(&d_send, rec));
+    ZK_CUDA(cudaMalloc(&d_recv, rec * G));
+    std::vector<uint8_t> h_send(rec, 0), h_recv(rec * G, 0);
+    auto gather = [&]() -> int {
+        ZK_CUDA(cudaMemcpyAsync(d_send, h_send.data(), rec, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_NCCL(g_nccl.AllGather(d_send, d_recv, rec, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+        ZK_CUDA(cudaMemcpyAsync(h_recv.data(), d_recv, rec * G, cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return ZK_OK;
+    };
+    memcpy(h_send.data(), &mine, 64);
+    h_send[64] = (uint8_t)ok;
+    int rc = gather();
+    if (rc) return rc;
+    for (int q = 0; q < G; ++q) ok = ok && h_recv[rec * q + 64];
+    if (ok) {
+        for (int q = 0; q < G && ok; ++q) {
+            if (q == ctx->rank) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, h_recv.data() + rec * q, 64);
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();   // clear: falling back is not an error
+                ok = 0;
+            } else {
+                ctx->peer_slots[q] = (PeerSlot*)p;
+            }
+        }
+    }
+    // every rank must have mapped every peer, or nobody uses the path
+    h_send[64] = (uint8_t)ok;
+    rc = gather();
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    if (rc) return rc;
+    for (int q = 0; q < G; ++q) ok = ok && h_recv[rec * q + 64];
+    ctx->peers_attached = ok != 0;
+    return ZK_OK;
+}
+static void detach_peers(zk_ctx* ctx) {
+    for (int q = 0; q < kMaxRanks; ++q) {
+        if (!ctx->peer_slots[q]) continue;
+        if (q == ctx->rank) cudaFree(ctx->peer_slots[q]);
+        else cudaIpcCloseMemHandle(ctx->peer_slots[q]);
+        ctx->peer_slots[q] = nullptr;
+    }
+    ctx->peers_attached = false;
+}
+// All ranks agree on the exchange sequence number a sharded prove starts from (a rank that failed half-way through an
+// earlier prove would otherwise wait for numbers its peers never send): one 4-byte all-gather per prove.
+static int agree_xseq(zk_ctx* ctx) {
+    const int G = ctx->world;
+    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_send, &ctx->xseq, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_NCCL(g_nccl.AllGather(ctx->xchg_send, ctx->xchg_recv, sizeof(unsigned), ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(ctx->xchg_host, ctx->xchg_recv, sizeof(unsigned) * G, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned mx = 0;
+    for (int q = 0; q < G; ++q) mx = std::max(mx, reinterpret_cast<const unsigned*>(ctx->xchg_host)[q]);
+    ctx->xseq = (mx + 128u) & ~63u;
+    return ZK_OK;
+}
+// rounds the sharded prover runs before the collapse, counted from a round that sees local tables of `len` entries:
+// round 0 evaluates without folding, every later round folds first and stays sharded while len/2 > collapse_len
+static uint32_t sharded_rounds_from(uint64_t len, bool pending, uint64_t collapse_len) {
+    uint32_t r = 0;
+    if (!pending) { r = 1; }          // this round only evaluates; the next one is the first to fold `len`
+    while (len / 2 > collapse_len && len >= 4) { ++r; len /= 2; }
+    return r;
+}
+
 extern "C" int zk_comm_unique_id(uint8_t out[128]) {
     if (!g_nccl.load()) return ZK_ERR_CUDA;
     ncclUniqueId id;
@@ -114,12 +205,15 @@ extern "C" int zk_comm_init(zk_ctx* ctx, int rank, int world, const uint8_t id_b
     ZK_CUDA(cudaMalloc(&ctx->xchg_send, kMaxEvals * sizeof(Fe)));
     ZK_CUDA(cudaMalloc(&ctx->xchg_recv, (size_t)world * kMaxEvals * sizeof(Fe)));
     ZK_CUDA(cudaHostAlloc(&ctx->xchg_host, (size_t)world * kMaxEvals * sizeof(Fe), cudaHostAllocDefault));
-    return ZK_OK;
+    return attach_peers(ctx);
 }
+// 1 if the per-round exchange of the sharded provers runs inside the round-loop kernels over peer memory (NVLink)
+extern "C" int zk_comm_peer_exchange(const zk_ctx* ctx) { return ctx->peers_attached ? 1 : 0; }
 
 extern "C" int zk_comm_destroy(zk_ctx* ctx) {
     if (!ctx->nccl_comm) return ZK_OK;
     cudaStreamSynchronize(ctx->stream);
+    detach_peers(ctx);
     g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     if (ctx->xmail_host) {
@@ -243,10 +337,31 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
     tr->t.append_be(f, claim);
     HFe evals[kMaxEvals], coeffs[kMaxEvals], r = f.zero(), running = claim;
     bool sharded = true;
+    const bool dev_exchange = ctx->peers_attached && !(flags & (ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_HOST_ROUNDS));
+    if (dev_exchange) {
+        int rc0 = agree_xseq(ctx);
+        if (rc0) return rc0;
+    }
     for (uint32_t k = 0; k < n; ++k) {
         const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
         int rc;
         bool need_plain_evals = (k == 0);
+        // the remaining SHARDED rounds in one persistent launch per rank: partial evaluations go from kernel to kernel
+        // over peer memory, every rank runs the transcript on its GPU (devrounds.cuh); the collapse follows on the host
+        if (sharded && dev_exchange && dev_rounds_apply(ctx, sp->len, P * D, flags) && (k == 0 ? sp->len > collapse_len : sp->len / 2 > collapse_len)) {
+            const uint32_t want = sharded_rounds_from(sp->len, k > 0, collapse_len);
+            uint32_t ran = 0;
+            rc = run_dev_rounds(ctx, ptrs_of(sp), P, D, 0, kDevProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
+                                coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, nullptr, want, true, &ran);
+            if (rc) return rc;
+            // the tables were folded by every challenge but the last one
+            const uint32_t folds = ran - (k == 0 ? 1u : 0u);
+            set_len(sp, sp->len >> folds);
+            k += ran - 1;
+            memcpy(r.l, challenges_out + (size_t)k * 4, 32);
+            running = f.horner(reinterpret_cast<const HFe*>(coeffs_out + (size_t)k * NE * 4), NE, r);
+            continue;
+        }
         if (k > 0 && sharded && sp->len / 2 <= collapse_len) {
             // fold by r_{k-1} locally, then gather: the remaining rounds run on the full table
             rc = launch_fold0(ctx, ptrs_of(sp), P * D, sp->len, make_fold_table(f, r));
@@ -263,9 +378,9 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
             sharded = false;
         }
         TablePtrs tp = ptrs_of(sp);
-        if (!sharded && tail_applies(ctx, sp->len, P * D, flags)) {   // collapsed and small: the rest in one launch per rank
-            rc = run_tail(ctx, tp, P, D, 0, kTailProduct, sp->len, need_plain_evals ? nullptr : &r, tr->t,
-                          coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
+        if (!sharded && dev_rounds_apply(ctx, sp->len, P * D, flags)) {   // collapsed and small: the rest in one launch per rank
+            rc = run_dev_rounds(ctx, tp, P, D, 0, kDevProduct, sp->len, need_plain_evals ? nullptr : &r, tr->t,
+                                coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
             if (rc) return rc;
             set_len(sp, 1);
             return ZK_OK;
@@ -324,6 +439,11 @@ extern "C" int zk_prove_basic_sharded(zk_ctx* ctx, zk_table* local, zk_transcrip
     sp.tabs.assign(1, local);
     HFe evals[2], r = f.zero();
     bool sharded = G > 1;
+    const bool dev_exchange = G > 1 && ctx->peers_attached && !(flags & (ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_HOST_ROUNDS));
+    if (dev_exchange) {
+        int rc0 = agree_xseq(ctx);
+        if (rc0) return rc0;
+    }
     if (n == 0) {
         ZK_CUDA(cudaMemcpyAsync(claimed_sum, local->d, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
         ZK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -348,10 +468,22 @@ extern "C" int zk_prove_basic_sharded(zk_ctx* ctx, zk_table* local, zk_transcrip
             if ((rc = collapse(ctx, &sp))) return rc;
             sharded = false;
         }
+        // sharded rounds k >= 1 in one persistent launch per rank (round 0 stays on the host: its sums are the claimed sum)
+        if (k > 0 && sharded && dev_exchange && dev_rounds_apply(ctx, sp.len, 1, flags) && sp.len / 2 > collapse_len) {
+            const uint32_t want = sharded_rounds_from(sp.len, true, collapse_len);
+            uint32_t ran = 0;
+            rc = run_dev_rounds(ctx, ptrs_of(&sp), 1, 1, 0, kDevPlain, sp.len, &r, tr->t, round_polys + (size_t)k * 8,
+                                challenges ? challenges + (size_t)k * 4 : nullptr, nullptr, want, true, &ran);
+            if (rc) return rc;
+            set_len(&sp, sp.len >> ran);
+            k += ran - 1;
+            memcpy(r.l, &ctx->dev_host->challenges[ran - 1], 32);
+            continue;
+        }
         TablePtrs tp = ptrs_of(&sp);
-        if (k > 0 && !sharded && tail_applies(ctx, sp.len, 1, flags)) {   // the rest in one launch (the claimed sum is in)
-            rc = run_tail(ctx, tp, 1, 1, 0, kTailPlain, sp.len, plain ? nullptr : &r, tr->t, round_polys + (size_t)k * 8,
-                          challenges ? challenges + (size_t)k * 4 : nullptr, final_value);
+        if (k > 0 && !sharded && dev_rounds_apply(ctx, sp.len, 1, flags)) {   // the rest in one launch (the claimed sum is in)
+            rc = run_dev_rounds(ctx, tp, 1, 1, 0, kDevPlain, sp.len, plain ? nullptr : &r, tr->t, round_polys + (size_t)k * 8,
+                                challenges ? challenges + (size_t)k * 4 : nullptr, final_value);
             if (rc) return rc;
             set_len(&sp, 1);
             return ZK_OK;

@@ -18,7 +18,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "round_launch.cuh"
-#include "tail_launch.cuh"
+#include "devrounds_launch.cuh"
 #include "internal.h"
 
 using namespace zk;
@@ -139,11 +139,13 @@ static int ctx_create(zk_ctx** out, int fid, int device, void* stream, bool own_
     ZK_CUDA(cudaHostAlloc(&ctx->mail_host, sizeof(Mailbox), cudaHostAllocMapped));
     memset(ctx->mail_host, 0, sizeof(Mailbox));
     ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->mail_dev, ctx->mail_host, 0));
-    ZK_CUDA(cudaHostAlloc(&ctx->tail_host, sizeof(TailOut), cudaHostAllocMapped));
-    memset(ctx->tail_host, 0, sizeof(TailOut));
-    ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->tail_dev, ctx->tail_host, 0));
+    ZK_CUDA(cudaHostAlloc(&ctx->dev_host, sizeof(DevOut), cudaHostAllocMapped));
+    memset(ctx->dev_host, 0, sizeof(DevOut));
+    ZK_CUDA(cudaHostGetDevicePointer((void**)&ctx->dev_dev, ctx->dev_host, 0));
+    ZK_CUDA(cudaMalloc(&ctx->dev_global, sizeof(DevGlobal)));
+    ZK_CUDA(cudaMemsetAsync(ctx->dev_global, 0, sizeof(DevGlobal), ctx->stream));
     if (const char* tl = getenv("ZKB200_TAIL_LOG")) ctx->tail_log = atoi(tl);
-    if (ctx->tail_log < 0 || ctx->tail_log > kTailMaxLog) ctx->tail_log = ctx->tail_log < 0 ? 0 : kTailMaxLog;
+    if (ctx->tail_log < 0 || ctx->tail_log > kDevMaxLog) ctx->tail_log = ctx->tail_log < 0 ? 0 : kDevMaxLog;
     {
         HFe cur = ctx->field.one(), m232 = ctx->field.from_u64(1ull << 32);
         for (int i = 0; i < 8; ++i) { ctx->pow32[i] = cur; cur = ctx->field.mul(cur, m232); }
@@ -170,7 +172,8 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     cudaFree(ctx->gacc);
     cudaFree(ctx->ticket);
     cudaFreeHost(ctx->mail_host);
-    cudaFreeHost(ctx->tail_host);
+    cudaFreeHost(ctx->dev_host);
+    cudaFree(ctx->dev_global);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -181,7 +184,7 @@ extern "C" int zk_ctx_synchronize(zk_ctx* ctx) {
 }
 extern "C" int zk_ctx_set_profiling(zk_ctx* ctx, int on) { ctx->profiling = on != 0; return ZK_OK; }
 extern "C" int zk_ctx_set_tail_log(zk_ctx* ctx, int tail_log) {
-    if (tail_log < 0 || tail_log > kTailMaxLog) return fail(ctx, ZK_ERR_ARG, "tail_log must be in 0..16");
+    if (tail_log < 0 || tail_log > kDevMaxLog) return fail(ctx, ZK_ERR_ARG, "tail_log must be in 0..32");
     ctx->tail_log = tail_log;
     return ZK_OK;
 }
@@ -428,39 +431,71 @@ int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, co
     return post_launch(ctx);
 }
 
-// One block folds ~256 pairs of ONE table per microsecond, a host-driven round costs 16-23 us: the hand-over pays once
-// tables x entries fits 2^tail_log (profiles/r01b: 2^13 entries for one table, 2^11 for the three of a GKR phase).
-bool tail_applies(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags) {
+// A host-driven round costs a launch, a PCIe mailbox write, a host Keccak and the next launch (~16 us) around its kernel;
+// in the persistent launch a round costs a grid barrier and the device transcript (~8 us), and the kernel's bandwidth
+// efficiency on big tables is that of the per-round kernels (same loop body).  The hand-over pays once the rounds stop
+// being pure bandwidth: tables x entries <= 2^tail_log (profiles/r02).
+bool dev_rounds_apply(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags) {
     if ((flags & ZK_FLAG_HOST_ROUNDS) || ctx->tail_log <= 0 || len < 2) return false;
     uint64_t budget = (1ull << ctx->tail_log) / (uint64_t)(tables < 1 ? 1 : tables);
     return len <= budget;
 }
 
-int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
-             uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals) {
+int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
+                   uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals, uint32_t max_rounds, bool sharded, uint32_t* rounds_run) {
     const int NE = D + 1, T = P * D + nlin;
     if (P < 1 || D < 1 || NE > kMaxEvals || T > kMaxTables || !supported_pd((uint32_t)P, (uint32_t)D) || (nlin != 0 && !(P == 1 && D == 2 && nlin == 1)))
         return fail(ctx, ZK_ERR_ARG, kUnsupportedPdMsg);
-    if (!is_pow2(len) || len < 2 || ilog2(len) > (uint32_t)kTailMaxLog) return fail(ctx, ZK_ERR_ARG, "internal: table too long for the device tail");
-    TailArgs a;
+    if (!is_pow2(len) || len < 2 || ilog2(len) > (uint32_t)kDevMaxLog) return fail(ctx, ZK_ERR_ARG, "internal: table too long for the device-resident rounds");
+    if (sharded && (ctx->world < 2 || !ctx->peers_attached)) return fail(ctx, ZK_ERR_ARG, "internal: sharded device rounds without attached peers");
+    DevArgs a;
     memset(&a, 0, sizeof a);
     a.tp = tp;
     a.log_len = ilog2(len);
     a.pending = pending_r ? 1u : 0u;
     a.mode = (uint32_t)mode;
-    a.seq = ++ctx->tail_seq;
+    a.seq = ++ctx->dev_seq;
+    const uint32_t all_rounds = a.log_len - (a.pending ? 1u : 0u);   // rounds until one entry is left
+    a.max_rounds = max_rounds ? (max_rounds < all_rounds ? max_rounds : all_rounds) : all_rounds;
+    if (a.max_rounds > (uint32_t)kDevMaxRounds) return fail(ctx, ZK_ERR_ARG, "internal: too many rounds for one launch");
     if (pending_r) a.ft = make_fold_table(ctx->field, *pending_r);
-    static_assert(sizeof(a.interp) == sizeof(Fe) * kMaxEvals * kMaxEvals, "TailArgs::interp holds kMaxEvals^2 elements");
+    static_assert(sizeof(a.interp) == sizeof(Fe) * kMaxEvals * kMaxEvals, "DevArgs::interp holds kMaxEvals^2 elements");
     memcpy(a.interp, interp_for(ctx, D).matrix(), (size_t)NE * NE * sizeof(Fe));   // NE <= kMaxEvals checked above
     memcpy(a.pow32, ctx->pow32, sizeof a.pow32);
     tr.export_state(a.sponge.s, &a.sponge.pos);
-    a.out = ctx->tail_dev;
+    a.out = ctx->dev_dev;
+    a.g = ctx->dev_global;
+    a.world = 1;
+    if (sharded) {
+        a.world = (uint32_t)ctx->world;
+        a.rank = (uint32_t)ctx->rank;
+        a.xseq = ctx->xseq;
+        for (int q = 0; q < ctx->world; ++q) a.peers[q] = ctx->peer_slots[q];
+    }
+    if (ctx->dev_global_dirty) {   // a previous launch gave up: its barrier words are in an unknown state
+        ZK_CUDA(cudaMemsetAsync(ctx->dev_global, 0, sizeof(DevGlobal), ctx->stream));
+        ctx->dev_global_dirty = false;
+    }
+    // grid: the blocks that have work in the first round, capped by what the device keeps resident (the barrier spins)
+    const int key = (P << 8) | (D << 4) | nlin;
+    auto cap = ctx->dev_capacity.find(key);
+    if (cap == ctx->dev_capacity.end()) {
+        int blocks = 0, rc0;
+        ZK_DISPATCH_FID(ctx, rc0 = launch_dev_rounds_pd<FID>(ctx, P, D, nlin, a, 0, &blocks));
+        if (rc0) return rc0;
+        cap = ctx->dev_capacity.emplace(key, blocks).first;
+    }
+    const uint64_t work = a.pending ? len / 4 : len / 2;
+    uint64_t grid = (work + kThreads - 1) / kThreads;
+    if (grid > (uint64_t)cap->second) grid = cap->second;
+    if (ctx->grid_cap > 0 && grid > (uint64_t)ctx->grid_cap) grid = ctx->grid_cap;
+    if (grid < 1) grid = 1;
     // algorithmic bytes of the rounds the launch covers (same accounting as the per-round launches)
     double bytes = 0;
     {
         uint64_t l = len;
         bool pend = pending_r != nullptr;
-        while (pend ? l > 2 : l >= 2) {
+        for (uint32_t k = 0; k < a.max_rounds; ++k) {
             bytes += pend ? 48.0 * T * (double)l : 32.0 * T * (double)l;
             if (pend) l /= 2;
             pend = true;
@@ -468,20 +503,27 @@ int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode,
     }
     prof_begin(ctx);
     int rc;
-    ZK_DISPATCH_FID(ctx, rc = launch_tail_pd<FID>(ctx, P, D, nlin, a));
+    ZK_DISPATCH_FID(ctx, rc = launch_dev_rounds_pd<FID>(ctx, P, D, nlin, a, (int)grid, nullptr));
     prof_end(ctx, bytes);
     if (rc) return rc;
-    rc = wait_seq(ctx, &ctx->tail_host->seq, a.seq, true);
-    if (rc) return rc;
-    const TailOut* o = ctx->tail_host;
-    const uint32_t expect = a.log_len - (a.pending ? 1u : 0u);
-    if (o->rounds != expect) return fail(ctx, ZK_ERR_CUDA, "device tail ran an unexpected number of rounds");
+    rc = wait_seq(ctx, &ctx->dev_host->seq, a.seq, true);
+    if (rc) { ctx->dev_global_dirty = true; return rc; }
+    const DevOut* o = ctx->dev_host;
+    if (o->status != kDevOk) {
+        ctx->dev_global_dirty = true;
+        static const char* what[] = {"", "device rounds: timed out waiting for the blocks of a round", "device rounds: timed out waiting for the leader's challenge",
+                                     "device rounds: timed out waiting for a peer rank's partial evaluations"};
+        return fail(ctx, ZK_ERR_CUDA, what[o->status < 4 ? o->status : 1]);
+    }
+    if (o->rounds != a.max_rounds) return fail(ctx, ZK_ERR_CUDA, "device rounds ran an unexpected number of rounds");
     for (uint32_t k = 0; k < o->rounds; ++k) {
         memcpy(vals_out + (size_t)k * NE * 4, o->round_vals[k], (size_t)NE * sizeof(Fe));
         if (chal_out) memcpy(chal_out + (size_t)k * 4, &o->challenges[k], sizeof(Fe));
     }
-    if (finals) memcpy(finals, o->finals, (size_t)T * sizeof(Fe));
+    if (finals && a.max_rounds == all_rounds) memcpy(finals, o->finals, (size_t)T * sizeof(Fe));
     tr.import_state(o->sponge.s, o->sponge.pos);
+    if (sharded) ctx->xseq += o->rounds;
+    if (rounds_run) *rounds_run = o->rounds;
     return ZK_OK;
 }
 
@@ -730,9 +772,9 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
     for (uint32_t k = 0; k < n; ++k) {                                           // :37
         const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
         int rc;
-        if (tail_applies(ctx, sp->len, T, flags)) {   // rounds k..n-1 and the last fold in one launch, transcript on the device
-            rc = run_tail(ctx, tp, P, D, NL, kTailProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
-                          coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
+        if (dev_rounds_apply(ctx, sp->len, T, flags)) {   // rounds k..n-1 and the last fold in one launch, transcript on the device
+            rc = run_dev_rounds(ctx, tp, P, D, NL, kDevProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
+                                coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
             if (rc) return rc;
             set_len(sp, 1);
             return ZK_OK;
@@ -810,9 +852,9 @@ extern "C" int zk_prove_basic_device(zk_ctx* ctx, zk_table* t, uint64_t claimed_
     tr.append_be(f, claimed);                                                    // :40-41
     memcpy(claimed_sum, claimed.l, 32);
     for (uint32_t k = 0; k < n; ++k) {                                           // :46
-        if (k > 0 && tail_applies(ctx, t->len, 1, flags)) {   // rounds k..n-1 and the last fold in one launch
+        if (k > 0 && dev_rounds_apply(ctx, t->len, 1, flags)) {   // rounds k..n-1 and the last fold in one launch
             uint64_t* chal = challenges ? challenges + (size_t)k * 4 : nullptr;
-            rc = run_tail(ctx, tp, 1, 1, 0, kTailPlain, t->len, &r, tr, round_polys + (size_t)k * 8, chal, final_value);
+            rc = run_dev_rounds(ctx, tp, 1, 1, 0, kDevPlain, t->len, &r, tr, round_polys + (size_t)k * 8, chal, final_value);
             if (rc) return rc;
             t->len = 1;
             return ZK_OK;

@@ -6,7 +6,7 @@
 #include <vector>
 #include "host_field.h"
 
-namespace zk { struct Fe; struct Mailbox; struct TailOut; }
+namespace zk { struct Fe; struct Mailbox; struct DevOut; struct DevGlobal; struct PeerSlot; }
 
 struct zk_ctx {
     explicit zk_ctx(int field_id) : fid(field_id), field(field_id) {}
@@ -31,11 +31,14 @@ struct zk_ctx {
     size_t xmail_bytes = 0;
     unsigned xmail_seq = 0;
     bool exchange_pending = false;      // the last round kernel published into the shared mailbox
-    // device tail (tail.cuh): all remaining rounds in one launch once the tables hold <= 2^tail_log entries
-    zk::TailOut* tail_host = nullptr;   // mapped pinned host memory
-    zk::TailOut* tail_dev = nullptr;
-    unsigned tail_seq = 0;
-    int tail_log = 13;                  // ZKB200_TAIL_LOG / zk_ctx_set_tail_log; 0 = always host-driven rounds
+    // device-resident rounds (devrounds.cuh): all remaining rounds in one persistent launch once tables x entries <= 2^tail_log
+    zk::DevOut* dev_host = nullptr;     // mapped pinned host memory
+    zk::DevOut* dev_dev = nullptr;
+    zk::DevGlobal* dev_global = nullptr;   // device: grid accumulator, arrival / release words, the current fold table
+    bool dev_global_dirty = false;      // a launch failed: re-zero before the next one
+    unsigned dev_seq = 0;
+    int tail_log = 24;                  // ZKB200_TAIL_LOG / zk_ctx_set_tail_log; 0 = always host-driven rounds
+    std::map<int, int> dev_capacity;    // co-resident blocks of the round-loop kernel per (P, D, nlin)
     zk::HFe pow32[8];                   // Montgomery forms of 2^(32 i)
     // general scratch (evaluate / convert_to_bytes / out-of-place folds)
     void* scratch = nullptr;
@@ -58,6 +61,10 @@ struct zk_ctx {
     zk::Fe* xchg_send = nullptr;   // device, kMaxEvals elements
     zk::Fe* xchg_recv = nullptr;   // device, world * kMaxEvals elements
     zk::Fe* xchg_host = nullptr;   // pinned, world * kMaxEvals elements
+    // in-kernel exchange of the device-resident rounds: every rank's PeerSlot[2][world] array, peer-mapped (cudaIpc)
+    zk::PeerSlot* peer_slots[16] = {nullptr};   // [q]: rank q's array as mapped in this process ([rank]: our own allocation)
+    bool peers_attached = false;
+    unsigned xseq = 0;             // exchange sequence number, re-agreed by all ranks at the start of every sharded prove
 };
 
 struct zk_table {

@@ -31,6 +31,9 @@ struct zk_wide_circuit {
     std::vector<uint32_t> bits;   // bits[li] = log2(#values of layer li), li = 0..L (L = inputs)
     std::vector<WideLayer> layers;
     int device = 0;
+    uint64_t* pool_off = nullptr;   // storage of every layer's CSR arrays (the GateCsr pointers point into these)
+    uint32_t *pool_x = nullptr, *pool_y = nullptr;
+    uint8_t* pool_op = nullptr;
     // prover workspace, allocated with the circuit so a prove never calls cudaMalloc/cudaFree:
     std::vector<DevBuf> W;        // all layer values (Circuit::evaluate result), resident
     DevBuf wtab, eqa, h1, h2, Wc, half_hi, half_lo, half_hi2, half_lo2;

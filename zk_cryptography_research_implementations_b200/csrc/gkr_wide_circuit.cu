@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(kThreads) find_duplicates_kernel(const uint32_
 }
 
 // off[key + 1] += 1 per gate (off zeroed before)
-__global__ void __launch_bounds__(kThreads) histogram_kernel(const uint32_t* key, uint64_t n, u64* off) {
+__global__ void __launch_bounds__(kThreads) histogram_kernel(const uint32_t* key, uint64_t n, uint64_t n_keys, u64* off) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(off + key[i] + 1, 1ull);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (key[i] < n_keys) atomicAdd(off + key[i] + 1, 1ull);   // an out-of-range key was flagged by validate_gates_kernel: never an array position
 }
 
 // inclusive scan of `data[0..n)` in three launches: per-chunk totals, a one-block scan of the totals, the chunks again
@@ -142,9 +143,10 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(u64* data, uint64_
 
 // gate i goes to the next free place of its bucket (cursor starts as a copy of off[0..n_keys))
 __global__ void __launch_bounds__(kThreads) scatter_gates_kernel(const uint32_t* key, const uint32_t* x, const uint32_t* y, const uint8_t* op, uint64_t n,
-                                                                 u64* cursor, uint32_t* sx, uint32_t* sy, uint8_t* so) {
+                                                                 uint64_t n_keys, u64* cursor, uint32_t* sx, uint32_t* sy, uint8_t* so) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (key[i] >= n_keys) continue;
         const u64 p = atomicAdd(cursor + key[i], 1ull);
         sx[p] = x[i];
         sy[p] = y[i];
@@ -163,27 +165,20 @@ struct Staging {   // one layer's flat gate arrays on the device + scratch of th
     }
 };
 
+// `out`'s arrays are already carved out of the circuit's pools (zk_wide_circuit_create)
 int build_csr_device(zk_ctx* ctx, Staging& st, uint64_t n_keys, uint64_t n, const uint32_t* key, const uint32_t* x, const uint32_t* y, GateCsr* out) {
-    ZK_CUDA(cudaMalloc(&out->off, (n_keys + 1) * sizeof(u64)));
-    ZK_CUDA(cudaMalloc(&out->x, (n ? n : 1) * sizeof(uint32_t)));
-    ZK_CUDA(cudaMalloc(&out->y, (n ? n : 1) * sizeof(uint32_t)));
-    ZK_CUDA(cudaMalloc(&out->op, (n ? n : 1)));
     u64* off = reinterpret_cast<u64*>(out->off);
     ZK_CUDA(cudaMemsetAsync(off, 0, (n_keys + 1) * sizeof(u64), ctx->stream));
-    if (n) histogram_kernel<<<blocks_for(ctx, n), kThreads, 0, ctx->stream>>>(key, n, off);
+    if (n) histogram_kernel<<<blocks_for(ctx, n), kThreads, 0, ctx->stream>>>(key, n, n_keys, off);
     const uint64_t total = n_keys + 1, n_chunks = (total + kScanChunk - 1) / kScanChunk;
     scan_chunk_totals_kernel<<<(unsigned)n_chunks, kThreads, 0, ctx->stream>>>(off, total, st.chunk_tot);
     scan_totals_kernel<<<1, kThreads, 0, ctx->stream>>>(st.chunk_tot, n_chunks);
     scan_apply_kernel<<<(unsigned)n_chunks, kThreads, 0, ctx->stream>>>(off, total, st.chunk_tot);
     ZK_CUDA(cudaMemcpyAsync(st.cursor, off, n_keys * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (n) scatter_gates_kernel<<<blocks_for(ctx, n), kThreads, 0, ctx->stream>>>(key, x, y, st.op, n, st.cursor, out->x, out->y, out->op);
+    if (n) scatter_gates_kernel<<<blocks_for(ctx, n), kThreads, 0, ctx->stream>>>(key, x, y, st.op, n, n_keys, st.cursor, out->x, out->y, out->op);
     ctx->launches += 5;
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;
-}
-void free_csr(GateCsr* g) {
-    cudaFree(g->off); cudaFree(g->x); cudaFree(g->y); cudaFree(g->op);
-    *g = GateCsr();
 }
 }  // namespace
 
@@ -212,6 +207,37 @@ extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint
     for (uint32_t b : wc->bits) max_keys = std::max<uint64_t>(max_keys, 1ull << b);
     wc->layers.resize(n_layers);
     int rc = ZK_OK;
+    {   // the CSR arrays of all layers and orderings come out of four pools: four allocations per circuit, not 12 per layer
+        uint64_t n_off = 0, n_g = 0;
+        for (uint32_t li = 0; li < n_layers; ++li) {
+            const uint64_t n = layer_off[li + 1] - layer_off[li];
+            n_off += 2 * ((1ull << wc->bits[li + 1]) + 1) + (1ull << wc->bits[li]) + 1;
+            n_g += 3 * (n ? n : 1);
+        }
+        cudaError_t e = cudaMalloc(&wc->pool_off, n_off * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&wc->pool_x, n_g * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&wc->pool_y, n_g * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&wc->pool_op, n_g);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("cudaMalloc (circuit): ") + cudaGetErrorString(e);
+            zk_wide_circuit_free(ctx, wc);
+            return ZK_ERR_CUDA;
+        }
+        uint64_t o = 0, g = 0;
+        for (uint32_t li = 0; li < n_layers; ++li) {
+            const uint64_t n = layer_off[li + 1] - layer_off[li], cap = n ? n : 1;
+            const uint64_t keys[3] = {1ull << wc->bits[li + 1], 1ull << wc->bits[li + 1], 1ull << wc->bits[li]};
+            GateCsr* csr[3] = {&wc->layers[li].by_left, &wc->layers[li].by_right, &wc->layers[li].by_out};
+            for (int k = 0; k < 3; ++k) {
+                csr[k]->off = wc->pool_off + o;
+                csr[k]->x = wc->pool_x + g;
+                csr[k]->y = wc->pool_y + g;
+                csr[k]->op = wc->pool_op + g;
+                o += keys[k] + 1;
+                g += cap;
+            }
+        }
+    }
     {
         Staging st;
         const uint64_t cap = max_gates ? max_gates : 1;
@@ -245,13 +271,9 @@ extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint
             if (e == cudaSuccess) e = up(st.op, op + g0, n);
             if (e != cudaSuccess) { ctx->err = std::string("cudaMemcpyAsync (gates): ") + cudaGetErrorString(e); rc = ZK_ERR_CUDA; break; }
             if (n) {
-                // indices are checked BEFORE anything consumes them as an array position
+                // every index is range-checked; the builders below never use an out-of-range index as an array position
+                // (they skip it), so the verdict can be read once, after the last layer, without a sync per layer
                 validate_gates_kernel<<<blocks_for(ctx, n), kThreads, 0, ctx->stream>>>(st.left, st.right, st.out, st.op, n, n_in, n_out_valid, st.flags);
-                unsigned flags = 0;
-                cudaMemcpyAsync(&flags, st.flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream);
-                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, ZK_ERR_CUDA, "gate validation kernel failed"); break; }
-                if (flags & 1u) { rc = fail(ctx, ZK_ERR_ARG, "gate index does not fit its layer width"); break; }
-                if (flags & 2u) { rc = fail(ctx, ZK_ERR_ARG, "gate operator must be 0 (add) or 1 (mul)"); break; }
                 uint64_t slots_n = 2;
                 while (slots_n < 2 * n) slots_n <<= 1;
                 cudaMemsetAsync(st.slots, 0, slots_n * sizeof(unsigned), ctx->stream);
@@ -262,10 +284,14 @@ extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint
             if (!rc) rc = build_csr_device(ctx, st, n_in, n, st.right, st.out, st.left, &wl.by_right);
             if (!rc) rc = build_csr_device(ctx, st, n_out, n, st.out, st.left, st.right, &wl.by_out);
             if (rc) break;
+        }
+        if (rc == ZK_OK) {
             unsigned flags = 0;
             cudaMemcpyAsync(&flags, st.flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream);
-            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, ZK_ERR_CUDA, "circuit construction kernels failed"); break; }
-            if (flags & 4u) { rc = fail(ctx, ZK_ERR_ARG, "duplicate gate: the wide prover needs a duplicate-free gate list (the reference's dense wiring tables store `= one`)"); break; }
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, ZK_ERR_CUDA, "circuit construction kernels failed");
+            else if (flags & 1u) rc = fail(ctx, ZK_ERR_ARG, "gate index does not fit its layer width");
+            else if (flags & 2u) rc = fail(ctx, ZK_ERR_ARG, "gate operator must be 0 (add) or 1 (mul)");
+            else if (flags & 4u) rc = fail(ctx, ZK_ERR_ARG, "duplicate gate: the wide prover needs a duplicate-free gate list (the reference's dense wiring tables store `= one`)");
         }
     }
     if (rc) { zk_wide_circuit_free(ctx, wc); return rc; }
@@ -296,7 +322,10 @@ extern "C" void zk_wide_circuit_free(zk_ctx* ctx, zk_wide_circuit* wc) {
     if (!wc) return;
     cudaSetDevice(wc->device);
     cudaStreamSynchronize(ctx->stream);
-    for (WideLayer& wl : wc->layers) { free_csr(&wl.by_left); free_csr(&wl.by_right); free_csr(&wl.by_out); }
+    cudaFree(wc->pool_off);
+    cudaFree(wc->pool_x);
+    cudaFree(wc->pool_y);
+    cudaFree(wc->pool_op);
     delete wc;
 }
 

@@ -3,7 +3,7 @@
 #include "../../include/zk_sumcheck.h"
 #include "engine.h"
 #include "kernels.cuh"
-#include "tail.cuh"
+#include "devrounds.cuh"
 
 int fail(zk_ctx* ctx, int code, const char* msg);
 zk::FoldTable make_fold_table(const zk::HostField& f, const zk::HFe& r_mont);
@@ -23,11 +23,15 @@ int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t l
 int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own);
 int wait_seq(zk_ctx* ctx, const volatile unsigned* word, unsigned seq, bool own);
 int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, const FoldTable& ft);
-// Device tail (tail.cuh): every remaining round of a sumcheck over T = P*D + nlin tables of `len` entries in ONE
-// single-block launch, transcript included; `pending_r` (may be null) is a challenge the tables still have to be
-// folded by.  mode: kTailProduct / kTailPlain.  vals_out receives (D+1) elements per round, chal_out (may be null)
-// one; finals (may be null) the T single entries left.  The tables end with one entry each.
-bool tail_applies(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags);
-int run_tail(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
-             uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals);
+// Device-resident rounds (devrounds.cuh): the remaining rounds of a sumcheck over T = P*D + nlin tables of `len` entries
+// in ONE persistent launch, transcript included; `pending_r` (may be null) is a challenge the tables still have to be
+// folded by.  mode: kDevProduct / kDevPlain.  max_rounds == 0: run to the end (the tables end with one entry each and
+// `finals`, if not null, receives them); otherwise stop after max_rounds rounds with the last challenge left pending.
+// sharded: the tables are this rank's shard and the partial evaluations are exchanged between the ranks' kernels over
+// peer memory (comm.cu must have attached the peers).  vals_out receives (D+1) elements per round, chal_out (may be
+// null) one; *rounds_run (may be null) the number of rounds the launch ran.
+bool dev_rounds_apply(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags);
+int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
+                   uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals, uint32_t max_rounds = 0, bool sharded = false,
+                   uint32_t* rounds_run = nullptr);
 }

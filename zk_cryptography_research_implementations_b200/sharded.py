@@ -68,6 +68,16 @@ def init_comm(ctx: Context, group=None, shared_mailboxes: bool = True) -> None:
             ctx.lib.zk_comm_unlink_mailboxes(name[0].encode())
 
 
+def exchange_kind(ctx: Context) -> str:
+    """how the sharded provers exchange a round's partial evaluations on this communicator"""
+    if ctx.lib.zk_comm_world(ctx.h) < 2:
+        return "none (one rank)"
+    if ctx.lib.zk_comm_peer_exchange(ctx.h):
+        return ("in-kernel over peer memory (NVLink): each rank's persistent round-loop kernel writes its (d+1) x 32 B partial evaluations "
+                "into every peer's slot and runs the transcript itself; host mailboxes only for rounds above the hand-over size")
+    return "shared-memory mailboxes written by the round kernels, summed on the host (no per-round collective)"
+
+
 def prove_product_native(ctx: Context, sp_handle, P: int, D: int, n_global: int, claimed_sum, transcript: Transcript,
                          flags: int = 0, collapse_len: int = 1 << 12):
     coeffs = np.zeros((max(n_global, 1), D + 1, 4), dtype=np.uint64)
