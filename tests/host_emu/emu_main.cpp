@@ -178,6 +178,8 @@ struct HostExec {   // one "thread" per block; blocks (and ranks) are stepped in
     uint32_t bid_ = 0, nblocks_ = 1;
     int lane() const { return 0; }
     int warp() const { return 0; }
+    uint32_t lanes() const { return 1; }
+    unsigned long long now_ns() const { return 0; }
     void permute(uint64_t* s) const { lanes_permute(s); }
     void finalize(const uint64_t* s, uint32_t pos, uint64_t* digest) const {
         uint64_t a[25];

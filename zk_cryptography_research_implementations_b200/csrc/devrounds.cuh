@@ -45,6 +45,11 @@ struct DevOut {                                 // mapped pinned host memory
     uint32_t rounds;
     uint32_t status;                            // DevStatus
     uint32_t seq;                               // written last, after a system-scope fence
+#ifdef ZK_DEV_TIMING
+    // measurement builds only (build.py ZKB200_DEFINES=-DZK_DEV_TIMING): the leader's clock (ns) per round at
+    // [0] round start, [1] own slice computed, [2] all blocks arrived, [3] evaluations (+ peer exchange) done, [4] challenge out
+    unsigned long long t_ns[kDevMaxRounds][5];
+#endif
 };
 
 struct PeerSlot {                               // one rank's partial evaluations of one round, in the RECEIVER's memory
@@ -55,11 +60,12 @@ struct PeerSlot {                               // one rank's partial evaluation
 
 struct DevGlobal {                              // device memory, one per context; all zero between launches
     unsigned long long gacc[kMaxCols];          // grid-wide column totals of the current round
-    uint32_t arrive;                            // blocks that have contributed (cumulative over the rounds of a launch)
-    uint32_t release;                           // rounds completed by the leader in this launch
+    // the two barrier words live in cache lines of their own: the waiting blocks poll `release` while the arriving blocks'
+    // atomics go to `arrive` -- in one line the polling loads would queue up in front of the atomics
+    alignas(128) uint32_t arrive;               // blocks that have contributed (cumulative over the rounds of a launch)
+    alignas(128) uint32_t release;              // rounds completed by the leader in this launch
     uint32_t abort_;
-    uint32_t pad_;
-    FoldTable ft;                               // fold table of the latest challenge
+    alignas(128) FoldTable ft;                  // fold table of the latest challenge
 };
 
 struct DevArgs {
@@ -126,9 +132,12 @@ template <int FID> struct DevField {
     }
 };
 
-// blocks that have work when `work` items are spread over blocks of `nthreads` threads (grid-stride, block b starts at b * nthreads)
-ZK_DEV uint32_t dev_participants(uint64_t work, uint32_t nblocks, uint32_t nthreads) {
-    const uint64_t b = (work + nthreads - 1) / nthreads;
+// Work distribution: the `work` items of a round go to WARPS, and consecutive warps sit in different blocks (global warp
+// w * nblocks + b is warp w of block b), so that a small round spreads over many SMs -- one warp each -- instead of
+// filling a few of them: below ~2^15 items the round is then bound by the latency of ONE iteration, not by one SM's
+// multiplier throughput.  Block b has work iff its warp 0 has: b * lanes < work.
+ZK_DEV uint32_t dev_participants(uint64_t work, uint32_t nblocks, uint32_t lanes) {
+    const uint64_t b = (work + lanes - 1) / lanes;
     return b >= nblocks ? nblocks : (b < 1 ? 1u : (uint32_t)b);
 }
 
@@ -168,9 +177,17 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
     ZK_DEV uint64_t work_after() const { return (pending ? len / 2 : len) / 4; }   // next round's quads (it folds)
 
     // ---- sub-step 1, every participating block: (fetch the challenge,) fold + accumulate, contribute, arrive
+    ZK_DEV void stamp(int slot) {
+#ifdef ZK_DEV_TIMING
+        if (ex.bid() == 0 && ex.tid() == 0 && round < (uint32_t)kDevMaxRounds) a.out->t_ns[round][slot] = ex.now_ns();
+#else
+        (void)slot;
+#endif
+    }
     ZK_DEV bool step_compute() {
         const int tid = ex.tid(), nt = ex.nthreads();
-        np = dev_participants(work_now(), ex.nblocks(), (uint32_t)nt);
+        stamp(0);
+        np = dev_participants(work_now(), ex.nblocks(), (uint32_t)ex.lanes());
         if (ex.bid() != 0 && round > 0) {   // the leader released round - 1: its fold table is in global memory
             if (!ex.wait_release(a.g, round)) { failed = true; return false; }
             for (int i = tid; i < 64; i += nt) sh.ft.w[i >> 3][i & 7] = ex.load_word(&a.g->ft.w[i >> 3][i & 7]);
@@ -179,7 +196,7 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
         RA ra;
         ra.init();
         const uint64_t stride = (uint64_t)ex.nblocks() * nt;
-        const uint64_t first = (uint64_t)ex.bid() * nt + tid;
+        const uint64_t first = ((uint64_t)ex.warp() * ex.nblocks() + ex.bid()) * ex.lanes() + ex.lane();
         if (pending) {   // fold table_{k-1} by r_{k-1} in place and evaluate round k (fold_evals_kernel's body)
             const uint64_t q = len / 4;
             for (uint64_t j = first; j < q; j += stride) {
@@ -229,6 +246,7 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
             for (int c = tid; c < RA::NC; c += nt) ex.grid_add(&a.g->gacc[c], sh.tot[c]);
             ex.arrive(a.g);
         }
+        stamp(1);
         return true;
     }
 
@@ -241,6 +259,7 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
             for (int c = tid; c < RA::NC; c += nt) sh.tot[c] = ex.grid_take(&a.g->gacc[c]);
             ex.sync();
         }
+        stamp(2);
         for (int e = tid; e < NE; e += nt) RA::finalize(sh.evals[e], e, sh.tot);
         ex.sync();
         if (a.world > 1) {
@@ -272,6 +291,7 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
             }
             ex.sync();
         }
+        stamp(3);
         if (a.mode == kDevProduct) {   // lagrange_interpolate on 0..D, then the coefficients little-endian
             for (int i = tid; i < NE; i += nt) {
                 Fe c;
@@ -317,6 +337,7 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
             }
         }
         ex.sync();
+        stamp(4);
         return true;
     }
 
@@ -326,7 +347,7 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
         if (pending) len /= 2;
         pending = true;
         ++round;
-        if (ex.bid() == 0 && rounds_left() && dev_participants(work_now(), ex.nblocks(), (uint32_t)nt) > 1) {
+        if (ex.bid() == 0 && rounds_left() && dev_participants(work_now(), ex.nblocks(), (uint32_t)ex.lanes()) > 1) {
             for (int i = tid; i < 64; i += nt) ex.store_word(&a.g->ft.w[i >> 3][i & 7], sh.ft.w[i >> 3][i & 7]);
             ex.release(a.g, round);   // barrier + fence + the release word
         }
@@ -362,7 +383,7 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
             if (ex.bid() == 0) finish_launch(kDevOk);
             return false;
         }
-        if (ex.bid() >= dev_participants(work_now(), ex.nblocks(), (uint32_t)ex.nthreads())) return false;
+        if (ex.bid() >= dev_participants(work_now(), ex.nblocks(), (uint32_t)ex.lanes())) return false;
         bool ok = step_compute();
         if (ok && ex.bid() == 0) ok = step_post() && step_finish();
         if (!ok) {

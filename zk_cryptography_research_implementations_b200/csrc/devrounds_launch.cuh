@@ -38,6 +38,8 @@ struct DevCudaExec {
     __device__ __forceinline__ DevCudaExec(uint32_t* flag) : wk_a(kWkA[threadIdx.x & 31u]), wk_b(kWkB[threadIdx.x & 31u]), sflag(flag), fail_code(0) {}
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
     __device__ __forceinline__ int warp() const { return (int)(threadIdx.x >> 5); }
+    __device__ __forceinline__ uint32_t lanes() const { return 32u; }
+    __device__ __forceinline__ unsigned long long now_ns() const { return dev_now_ns(); }
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
     __device__ __forceinline__ uint32_t bid() const { return blockIdx.x; }
@@ -112,6 +114,7 @@ struct DevCudaExec {
             uint32_t ok = 1;
             const unsigned long long t0 = dev_now_ns();
             for (uint32_t spins = 0; ld_acquire_gpu(&g->release) < round; ++spins) {
+                __nanosleep(40);   // up to ~150 blocks poll this word: keep the L2 slice free for the leader's release
                 if ((spins & 0xffu) == 0xffu) {
                     if (ld_volatile_u32(&g->abort_) != 0 || dev_now_ns() - t0 > kDevSpinLimitNs) { ok = 0; break; }
                 }

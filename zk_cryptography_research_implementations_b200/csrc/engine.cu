@@ -486,7 +486,7 @@ int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int
         cap = ctx->dev_capacity.emplace(key, blocks).first;
     }
     const uint64_t work = a.pending ? len / 4 : len / 2;
-    uint64_t grid = (work + kThreads - 1) / kThreads;
+    uint64_t grid = (work + 31) / 32;   // the round's items go to warps, consecutive warps to different blocks (devrounds.cuh)
     if (grid > (uint64_t)cap->second) grid = cap->second;
     if (ctx->grid_cap > 0 && grid > (uint64_t)ctx->grid_cap) grid = ctx->grid_cap;
     if (grid < 1) grid = 1;
@@ -516,6 +516,18 @@ int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int
         return fail(ctx, ZK_ERR_CUDA, what[o->status < 4 ? o->status : 1]);
     }
     if (o->rounds != a.max_rounds) return fail(ctx, ZK_ERR_CUDA, "device rounds ran an unexpected number of rounds");
+#ifdef ZK_DEV_TIMING
+    if (getenv("ZKB200_DEV_TIMING")) {   // measurement builds: the leader's per-round timeline
+        fprintf(stderr, "devrounds T=%d len=2^%u pending=%u grid=%d:", T, a.log_len, a.pending, (int)grid);
+        for (uint32_t k = 0; k < o->rounds; ++k) {
+            const unsigned long long* t = o->t_ns[k];
+            const unsigned long long next = k + 1 < o->rounds ? o->t_ns[k + 1][0] : t[4];
+            fprintf(stderr, " [%u: own %.1f wait %.1f evals %.1f transcript %.1f release %.1f]", k, (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3,
+                    (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (next - t[4]) * 1e-3);
+        }
+        fprintf(stderr, "\n");
+    }
+#endif
     for (uint32_t k = 0; k < o->rounds; ++k) {
         memcpy(vals_out + (size_t)k * NE * 4, o->round_vals[k], (size_t)NE * sizeof(Fe));
         if (chal_out) memcpy(chal_out + (size_t)k * 4, &o->challenges[k], sizeof(Fe));
@@ -554,41 +566,6 @@ extern "C" int zk_mle_partial_evaluate(zk_ctx* ctx, zk_table* t, uint32_t var, c
     if (rc) return rc;
     ZK_CUDA(cudaMemcpyAsync(t->d, ctx->scratch, (size_t)half * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
     t->len = half;
-    return ZK_OK;
-}
-
-extern "C" int zk_mle_evaluate(zk_ctx* ctx, const zk_table* t, const uint64_t* values, uint32_t n_values, uint64_t out[4]) {
-    uint32_t nvars = ilog2(t->len);
-    if (n_values > nvars) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");  // fold of a 1-entry table
-    const Fe* cur = t->d;
-    uint64_t len = t->len;
-    uint32_t done = 0;
-    if (n_values > 0) {
-        int rc = ensure_scratch(ctx, (size_t)(len / 2) * sizeof(Fe));
-        if (rc) return rc;
-    }
-    while (done < n_values) {
-        uint32_t k = n_values - done >= 3 ? 3 : n_values - done;
-        FoldTables3 fts;
-        for (uint32_t i = 0; i < k; ++i) {
-            HFe rr;
-            memcpy(rr.l, values + 4 * (done + i), 32);
-            fts.t[i] = make_fold_table(ctx->field, rr);
-        }
-        uint64_t m = len >> k;
-        Fe* dst = (Fe*)ctx->scratch;
-        int grid = grid_for(ctx, m, 4);
-        if (k == 3) { ZK_DISPATCH_FID(ctx, (fold_multi_kernel<FID, 3><<<grid, kThreads, 0, ctx->stream>>>(cur, dst, m, fts))); }
-        else if (k == 2) { ZK_DISPATCH_FID(ctx, (fold_multi_kernel<FID, 2><<<grid, kThreads, 0, ctx->stream>>>(cur, dst, m, fts))); }
-        else { ZK_DISPATCH_FID(ctx, (fold_multi_kernel<FID, 1><<<grid, kThreads, 0, ctx->stream>>>(cur, dst, m, fts))); }
-        int rc = post_launch(ctx);
-        if (rc) return rc;
-        cur = dst;
-        len = m;
-        done += k;
-    }
-    ZK_CUDA(cudaMemcpyAsync(out, cur, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZK_OK;
 }
 
