@@ -40,7 +40,7 @@ enum {
     ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
     ZK_FLAG_HOST_ROUNDS = 16   /* keep every round on the host-driven path: one kernel + one host Fiat-Shamir step per
-                                  round.  Default: once tables x entries <= 2^tail_log (zk_ctx_set_tail_log, default 24)
+                                  round.  Default: once tables x entries <= 2^tail_log (zk_ctx_set_tail_log, default 20)
                                   ONE persistent launch runs all remaining rounds with the transcript on the device
                                   (transcripts/.../fiat_shamir_transcript.rs:12-43 restated in csrc/dev_transcript.cuh,
                                   the round loop in csrc/devrounds.cuh); the proof is identical either way */
@@ -70,7 +70,7 @@ int  zk_ctx_get_stats(zk_ctx *, uint64_t *launches, uint64_t *round_launches, do
  * every remaining round -- sums, fold, grid barrier, Lagrange coefficients (dense_univariate.rs:74-127), transcript absorb
  * and challenge (fiat_shamir_transcript.rs:22-43) -- on the GPU; blocks leave the loop as the tables shrink, so the last
  * rounds run on one block.  Sharded provers exchange the per-round partial evaluations between the ranks' kernels over
- * peer memory (zk_comm_peer_exchange).  Default 24 (env ZKB200_TAIL_LOG); 0 keeps every round host-driven; at most 32.
+ * peer memory (zk_comm_peer_exchange).  Default 20 (env ZKB200_TAIL_LOG); 0 keeps every round host-driven; at most 32.
  * Proofs are bit-identical for every setting. */
 int  zk_ctx_set_tail_log(zk_ctx *, int tail_log);
 int  zk_ctx_get_tail_log(const zk_ctx *);

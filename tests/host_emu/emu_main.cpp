@@ -307,6 +307,7 @@ static zk::FoldTable host_fold_table(const zk::HostField& f, const zk::HFe& r_mo
 template <int FID> static void fill_tail_consts(zk::DevArgs& a, const zk::HostField& f, int D) {
     zk::Interpolator ip(f, D);
     memcpy(a.interp, ip.matrix(), (size_t)(D + 1) * (D + 1) * 32);
+    for (int i = 0; i < (D + 1) * (D + 1); ++i) { zk::HFe pl = f.from_mont(ip.matrix()[i]); memcpy(a.interp_plain[i].v, pl.l, 32); }
     zk::HFe cur = f.one(), m232 = f.from_u64(1ull << 32);
     for (int i = 0; i < 8; ++i) { memcpy(a.pow32[i].v, cur.l, 32); cur = f.mul(cur, m232); }
 }

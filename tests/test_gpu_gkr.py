@@ -208,7 +208,7 @@ def test_wide_prover_reduction_layer_with_heavy_fan_in(zk, co, ctx_for):
         try:
             proof = gkr.prove_wide(ctx, gkr.WideCircuit(ctx, bits, layers), zk.fe_from_ints(fid, inputs))
         finally:
-            ctx.set_tail_log(24)
+            ctx.set_tail_log(20)
         _compare_wide(zk, fid, proof,
                       [c for (_, polys, _) in want.sumcheck_proofs for poly in polys for c in poly],
                       [c for (_, _, ch) in want.sumcheck_proofs for c in ch],
@@ -242,8 +242,10 @@ def test_wide_prover_limb_for_limb_against_the_gate_list_oracle(zk, co, ctx_for,
     """widths the dense oracles cannot reach (2^12, 2^16: multi-block round kernels, the row-form eq tables, the sliced
     evaluation of the reduction layer, the CSR orderings built on the GPU): every limb of the proof against
     oracle/zkoracle.c zko_gkr_prove_sparse -- gkr_protocol.rs:57-134 with add_i / mul_i evaluated from the gate list --
-    which is itself pinned to the dense restatement on reference shapes (tests/test_oracle.py).  Both eq-table forms
-    (ZKB200_EQ_ROWS) must give that proof, and both verifiers (the CUDA one and the oracle's) must accept it."""
+    which is itself pinned to the dense restatement on reference shapes (tests/test_oracle.py).  Every form of the table
+    builders -- w(.) and eq(u, .) formed per gate from their half tables (default), materialised as row-form or as
+    entry-wise outer products (ZKB200_GKR_TABLES, ZKB200_EQ_ROWS) -- must give that proof, and both verifiers (the CUDA
+    one and the oracle's) must accept it."""
     import os
     from zk_cryptography_research_implementations_b200 import gkr
     ctx = ctx_for(fid)
@@ -253,8 +255,8 @@ def test_wide_prover_limb_for_limb_against_the_gate_list_oracle(zk, co, ctx_for,
     sc = co.SparseCircuit(bits, layers)
     want = co.gkr_prove_sparse(fid, sc, inputs)
     assert co.gkr_verify_sparse(fid, sc, want, inputs)
-    for knob in ("1", "0"):
-        os.environ["ZKB200_EQ_ROWS"] = knob
+    for knobs in ({}, {"ZKB200_GKR_TABLES": "1", "ZKB200_EQ_ROWS": "1"}, {"ZKB200_GKR_TABLES": "1", "ZKB200_EQ_ROWS": "0"}):
+        os.environ.update(knobs)
         try:
             wc = gkr.WideCircuit(ctx, bits, layers)
             proof = gkr.prove_wide(ctx, wc, inputs)
@@ -262,7 +264,8 @@ def test_wide_prover_limb_for_limb_against_the_gate_list_oracle(zk, co, ctx_for,
             assert gkr.verify_wide(ctx, wc, proof, inputs)
             wc.close()
         finally:
-            del os.environ["ZKB200_EQ_ROWS"]
+            for k in knobs:
+                del os.environ[k]
 
 
 def test_wide_verifier_accepts_honest_and_rejects_tampered_proofs(zk, co, ctx_for):

@@ -49,7 +49,7 @@ def tail_logs(ctx_for):
     entries, then a single-block device launch; 24 = the whole prove in ONE persistent multi-block launch"""
     yield (13, 24)
     for fid in (0, 1, 2):
-        ctx_for(fid).set_tail_log(24)
+        ctx_for(fid).set_tail_log(20)
 
 
 @pytest.mark.parametrize("n", [20, 22])

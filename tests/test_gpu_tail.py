@@ -14,7 +14,7 @@ from test_gpu_parity import rand_table, sumpoly_handle
 pytestmark = pytest.mark.gpu
 
 TAIL_LOGS = [0, 2, 5, 13, 16, 24]
-DEFAULT_TAIL_LOG = 24
+DEFAULT_TAIL_LOG = 20
 
 
 @pytest.fixture

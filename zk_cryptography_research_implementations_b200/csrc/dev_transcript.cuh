@@ -110,7 +110,11 @@ template <class L> ZK_DEV void warp_keccak_f1600(L& lo, L& hi, const L A, const 
     const L rot = B & 31u;                        // rho mod 32
     const L swap = ~(((B >> 5) & 1u) + 0xffffffffu);   // all ones where rho >= 32: the halves trade places first
     const L lane0 = wk_lane0_mask(lo);
+#if defined(ZK_HOST_EMU)
 #pragma unroll 1
+#else
+#pragma unroll   // 24 rounds inline: the round constants become immediates and the scheduler overlaps a round's tail with the next one's head
+#endif
     for (int r = 0; r < 24; ++r) {
         // theta: column parity, then D
         L cl = lo ^ wk_shfl(lo, s1) ^ wk_shfl(lo, s2) ^ wk_shfl(lo, s3) ^ wk_shfl(lo, s4);

@@ -80,6 +80,7 @@ struct DevArgs {
     uint32_t xseq;         // sequence number of the round before this launch's first one (agreed by all ranks)
     FoldTable ft;          // fold table of the pending challenge
     Fe interp[kMaxEvals * kMaxEvals];   // inverse Vandermonde on the nodes 0..D, row-major, Montgomery form
+    Fe interp_plain[kMaxEvals * kMaxEvals];   // the same matrix as plain canonical integers (gives the coefficients' bytes directly)
     Fe pow32[8];           // Montgomery forms of 2^(32 i)
     KeccakState sponge;    // transcript state on entry
     DevOut* out;
@@ -292,18 +293,27 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
             ex.sync();
         }
         stamp(3);
-        if (a.mode == kDevProduct) {   // lagrange_interpolate on 0..D, then the coefficients little-endian
-            for (int i = tid; i < NE; i += nt) {
-                Fe c;
-                Fp<FID>::mont_mul(c, a.interp[i * NE], sh.evals[0]);
+        if (a.mode == kDevProduct) {
+            // lagrange_interpolate on 0..D as a fixed matrix: coefficient i = sum_k M[i][k] s(k), accumulated UNREDUCED with one
+            // Montgomery reduction.  2 (D+1) threads: with M in Montgomery form the reduction yields the coefficient as the
+            // proof reports it; with M as plain integers it yields the coefficient's canonical integer -- the little-endian
+            // bytes the transcript absorbs (sumcheck_gkr_protocol.rs:145-150) -- without a second pass.
+            for (int j = tid; j < 2 * NE; j += nt) {
+                const int i = j < NE ? j : j - NE;
+                const Fe* m = (j < NE ? a.interp : a.interp_plain) + i * NE;
+                uint32_t acc[17];
 #pragma unroll
-                for (int k = 1; k < NE; ++k) {
-                    Fe t;
-                    Fp<FID>::mont_mul(t, a.interp[i * NE + k], sh.evals[k]);
-                    Fp<FID>::add(c, c, t);
+                for (int k = 0; k < 17; ++k) acc[k] = 0;
+#pragma unroll
+                for (int k = 0; k < NE; ++k) Fp<FID>::mul_acc(acc, m[k], sh.evals[k]);
+                Fe c;
+                Fp<FID>::redc_wide(c, acc);
+                if (j < NE) {
+                    a.out->round_vals[round][i] = c;
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) sh.words[i][w] = (uint64_t)c.v[2 * w] | ((uint64_t)c.v[2 * w + 1] << 32);
                 }
-                a.out->round_vals[round][i] = c;
-                TF::le_words(sh.words[i], c);
             }
         } else {                       // plain sumcheck: the two half sums big-endian
             for (int i = tid; i < NE; i += nt) {

@@ -461,6 +461,10 @@ int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int
     if (pending_r) a.ft = make_fold_table(ctx->field, *pending_r);
     static_assert(sizeof(a.interp) == sizeof(Fe) * kMaxEvals * kMaxEvals, "DevArgs::interp holds kMaxEvals^2 elements");
     memcpy(a.interp, interp_for(ctx, D).matrix(), (size_t)NE * NE * sizeof(Fe));   // NE <= kMaxEvals checked above
+    for (int i = 0; i < NE * NE; ++i) {
+        const HFe plain = ctx->field.from_mont(interp_for(ctx, D).matrix()[i]);
+        memcpy(a.interp_plain[i].v, plain.l, 32);
+    }
     memcpy(a.pow32, ctx->pow32, sizeof a.pow32);
     tr.export_state(a.sponge.s, &a.sponge.pos);
     a.out = ctx->dev_dev;

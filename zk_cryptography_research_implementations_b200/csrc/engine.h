@@ -37,7 +37,7 @@ struct zk_ctx {
     zk::DevGlobal* dev_global = nullptr;   // device: grid accumulator, arrival / release words, the current fold table
     bool dev_global_dirty = false;      // a launch failed: re-zero before the next one
     unsigned dev_seq = 0;
-    int tail_log = 24;                  // ZKB200_TAIL_LOG / zk_ctx_set_tail_log; 0 = always host-driven rounds
+    int tail_log = 20;                  // ZKB200_TAIL_LOG / zk_ctx_set_tail_log; 0 = always host-driven rounds
     std::map<int, int> dev_capacity;    // co-resident blocks of the round-loop kernel per (P, D, nlin)
     zk::HFe pow32[8];                   // Montgomery forms of 2^(32 i)
     // general scratch (evaluate / convert_to_bytes / out-of-place folds)

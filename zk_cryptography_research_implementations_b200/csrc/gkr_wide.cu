@@ -182,6 +182,58 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// The same two builders with the bound `a` weights w(.) and eq(u, .) formed per gate from their half tables (eq_at) instead
+// of gathered from 2^m-entry tables: phase 1 keeps ONE random HBM gather per gate (the layer value W[right]) and pays two
+// unreduced products + one reduction for w; phase 2 has no full-width gather left at all.  The w / eq(u) tables are then
+// never built.  (ZKB200_GKR_TABLES=1 selects the table form: same proof, tests/test_gpu_gkr.py.)
+template <int FID>
+__global__ void __launch_bounds__(kThreads) phase1_fly_kernel(GateCsr g, EqHalves wq, const Fe* W, Fe* h1, Fe* h2, uint64_t nb) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += stride) {
+        Fe a1, a2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a1.v[k] = a2.v[k] = 0;
+        for (uint64_t i = g.off[b]; i < g.off[b + 1]; ++i) {
+            Fe wc = ld256(W + g.y[i]);
+            Fe wv = eq_at<FID>(wq, g.x[i]), t;
+            Fp<FID>::mont_mul(t, wv, wc);
+            if (g.op[i] == 0) {
+                Fp<FID>::add(a1, a1, wv);
+                Fp<FID>::add(a2, a2, t);
+            } else {
+                Fp<FID>::add(a1, a1, t);
+            }
+        }
+        st256(h1 + b, a1);
+        st256(h2 + b, a2);
+    }
+}
+template <int FID>
+__global__ void __launch_bounds__(kThreads)
+    phase2_fly_kernel(GateCsr g, EqHalves wq, EqHalves uq, const __grid_constant__ FoldTable Wu, Fe* A, Fe* B, uint64_t nc) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    Fe zero;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) zero.v[k] = 0;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += stride) {
+        Fe addu, mulu;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) addu.v[k] = mulu.v[k] = 0;
+        for (uint64_t i = g.off[c]; i < g.off[c + 1]; ++i) {
+            Fe wv = eq_at<FID>(wq, g.x[i]), e = eq_at<FID>(uq, g.y[i]), t;
+            Fp<FID>::mont_mul(t, wv, e);
+            if (g.op[i] == 0) Fp<FID>::add(addu, addu, t);
+            else Fp<FID>::add(mulu, mulu, t);
+        }
+        Fe a, m, bsum;
+        FoldScalar<FID>::fold(a, zero, addu, Wu);
+        FoldScalar<FID>::fold(m, zero, mulu, Wu);
+        Fp<FID>::add(bsum, addu, m);
+        st256(A + c, a);
+        st256(B + c, bsum);
+    }
+}
+
 // verifier: add_i / mul_i at the sumcheck point with `a` bound (gkr/src/utils.rs:84-135) from the gate list,
 //   add_r = sum over add gates of w(out_g) eq(u, left_g) eq(v, right_g),   mul_r likewise,
 // one thread per b = left index (by_left CSR: x = out, y = right); per-block partial sums, added on the host.
@@ -396,6 +448,9 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
 
     // ---- scratch tables
     DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
+    // ZKB200_GKR_TABLES=1: materialise w(.) and eq(u, .) as 2^m-entry tables and gather from them (the round-1 form; A/B and tests)
+    const char* tables_knob = getenv("ZKB200_GKR_TABLES");
+    const bool use_tables = tables_knob && tables_knob[0] == '1';
 
 
     HFe alpha = f.zero(), beta = f.zero();
@@ -409,14 +464,32 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         const WideLayer& wl = wc->layers[li];
         int rc;
         // ---- w(a): eq(r_a, .) at the output layer, alpha eq(r_b, .) + beta eq(r_c, .) below
-        if (li == 0) {
-            if ((rc = build_eq2(ctx, wc, ra, f.one(), nullptr, f.one(), wtab.p))) return rc;
-        } else {
-            if ((rc = build_eq2(ctx, wc, rb, alpha, &rcv, beta, wtab.p))) return rc;
+        const uint32_t ka = wc->bits[li], ka_hi = ka / 2, ka_lo = ka - ka_hi;
+        EqHalves wq{wc->half_hi.p, wc->half_lo.p, nullptr, nullptr, ka_lo};
+        if (use_tables) {
+            if (li == 0) {
+                if ((rc = build_eq2(ctx, wc, ra, f.one(), nullptr, f.one(), wtab.p))) return rc;
+            } else {
+                if ((rc = build_eq2(ctx, wc, rb, alpha, &rcv, beta, wtab.p))) return rc;
+            }
+        } else {   // only the half tables; w(out) is formed per gate
+            if (ka_lo > (uint32_t)kEqHalfBits) return fail(ctx, ZK_ERR_ARG, "layer wider than 2^30");
+            if (li == 0) {
+                if ((rc = launch_eq_halves(ctx, ra, f.one(), wc->half_hi.p, wc->half_lo.p, ka_hi, ka_lo))) return rc;
+            } else {
+                if ((rc = launch_eq_halves(ctx, rb, alpha, wc->half_hi.p, wc->half_lo.p, ka_hi, ka_lo))) return rc;
+                if ((rc = launch_eq_halves(ctx, rcv, beta, wc->half_hi2.p, wc->half_lo2.p, ka_hi, ka_lo))) return rc;
+                wq.hi2 = wc->half_hi2.p;
+                wq.lo2 = wc->half_lo2.p;
+            }
         }
         mark(1);
         // ---- phase 1 tables and sumcheck over b
-        ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nm)));
+        if (use_tables) {
+            ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nm)));
+        } else {
+            ZK_FID_SWITCH(ctx, (phase1_fly_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wq, W[li + 1].p, h1.p, h2.p, nm)));
+        }
         ctx->launches++;
         ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
         ZK_CUDA(cudaGetLastError());
@@ -441,9 +514,17 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         const HFe Wu = fin1[1];                                                                           // W(r_b)
         std::vector<HFe> u(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + m);
         // ---- phase 2 tables and sumcheck over c
-        if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
         const FoldTable Wu_ft = make_fold_table(f, Wu);
-        ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nm)));
+        if (use_tables) {
+            if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
+            ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nm)));
+        } else {
+            const uint32_t mh = m / 2, ml = m - mh;
+            if (ml > (uint32_t)kEqHalfBits) return fail(ctx, ZK_ERR_ARG, "layer wider than 2^30");
+            if ((rc = launch_eq_halves(ctx, u, f.one(), wc->half_u_hi.p, wc->half_u_lo.p, mh, ml))) return rc;
+            EqHalves uq{wc->half_u_hi.p, wc->half_u_lo.p, nullptr, nullptr, ml};
+            ZK_FID_SWITCH(ctx, (phase2_fly_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wq, uq, Wu_ft, h1.p, h2.p, nm)));
+        }
         ctx->launches += 1;
         ZK_CUDA(cudaGetLastError());
         mark(4);

@@ -42,6 +42,15 @@ __device__ __forceinline__ void st256(Fe* p, const Fe& r) {
                  "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
                  : "memory");
 }
+// cached (L1-allocating) 256-bit load, for small tables that are re-read many times (eq half tables)
+__device__ __forceinline__ Fe ld256_ca(const Fe* p) {
+    Fe r;
+    asm volatile("ld.global.ca.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                   "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
 // pull one 32-byte sector into L2 ahead of use (no register cost)
 __device__ __forceinline__ void prefetch_l2(const Fe* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // coherent (L2) read of data another block published

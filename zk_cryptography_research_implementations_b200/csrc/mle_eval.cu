@@ -52,15 +52,6 @@ inline int grid_of(const zk_ctx* ctx, uint64_t work, int bps) {
     return (int)(blocks < 1 ? 1 : blocks);
 }
 
-// cached (L1-allocating) 256-bit load for the small eq tables
-__device__ __forceinline__ Fe ld256_ca(const Fe* p) {
-    Fe r;
-    asm volatile("ld.global.ca.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-                 : "l"(p));
-    return r;
-}
-
 // what publish_round (kernels.cuh) needs: one evaluation, 17 columns
 template <int FID> struct InnerAcc {
     static constexpr int NC = 17, NE = 1;
