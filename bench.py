@@ -174,9 +174,10 @@ def run_gkr_wide(args, wl, steps=None, warmup=None):
     warmup = args.warmup if warmup is None else warmup
     depth = 16
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return None     # single-GPU workload: 704 latency-bound rounds over 128 MiB tables do not shard usefully
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        if rank != 0:
+            return None
         args.workload = "gkr"
         return run_gkr(args, WORKLOADS["gkr"])
     import torch
@@ -185,6 +186,19 @@ def run_gkr_wide(args, wl, steps=None, warmup=None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     ctx = zk.Context(field, local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    if world > 1:   # N > 1: the circuit and the input layer are replicated, every layer's phase tables and sumchecks are sharded
+        import torch.distributed as dist
+        from zk_cryptography_research_implementations_b200 import sharded
+        sharded.init_comm(ctx)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def prove():
+        return gkr.prove_wide(ctx, circuit, dev_I, sharded=world > 1, collapse_len=args.collapse_len)
     t0 = time.perf_counter()
     bits, flat = wide_circuit_arrays(w, depth)
     gen_s = time.perf_counter() - t0
@@ -196,25 +210,30 @@ def run_gkr_wide(args, wl, steps=None, warmup=None):
     I = dev_I.download()
     proof = None
     for _ in range(warmup):
-        proof = gkr.prove_wide(ctx, circuit, dev_I)
+        barrier()
+        proof = prove()
     ctx.set_profiling(True)
     ctx.reset_stats()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     times = []
     for _ in range(steps):
-        torch.cuda.synchronize()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        proof = gkr.prove_wide(ctx, circuit, dev_I)  # resident inputs -> proof on the host
+        proof = prove()                              # resident inputs -> proof on the host (every rank gets the same one)
         e1.record()
-        torch.cuda.synchronize()
+        barrier()
         times.append(e0.elapsed_time(e1))
     st = ctx.stats()
     ctx.set_profiling(False)
     ms = statistics.mean(times)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     # e2e: the reference-facing call, inputs in pinned HOST memory, proof back on the host
     e2e_ms = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         pin = C.c_void_p()
         if ctx.lib.zk_pinned_alloc(C.c_size_t(I.nbytes), C.byref(pin)) == 0:
             host_I = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint64)), shape=(I.size,)).reshape(I.shape)
@@ -231,7 +250,13 @@ def run_gkr_wide(args, wl, steps=None, warmup=None):
             assert np.array_equal(proof_e.claimed_sum, proof.claimed_sum)
             del host_I
             ctx.lib.zk_pinned_free(pin)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        barrier()
+        dev_I.free()
+        circuit.close()
+        ctx.close()
+        return None
     # after the timed region: the reference's verifier (gkr_protocol.rs:146-236) over this very proof, wiring predicates
     # evaluated from the gate list on the GPU, the input layer's W(u), W(v) by the evaluate kernels
     t0 = time.perf_counter()
@@ -250,11 +275,13 @@ def run_gkr_wide(args, wl, steps=None, warmup=None):
     coeffs = np.stack([p.coefficients for sp in proof.sumcheck_proofs for p in sp.round_univariate_polynomials])
     # algorithmic HBM bytes of one prove: per layer 2 phases x 128 x 3 tables x 2^w, plus the gate passes
     alg_bytes = depth * (2 * 128.0 * 3 * (1 << w) + 3 * 48.0 * (1 << w))
-    line = {"metric": "gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": 1, "steps": steps, "warmup": warmup,
+    line = {"metric": "gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u256 (8x u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
             "config": {"workload": "gkr_wide: " + desc, "field": fname, "depth": depth, "width_log2": w, "gates": depth << w,
                        "layer_bits": bits, "sumcheck_rounds": rounds, "prover": "sparse two-phase (csrc/gkr_wide.cu)",
+                       "sharding": ("none" if world == 1 else "circuit, layer values and transcript replicated; every layer's phase tables and "
+                                    "sumchecks sharded on the low index bits across %d ranks (zk_gkr_prove_wide_sharded)" % world),
                        "circuit_setup_s": setup_s,
                        "circuit_setup_note": "NOT inside `value`: zk_wide_circuit_create = upload of the gate lists + range / duplicate checks + the three "
                                              "CSR orderings of every layer, built on the GPU (the reference builds its wiring tables inside prove, "
@@ -271,9 +298,11 @@ def run_gkr_wide(args, wl, steps=None, warmup=None):
                     "call": "zk_gkr_prove_wide: input layer in pinned host memory -> proof on the host (the circuit's CSR lives on the GPU); "
                             "`value` is zk_gkr_prove_wide_device with the input layer already in HBM"},
             "gpu_launches": st["launches"], "clocks": clocks, "tail_log": ctx.tail_log(),
+            "exchange": None if world == 1 else ctx_exchange_name(ctx),
             "verified": verified, "verify_ms": verify_ms,
             "verified_by": "zk_gkr_verify_wide_device (gkr_protocol.rs:146-236) on the proof of the last timed step",
             "proof_digest": keccak_digest([coeffs, proof.claimed_sum, proof.wb_evaluations, proof.wc_evaluations])}
+    barrier()
     dev_I.free()
     circuit.close()
     ctx.close()
@@ -947,6 +976,7 @@ def run_extras(args):
     else:
         lg = min(32, 29 + world.bit_length())       # 2^31 at 2 ranks, 2^32 at 4 and 8 (configs[4]: 2^32 sharded over 8 GPUs)
         attempt("mle", lambda: run_mle(args, WORKLOADS["mle"], log2=lg, sweep="", steps=min(args.steps, 5), warmup=min(args.warmup, 3)))
+        attempt("gkr_wide", lambda: run_gkr_wide(args, WORKLOADS["gkr_wide"], steps=min(args.steps, 5), warmup=min(args.warmup, 2)))   # configs[3]: "on 8 x B200"
     return extras
 
 

@@ -34,9 +34,8 @@ enum {
                                   serial host Keccak.  The resulting proof does NOT match the reference or verify; real proofs
                                   pass 0.  (zk_prove_basic_sharded takes the caller's transcript instead, which carries the
                                   absorb.)  zk_gkr_prove_wide*: do not absorb the output layer (same caveat). */
-    ZK_FLAG_NO_CLAIM_ABSORB = 8, /* zk_prove_product only: do not absorb claimed_sum first (continuation of a sumcheck whose
-                                  earlier rounds ran in a previous call -- the two phases of a sparse GKR layer).  The sharded
-                                  provers refuse it (ZK_ERR_ARG). */
+    ZK_FLAG_NO_CLAIM_ABSORB = 8, /* zk_prove_product[_sharded]: do not absorb claimed_sum first (continuation of a sumcheck whose
+                                  earlier rounds ran in a previous call -- the two phases of a sparse GKR layer) */
     ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
     ZK_FLAG_HOST_ROUNDS = 16   /* keep every round on the host-driven path: one kernel + one host Fiat-Shamir step per
@@ -260,6 +259,13 @@ int  zk_prove_product_sharded(zk_ctx *, zk_sumpoly *sp, const uint64_t claimed_s
  * caller's: every rank passes an identical transcript that has already absorbed it (or deliberately has not). */
 int  zk_prove_basic_sharded(zk_ctx *, zk_table *local, zk_transcript *, uint64_t claimed_sum[4], uint64_t *round_polys,
                             uint64_t *challenges, uint64_t final_value[4], uint32_t flags, uint64_t collapse_len);
+/* gkr_protocol::prove (gkr_protocol.rs:26-143) with every layer's phase tables and sumchecks spread over the ranks.
+ * The circuit object, the input layer (`inputs`: ALL 2^layer_bits[n_layers] values) and the transcript are replicated on every
+ * rank; rank q builds and proves the wires whose low index bits are q; every rank returns the same proof, equal to
+ * zk_gkr_prove_wide's.  Layers with fewer than two wires per rank run unsharded on every rank.  Outputs as zk_gkr_prove_wide. */
+int  zk_gkr_prove_wide_sharded(zk_ctx *, const zk_wide_circuit *, const zk_table *inputs, uint64_t *output,
+                               uint64_t *claimed_sum, uint64_t *layer_claims, uint64_t *coeffs, uint64_t *challenges,
+                               uint64_t *wb, uint64_t *wc, uint32_t flags, uint64_t collapse_len);
 /* MultilinearPolynomial::evaluate over a sharded table (values: all log2(global length) challenges) */
 int  zk_mle_evaluate_sharded(zk_ctx *, const zk_table *local, const uint64_t *values, uint32_t n_values, uint64_t out[4]);
 

@@ -242,10 +242,9 @@ def test_wide_prover_limb_for_limb_against_the_gate_list_oracle(zk, co, ctx_for,
     """widths the dense oracles cannot reach (2^12, 2^16: multi-block round kernels, the row-form eq tables, the sliced
     evaluation of the reduction layer, the CSR orderings built on the GPU): every limb of the proof against
     oracle/zkoracle.c zko_gkr_prove_sparse -- gkr_protocol.rs:57-134 with add_i / mul_i evaluated from the gate list --
-    which is itself pinned to the dense restatement on reference shapes (tests/test_oracle.py).  Every form of the table
-    builders -- w(.) and eq(u, .) formed per gate from their half tables (default), materialised as row-form or as
-    entry-wise outer products (ZKB200_GKR_TABLES, ZKB200_EQ_ROWS) -- must give that proof, and both verifiers (the CUDA
-    one and the oracle's) must accept it."""
+    which is itself pinned to the dense restatement on reference shapes (tests/test_oracle.py).  Both eq-table forms
+    (row-form / entry-wise outer products, ZKB200_EQ_ROWS) must give that proof, and both verifiers (the CUDA one and the
+    oracle's) must accept it."""
     import os
     from zk_cryptography_research_implementations_b200 import gkr
     ctx = ctx_for(fid)
@@ -255,7 +254,7 @@ def test_wide_prover_limb_for_limb_against_the_gate_list_oracle(zk, co, ctx_for,
     sc = co.SparseCircuit(bits, layers)
     want = co.gkr_prove_sparse(fid, sc, inputs)
     assert co.gkr_verify_sparse(fid, sc, want, inputs)
-    for knobs in ({}, {"ZKB200_GKR_TABLES": "1", "ZKB200_EQ_ROWS": "1"}, {"ZKB200_GKR_TABLES": "1", "ZKB200_EQ_ROWS": "0"}):
+    for knobs in ({"ZKB200_EQ_ROWS": "1"}, {"ZKB200_EQ_ROWS": "0"}):
         os.environ.update(knobs)
         try:
             wc = gkr.WideCircuit(ctx, bits, layers)

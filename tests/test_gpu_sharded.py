@@ -99,6 +99,33 @@ def _worker(rank, world, port, q):
                 if not same:
                     notes.append("plain (n,collapse)=%s flags=%d differs from the oracle" % ((n, collapse), flags))
                 ok &= same
+        # GKR with every layer's phase tables and sumchecks spread over the ranks (gkr_protocol.rs:26-143): every
+        # rank must return the gate-list oracle's proof, limb for limb, on every exchange path
+        from zk_cryptography_research_implementations_b200 import gkr
+        for (w, depth, collapse) in [(10, 3, 16), (13, 3, 256)]:
+            rng = np.random.default_rng(40 + w)
+            n = 1 << w
+            g = np.arange(n, dtype=np.int64)
+            layers = [np.stack([g, rng.integers(0, n, size=n), g & 1, rng.integers(0, 2, size=n)], axis=1)]
+            for _ in range(depth - 1):
+                layers.append(np.stack([rng.integers(0, n, size=n), rng.integers(0, n, size=n), g, rng.integers(0, 2, size=n)], axis=1))
+            bits = [1] + [w] * depth
+            dev_in = ctx.generate(9, 0, n)
+            inputs = dev_in.download()
+            sc = co.SparseCircuit(bits, layers)
+            want = co.gkr_prove_sparse(fid, sc, inputs)
+            wc = gkr.WideCircuit(ctx, bits, layers)
+            for flags in (0, 16, 4):
+                proof = gkr.prove_wide(ctx, wc, dev_in, flags=flags, sharded=True, collapse_len=collapse)
+                got = np.concatenate([np.stack([p_.coefficients for p_ in sp_.round_univariate_polynomials]) for sp_ in proof.sumcheck_proofs])
+                same = (np.array_equal(got, want.coeffs[: got.shape[0]]) and np.array_equal(proof.claimed_sum, want.claimed_sum)
+                        and np.array_equal(proof.wb_evaluations, want.wb[: depth - 1]) and np.array_equal(proof.wc_evaluations, want.wc[: depth - 1])
+                        and np.array_equal(np.concatenate([sp_.random_challenges for sp_ in proof.sumcheck_proofs]), want.challenges[: got.shape[0]]))
+                if not same:
+                    notes.append("sharded GKR w=%d flags=%d differs from the oracle" % (w, flags))
+                ok &= same
+                ok &= bool(gkr.verify_wide(ctx, wc, proof, dev_in))
+            wc.close()
         q.put((rank, bool(ok), peer, notes))
     except Exception as e:  # pragma: no cover
         import traceback

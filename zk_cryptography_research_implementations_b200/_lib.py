@@ -102,6 +102,7 @@ SIGNATURES = {
     "zk_comm_world": (C.c_int, [vp]),
     "zk_prove_product_sharded": (C.c_int, [vp, vp, u64p, vp, u64p, u64p, u64p, C.c_uint32, C.c_uint64]),
     "zk_prove_basic_sharded": (C.c_int, [vp, vp, vp, u64p, u64p, u64p, u64p, C.c_uint32, C.c_uint64]),
+    "zk_gkr_prove_wide_sharded": (C.c_int, [vp, vp, vp, u64p, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint32, C.c_uint64]),
     "zk_mle_evaluate_sharded": (C.c_int, [vp, vp, u64p, C.c_uint32, u64p]),
     "zk_arith_probe": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

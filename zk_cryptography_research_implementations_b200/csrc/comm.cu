@@ -326,15 +326,14 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
     if (ctx->world == 1) return zk_prove_product(ctx, sp, claimed_sum, tr, coeffs_out, challenges_out, final_values, flags);
     if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_ARG, "zk_comm_init has not been called");
     if (!is_pow2(sp->len)) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
-    if (flags & ZK_FLAG_NO_CLAIM_ABSORB) return fail(ctx, ZK_ERR_ARG, "ZK_FLAG_NO_CLAIM_ABSORB is not supported by the sharded prover");
     if (collapse_len < 1) collapse_len = 1;
     const HostField& f = ctx->field;
-    const int D = sp->D, P = sp->P, NE = D + 1, G = ctx->world;
+    const int D = sp->D, P = sp->P, NE = D + 1, G = ctx->world, NL = (int)sp->nlin, T = P * D + NL;
     const uint32_t n = ilog2(sp->len) + ilog2((uint64_t)G);
     const Interpolator& ip = interp_for(ctx, D);
     HFe claim;
     memcpy(claim.l, claimed_sum, 32);
-    tr->t.append_be(f, claim);
+    if (!(flags & ZK_FLAG_NO_CLAIM_ABSORB)) tr->t.append_be(f, claim);
     HFe evals[kMaxEvals], coeffs[kMaxEvals], r = f.zero(), running = claim;
     bool sharded = true;
     const bool dev_exchange = ctx->peers_attached && !(flags & (ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_HOST_ROUNDS));
@@ -348,10 +347,10 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
         bool need_plain_evals = (k == 0);
         // the remaining SHARDED rounds in one persistent launch per rank: partial evaluations go from kernel to kernel
         // over peer memory, every rank runs the transcript on its GPU (devrounds.cuh); the collapse follows on the host
-        if (sharded && dev_exchange && dev_rounds_apply(ctx, sp->len, P * D, flags) && (k == 0 ? sp->len > collapse_len : sp->len / 2 > collapse_len)) {
+        if (sharded && dev_exchange && dev_rounds_apply(ctx, sp->len, T, flags) && (k == 0 ? sp->len > collapse_len : sp->len / 2 > collapse_len)) {
             const uint32_t want = sharded_rounds_from(sp->len, k > 0, collapse_len);
             uint32_t ran = 0;
-            rc = run_dev_rounds(ctx, ptrs_of(sp), P, D, 0, kDevProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
+            rc = run_dev_rounds(ctx, ptrs_of(sp), P, D, NL, kDevProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
                                 coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, nullptr, want, true, &ran);
             if (rc) return rc;
             // the tables were folded by every challenge but the last one
@@ -364,7 +363,7 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
         }
         if (k > 0 && sharded && sp->len / 2 <= collapse_len) {
             // fold by r_{k-1} locally, then gather: the remaining rounds run on the full table
-            rc = launch_fold0(ctx, ptrs_of(sp), P * D, sp->len, make_fold_table(f, r));
+            rc = launch_fold0(ctx, ptrs_of(sp), T, sp->len, make_fold_table(f, r));
             if (rc) return rc;
             set_len(sp, sp->len / 2);
             rc = collapse(ctx, sp);
@@ -378,8 +377,8 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
             sharded = false;
         }
         TablePtrs tp = ptrs_of(sp);
-        if (!sharded && dev_rounds_apply(ctx, sp->len, P * D, flags)) {   // collapsed and small: the rest in one launch per rank
-            rc = run_dev_rounds(ctx, tp, P, D, 0, kDevProduct, sp->len, need_plain_evals ? nullptr : &r, tr->t,
+        if (!sharded && dev_rounds_apply(ctx, sp->len, T, flags)) {   // collapsed and small: the rest in one launch per rank
+            rc = run_dev_rounds(ctx, tp, P, D, NL, kDevProduct, sp->len, need_plain_evals ? nullptr : &r, tr->t,
                                 coeffs_out + (size_t)k * NE * 4, challenges_out + (size_t)k * 4, final_values);
             if (rc) return rc;
             set_len(sp, 1);
@@ -387,9 +386,9 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
         }
         const bool shared = sharded && ctx->xmail_host != nullptr && !(flags & ZK_FLAG_NCCL_EXCHANGE);
         if (need_plain_evals) {
-            rc = launch_round_evals(ctx, tp, P, D, sp->len, shared);
+            rc = launch_round_evals(ctx, tp, P, D, sp->len, shared, NL);
         } else {
-            rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1, shared);
+            rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1, shared, NL);
             set_len(sp, sp->len / 2);
         }
         if (rc) return rc;
@@ -407,11 +406,11 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
         memcpy(challenges_out + (size_t)k * 4, r.l, 32);
     }
     if (sharded) return fail(ctx, ZK_ERR_ARG, "internal: tables still sharded after the last round");
-    int rc = launch_fold0(ctx, ptrs_of(sp), P * D, sp->len, make_fold_table(f, r));
+    int rc = launch_fold0(ctx, ptrs_of(sp), T, sp->len, make_fold_table(f, r));
     if (rc) return rc;
     set_len(sp, sp->len / 2);
     if (final_values) {
-        for (int t = 0; t < P * D; ++t)
+        for (int t = 0; t < T; ++t)
             ZK_CUDA(cudaMemcpyAsync(final_values + 4 * t, sp->tabs[t]->d, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
     }
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -55,26 +55,4 @@ __global__ void __launch_bounds__(kThreads) eq_outer2_kernel(Fe* out, const Fe* 
     }
 }
 
-// eq tables that are never materialised: s1 eq(r1, idx) [+ s2 eq(r2, idx)] from the half tables, per use.  The half
-// tables (<= 2^15 entries each) stay in L1 / L2; a full-width table would be a random 32-byte gather from HBM per use.
-struct EqHalves {
-    const Fe *hi1, *lo1, *hi2, *lo2;   // hi2 == nullptr: one term
-    uint32_t lo_bits;
-};
-template <int FID> __device__ __forceinline__ Fe eq_at(const EqHalves& q, uint32_t idx) {
-    const uint32_t h = idx >> q.lo_bits, l = idx & ((1u << q.lo_bits) - 1u);
-    Fe r;
-    if (q.hi2 == nullptr) {
-        Fp<FID>::mont_mul(r, ld256_ca(q.hi1 + h), ld256_ca(q.lo1 + l));
-    } else {   // two unreduced products, ONE Montgomery reduction
-        uint32_t acc[17];
-#pragma unroll
-        for (int k = 0; k < 17; ++k) acc[k] = 0;
-        Fp<FID>::mul_acc(acc, ld256_ca(q.hi1 + h), ld256_ca(q.lo1 + l));
-        Fp<FID>::mul_acc(acc, ld256_ca(q.hi2 + h), ld256_ca(q.lo2 + l));
-        Fp<FID>::redc_wide(r, acc);
-    }
-    return r;
-}
-
 }  // namespace zk

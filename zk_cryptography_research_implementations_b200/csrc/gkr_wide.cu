@@ -132,11 +132,13 @@ template <int FID> __global__ void __launch_bounds__(kThreads) sum_slices_kernel
     }
 }
 
-// phase-1 tables: one thread per b
+// phase-1 tables: one thread per b.  (first, step): the b this launch covers are first + j * step, j < nb, written to
+// position j -- a rank's shard of the phase tables (low index bits, comm.cu) or, with (0, 1), the whole table.
 template <int FID>
-__global__ void __launch_bounds__(kThreads) phase1_kernel(GateCsr g, const Fe* w, const Fe* W, Fe* h1, Fe* h2, uint64_t nb) {
+__global__ void __launch_bounds__(kThreads) phase1_kernel(GateCsr g, const Fe* w, const Fe* W, Fe* h1, Fe* h2, uint64_t nb, uint64_t first, uint64_t step) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += stride) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nb; j += stride) {
+        const uint64_t b = first + j * step;
         Fe a1, a2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) a1.v[k] = a2.v[k] = 0;
@@ -150,20 +152,26 @@ __global__ void __launch_bounds__(kThreads) phase1_kernel(GateCsr g, const Fe* w
                 Fp<FID>::add(a1, a1, t);
             }
         }
-        st256(h1 + b, a1);
-        st256(h2 + b, a2);
+        st256(h1 + j, a1);
+        st256(h2 + j, a2);
     }
+}
+// out[j] = in[first + j * step]: a rank's shard of a replicated table
+__global__ void __launch_bounds__(kThreads) strided_copy_kernel(const Fe* in, Fe* out, uint64_t n, uint64_t first, uint64_t step) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) st256(out + j, ld256(in + first + j * step));
 }
 
 // phase-2 tables: one thread per c
 template <int FID>
 __global__ void __launch_bounds__(kThreads)
-    phase2_kernel(GateCsr g, const Fe* w, const Fe* equ, const __grid_constant__ FoldTable Wu, Fe* A, Fe* B, uint64_t nc) {
+    phase2_kernel(GateCsr g, const Fe* w, const Fe* equ, const __grid_constant__ FoldTable Wu, Fe* A, Fe* B, uint64_t nc, uint64_t first, uint64_t step) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     Fe zero;
 #pragma unroll
     for (int k = 0; k < 8; ++k) zero.v[k] = 0;
-    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += stride) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += stride) {
+        const uint64_t c = first + j * step;
         Fe addu, mulu;
 #pragma unroll
         for (int k = 0; k < 8; ++k) addu.v[k] = mulu.v[k] = 0;
@@ -177,60 +185,8 @@ __global__ void __launch_bounds__(kThreads)
         FoldScalar<FID>::fold(a, zero, addu, Wu);   // W(u) * add_u(c): a product by a per-launch constant (0 + W(u) (x - 0))
         FoldScalar<FID>::fold(m, zero, mulu, Wu);
         Fp<FID>::add(bsum, addu, m);
-        st256(A + c, a);
-        st256(B + c, bsum);
-    }
-}
-
-// The same two builders with the bound `a` weights w(.) and eq(u, .) formed per gate from their half tables (eq_at) instead
-// of gathered from 2^m-entry tables: phase 1 keeps ONE random HBM gather per gate (the layer value W[right]) and pays two
-// unreduced products + one reduction for w; phase 2 has no full-width gather left at all.  The w / eq(u) tables are then
-// never built.  (ZKB200_GKR_TABLES=1 selects the table form: same proof, tests/test_gpu_gkr.py.)
-template <int FID>
-__global__ void __launch_bounds__(kThreads) phase1_fly_kernel(GateCsr g, EqHalves wq, const Fe* W, Fe* h1, Fe* h2, uint64_t nb) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += stride) {
-        Fe a1, a2;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a1.v[k] = a2.v[k] = 0;
-        for (uint64_t i = g.off[b]; i < g.off[b + 1]; ++i) {
-            Fe wc = ld256(W + g.y[i]);
-            Fe wv = eq_at<FID>(wq, g.x[i]), t;
-            Fp<FID>::mont_mul(t, wv, wc);
-            if (g.op[i] == 0) {
-                Fp<FID>::add(a1, a1, wv);
-                Fp<FID>::add(a2, a2, t);
-            } else {
-                Fp<FID>::add(a1, a1, t);
-            }
-        }
-        st256(h1 + b, a1);
-        st256(h2 + b, a2);
-    }
-}
-template <int FID>
-__global__ void __launch_bounds__(kThreads)
-    phase2_fly_kernel(GateCsr g, EqHalves wq, EqHalves uq, const __grid_constant__ FoldTable Wu, Fe* A, Fe* B, uint64_t nc) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    Fe zero;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) zero.v[k] = 0;
-    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += stride) {
-        Fe addu, mulu;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) addu.v[k] = mulu.v[k] = 0;
-        for (uint64_t i = g.off[c]; i < g.off[c + 1]; ++i) {
-            Fe wv = eq_at<FID>(wq, g.x[i]), e = eq_at<FID>(uq, g.y[i]), t;
-            Fp<FID>::mont_mul(t, wv, e);
-            if (g.op[i] == 0) Fp<FID>::add(addu, addu, t);
-            else Fp<FID>::add(mulu, mulu, t);
-        }
-        Fe a, m, bsum;
-        FoldScalar<FID>::fold(a, zero, addu, Wu);
-        FoldScalar<FID>::fold(m, zero, mulu, Wu);
-        Fp<FID>::add(bsum, addu, m);
-        st256(A + c, a);
-        st256(B + c, bsum);
+        st256(A + j, a);
+        st256(B + j, bsum);
     }
 }
 
@@ -367,7 +323,8 @@ int build_eq2(zk_ctx* ctx, zk_wide_circuit* wc, const std::vector<HFe>& r1, cons
 // is a serial host Keccak over 32 * 2^bits[0] bytes).
 static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* inputs, const Fe* device_inputs, uint64_t n_inputs,
                               uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
-                              uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags);
+                              uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags, bool sharded = false,
+                              uint64_t collapse_len = 1 << 12);
 
 extern "C" int zk_gkr_prove_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const uint64_t* inputs, uint64_t n_inputs,
                                  uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
@@ -383,9 +340,23 @@ extern "C" int zk_gkr_prove_wide_device(zk_ctx* ctx, const zk_wide_circuit* wc, 
                                wb_out, wc_out, flags);
 }
 
+// gkr_protocol::prove with every layer sumcheck spread over the ranks of the communicator ("GKR: shard the
+// 2^m phase tables the same way").  The circuit, its layer values and the transcript are REPLICATED -- every rank holds the
+// circuit object, evaluates all layers and runs the same Fiat-Shamir steps -- while the expensive part is split: rank q
+// builds the phase tables h1, h2 / A, B only for the wires b (resp. c) whose low index bits are q (1/G of the gate list's
+// buckets, the random gathers go to the replicated w(.), eq(u, .) and W tables), takes its shard of W, and the phase's
+// sumcheck runs as zk_prove_product_sharded (partial evaluations exchanged per round, collapse, redundant tail).
+// Every rank returns the same proof.  `inputs`: the whole input layer on every rank.
+extern "C" int zk_gkr_prove_wide_sharded(zk_ctx* ctx, const zk_wide_circuit* wc, const zk_table* inputs, uint64_t* output,
+                                         uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out, uint64_t* challenges_out,
+                                         uint64_t* wb_out, uint64_t* wc_out, uint32_t flags, uint64_t collapse_len) {
+    return gkr_prove_wide_impl(ctx, wc, nullptr, inputs->d, inputs->len, output, claimed_sum, layer_claims, coeffs_out, challenges_out,
+                               wb_out, wc_out, flags, zk_comm_world(ctx) > 1, collapse_len ? collapse_len : 1);
+}
+
 static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* inputs, const Fe* device_inputs, uint64_t n_inputs,
                               uint64_t* output, uint64_t* claimed_sum, uint64_t* layer_claims, uint64_t* coeffs_out,
-                              uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags) {
+                              uint64_t* challenges_out, uint64_t* wb_out, uint64_t* wc_out, uint32_t flags, bool sharded, uint64_t collapse_len) {
     zk_wide_circuit* wc = const_cast<zk_wide_circuit*>(wc_);   // the workspace inside the circuit object is mutable
     // ZKB200_TRACE=1: coarse host-side timeline of one prove (stream synchronised at each mark)
     const bool trace = getenv("ZKB200_TRACE") != nullptr;
@@ -446,11 +417,10 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
     }
     HFe claim = w0[0];
 
+    // how the layer sumchecks run their rounds / exchange their partial sums is the caller's choice; the proof does not depend on it
+    const uint32_t sc_flags = flags & (ZK_FLAG_HOST_ROUNDS | ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_DIRECT_S1);
     // ---- scratch tables
     DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
-    // ZKB200_GKR_TABLES=1: materialise w(.) and eq(u, .) as 2^m-entry tables and gather from them (the round-1 form; A/B and tests)
-    const char* tables_knob = getenv("ZKB200_GKR_TABLES");
-    const bool use_tables = tables_knob && tables_knob[0] == '1';
 
 
     HFe alpha = f.zero(), beta = f.zero();
@@ -464,43 +434,33 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         const WideLayer& wl = wc->layers[li];
         int rc;
         // ---- w(a): eq(r_a, .) at the output layer, alpha eq(r_b, .) + beta eq(r_c, .) below
-        const uint32_t ka = wc->bits[li], ka_hi = ka / 2, ka_lo = ka - ka_hi;
-        EqHalves wq{wc->half_hi.p, wc->half_lo.p, nullptr, nullptr, ka_lo};
-        if (use_tables) {
-            if (li == 0) {
-                if ((rc = build_eq2(ctx, wc, ra, f.one(), nullptr, f.one(), wtab.p))) return rc;
-            } else {
-                if ((rc = build_eq2(ctx, wc, rb, alpha, &rcv, beta, wtab.p))) return rc;
-            }
-        } else {   // only the half tables; w(out) is formed per gate
-            if (ka_lo > (uint32_t)kEqHalfBits) return fail(ctx, ZK_ERR_ARG, "layer wider than 2^30");
-            if (li == 0) {
-                if ((rc = launch_eq_halves(ctx, ra, f.one(), wc->half_hi.p, wc->half_lo.p, ka_hi, ka_lo))) return rc;
-            } else {
-                if ((rc = launch_eq_halves(ctx, rb, alpha, wc->half_hi.p, wc->half_lo.p, ka_hi, ka_lo))) return rc;
-                if ((rc = launch_eq_halves(ctx, rcv, beta, wc->half_hi2.p, wc->half_lo2.p, ka_hi, ka_lo))) return rc;
-                wq.hi2 = wc->half_hi2.p;
-                wq.lo2 = wc->half_lo2.p;
-            }
+        if (li == 0) {
+            if ((rc = build_eq2(ctx, wc, ra, f.one(), nullptr, f.one(), wtab.p))) return rc;
+        } else {
+            if ((rc = build_eq2(ctx, wc, rb, alpha, &rcv, beta, wtab.p))) return rc;
         }
         mark(1);
+        // a layer is spread over the ranks when every rank gets at least two wires; narrower layers run redundantly on all
+        const uint64_t G = (sharded && nm >= 2 * (uint64_t)ctx->world) ? (uint64_t)ctx->world : 1, q = G > 1 ? (uint64_t)ctx->rank : 0;
+        const uint64_t nl = nm / G;   // this rank's wires: b = q + j G
         // ---- phase 1 tables and sumcheck over b
-        if (use_tables) {
-            ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nm)));
-        } else {
-            ZK_FID_SWITCH(ctx, (phase1_fly_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wq, W[li + 1].p, h1.p, h2.p, nm)));
-        }
+        ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nl, q, G)));
         ctx->launches++;
-        ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (G > 1) {
+            strided_copy_kernel<<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(W[li + 1].p, Wc.p, nl, q, G);
+            ctx->launches++;
+        } else {
+            ZK_CUDA(cudaMemcpyAsync(Wc.p, W[li + 1].p, nm * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         ZK_CUDA(cudaGetLastError());
         // h1*W + h2*1: one product plus one LINEAR table -- the all-ones factor is never materialised
         zk_table t_h1, t_W, t_h2;
         zk_table* tabs1[3] = {&t_h1, &t_W, &t_h2};
         Fe* ptr1[3] = {h1.p, Wc.p, h2.p};
-        for (int i = 0; i < 3; ++i) { tabs1[i]->d = ptr1[i]; tabs1[i]->len = tabs1[i]->cap = nm; tabs1[i]->owned = false; }
+        for (int i = 0; i < 3; ++i) { tabs1[i]->d = ptr1[i]; tabs1[i]->len = nl; tabs1[i]->cap = nm; tabs1[i]->owned = false; }
         mark(2);
         zk_sumpoly sp1;
-        sp1.P = 1; sp1.D = 2; sp1.nlin = 1; sp1.len = nm;
+        sp1.P = 1; sp1.D = 2; sp1.nlin = 1; sp1.len = nl;
         sp1.tabs.assign(tabs1, tabs1 + 3);
         memcpy(layer_claims + 4 * li, claim.l, 32);
         zk_transcript wrap;
@@ -508,37 +468,37 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         uint64_t* chal = challenges_out + 4 * round_off;
         uint64_t* coef = coeffs_out + 12 * round_off;
         HFe fin1[4], fin2[4];
-        rc = zk_prove_product(ctx, &sp1, claim.l, &wrap, coef, chal, fin1[0].l, 0);                      // rounds 0..m-1
+        if (G > 1) rc = zk_prove_product_sharded(ctx, &sp1, claim.l, &wrap, coef, chal, fin1[0].l, sc_flags, collapse_len);
+        else rc = zk_prove_product(ctx, &sp1, claim.l, &wrap, coef, chal, fin1[0].l, sc_flags);          // rounds 0..m-1
         if (rc) return rc;
         mark(3);
         const HFe Wu = fin1[1];                                                                           // W(r_b)
         std::vector<HFe> u(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + m);
         // ---- phase 2 tables and sumcheck over c
+        if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
         const FoldTable Wu_ft = make_fold_table(f, Wu);
-        if (use_tables) {
-            if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
-            ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nm)));
-        } else {
-            const uint32_t mh = m / 2, ml = m - mh;
-            if (ml > (uint32_t)kEqHalfBits) return fail(ctx, ZK_ERR_ARG, "layer wider than 2^30");
-            if ((rc = launch_eq_halves(ctx, u, f.one(), wc->half_u_hi.p, wc->half_u_lo.p, mh, ml))) return rc;
-            EqHalves uq{wc->half_u_hi.p, wc->half_u_lo.p, nullptr, nullptr, ml};
-            ZK_FID_SWITCH(ctx, (phase2_fly_kernel<FID><<<grid_of(ctx, nm, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wq, uq, Wu_ft, h1.p, h2.p, nm)));
-        }
+        ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nl, q, G)));
         ctx->launches += 1;
         ZK_CUDA(cudaGetLastError());
         mark(4);
-        for (int i = 0; i < 3; ++i) { tabs1[i]->len = nm; }
-        // this sumcheck is the last reader of the layer's values (the next layer works on W[li + 2]): fold them in place
-        // instead of copying 2^m elements into the scratch table first
-        t_W.d = W[li + 1].p;
+        for (int i = 0; i < 3; ++i) { tabs1[i]->len = nl; }
+        if (G > 1) {   // this rank's shard of the layer values, again (phase 1 folded the first copy away)
+            strided_copy_kernel<<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(W[li + 1].p, Wc.p, nl, q, G);
+            ctx->launches++;
+            ZK_CUDA(cudaGetLastError());
+        } else {
+            // this sumcheck is the last reader of the layer's values (the next layer works on W[li + 2]): fold them in place
+            // instead of copying 2^m elements into the scratch table first
+            t_W.d = W[li + 1].p;
+        }
         zk_table* tabs2[3] = {&t_h2, &t_W, &t_h1};                                                       // B*W + A*1 (A in h1, B in h2)
         zk_sumpoly sp2;
-        sp2.P = 1; sp2.D = 2; sp2.nlin = 1; sp2.len = nm;
+        sp2.P = 1; sp2.D = 2; sp2.nlin = 1; sp2.len = nl;
         sp2.tabs.assign(tabs2, tabs2 + 3);
         // the running claim entering round m is s_{m-1}(r_{m-1}); it is not absorbed again (one 2m-round sumcheck)
         HFe mid = f.horner(reinterpret_cast<HFe*>(coef + 12 * (m - 1)), 3, u[m - 1]);
-        rc = zk_prove_product(ctx, &sp2, mid.l, &wrap, coef + 12 * m, chal + 4 * m, fin2[0].l, ZK_FLAG_NO_CLAIM_ABSORB);   // rounds m..2m-1
+        if (G > 1) rc = zk_prove_product_sharded(ctx, &sp2, mid.l, &wrap, coef + 12 * m, chal + 4 * m, fin2[0].l, sc_flags | ZK_FLAG_NO_CLAIM_ABSORB, collapse_len);
+        else rc = zk_prove_product(ctx, &sp2, mid.l, &wrap, coef + 12 * m, chal + 4 * m, fin2[0].l, sc_flags | ZK_FLAG_NO_CLAIM_ABSORB);   // rounds m..2m-1
         if (rc) return rc;
         tr = wrap.t;
         mark(5);

@@ -36,6 +36,6 @@ struct zk_wide_circuit {
     uint8_t* pool_op = nullptr;
     // prover workspace, allocated with the circuit so a prove never calls cudaMalloc/cudaFree:
     std::vector<DevBuf> W;        // all layer values (Circuit::evaluate result), resident
-    DevBuf wtab, eqa, h1, h2, Wc, half_hi, half_lo, half_hi2, half_lo2, half_u_hi, half_u_lo;
+    DevBuf wtab, eqa, h1, h2, Wc, half_hi, half_lo, half_hi2, half_lo2;
 };
 

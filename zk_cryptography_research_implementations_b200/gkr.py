@@ -123,8 +123,11 @@ class WideCircuit:
             pass
 
 
-def prove_wide(ctx: Context, circuit: WideCircuit, inputs, flags: int = 0, want_output: bool = True) -> Proof:
-    """gkr_protocol::prove with the sparse two-phase layer sumcheck (same proof as `prove` on reference shapes)."""
+def prove_wide(ctx: Context, circuit: WideCircuit, inputs, flags: int = 0, want_output: bool = True, sharded: bool = False,
+               collapse_len: int = 1 << 12) -> Proof:
+    """gkr_protocol::prove with the sparse two-phase layer sumcheck (same proof as `prove` on reference shapes).
+    sharded=True (after sharded.init_comm, every rank calls with the same circuit and the whole input layer as a
+    DeviceTable): the layer sumchecks are spread over the ranks; every rank returns the same proof."""
     lib = ctx.lib
     from .core import DeviceTable
     resident = isinstance(inputs, DeviceTable)      # input layer already in HBM: no host-to-device copy in the call
@@ -140,7 +143,12 @@ def prove_wide(ctx: Context, circuit: WideCircuit, inputs, flags: int = 0, want_
     chal = np.zeros((R, 4), dtype=np.uint64)
     wb = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
     wc = np.zeros((max(L - 1, 1), 4), dtype=np.uint64)
-    if resident:
+    if sharded:
+        if not resident:
+            raise ValueError("sharded GKR takes the input layer as a DeviceTable (replicated on every rank)")
+        ctx.check(lib.zk_gkr_prove_wide_sharded(ctx.h, circuit.h, inputs.h, _ptr(output) if want_output else None, _ptr(claimed),
+                                                _ptr(claims), _ptr(coeffs), _ptr(chal), _ptr(wb), _ptr(wc), flags, collapse_len))
+    elif resident:
         ctx.check(lib.zk_gkr_prove_wide_device(ctx.h, circuit.h, inputs.h, _ptr(output) if want_output else None,
                                                _ptr(claimed), _ptr(claims), _ptr(coeffs), _ptr(chal), _ptr(wb), _ptr(wc), flags))
     else:
