@@ -50,6 +50,19 @@ template <int FID> static int run() {
             P::redc_wide(R, acc);
             if (!eq(R, s)) { ++bad; printf("redc_wide mismatch\n"); }
         }
+        // one-level Karatsuba product against the schoolbook one, limb for limb (edge operands included above: 0, 1, p-1, all ones)
+        {
+            uint32_t t1[16], t2[16];
+            P::mul_wide(t1, A, B);
+            P::mul_wide_karatsuba(t2, A, B);
+            if (memcmp(t1, t2, sizeof t1)) { ++bad; printf("karatsuba product differs from the schoolbook product (it=%d)\n", it); }
+            zk::Fe X = A, Y = to_fe(c);          // halves that make a1 - a0 / b1 - b0 negative, zero, extreme
+            for (int k = 0; k < 4; ++k) { X.v[k + 4] = A.v[k]; Y.v[k] = 0xffffffffu; }
+            if (it & 1) for (int k = 0; k < 4; ++k) X.v[k] = 0xffffffffu;
+            P::mul_wide(t1, X, Y);
+            P::mul_wide_karatsuba(t2, X, Y);
+            if (memcmp(t1, t2, sizeof t1)) { ++bad; printf("karatsuba product differs on the edge halves (it=%d)\n", it); }
+        }
         // fold by scalar table: out = lo + r*(hi-lo); r = b, lo = a, hi = c
         {
             zk::FoldTable tab;
@@ -373,7 +386,7 @@ template <int FID, int P, int D, int NLIN> static int run_tail_product(int n, in
     zk::DevOut out; memset(&out, 0, sizeof out);
     for (int t = 0; t < T; ++t) a.tp.t[t] = tabs[t].data();
     a.log_len = 0; while ((1ull << a.log_len) < cur_len) ++a.log_len;
-    a.pending = host_rounds > 0; a.mode = zk::kDevProduct; a.seq = 77; a.world = 1;
+    a.pending = host_rounds > 0; a.mode = zk::kDevProduct; a.seq = 77; a.world = 1; a.final_fold = 1;
     a.max_rounds = a.log_len - (a.pending ? 1 : 0);
     if (a.pending) a.ft = host_fold_table(f, r);
     fill_tail_consts<FID>(a, f, D);
@@ -431,7 +444,7 @@ template <int FID> static int run_tail_plain(int n, int host_rounds, int nblocks
     zk::DevOut out; memset(&out, 0, sizeof out);
     a.tp.t[0] = tab.data();
     a.log_len = 0; while ((1ull << a.log_len) < cur_len) ++a.log_len;
-    a.pending = host_rounds > 0; a.mode = zk::kDevPlain; a.seq = 5; a.world = 1;
+    a.pending = host_rounds > 0; a.mode = zk::kDevPlain; a.seq = 5; a.world = 1; a.final_fold = 1;
     a.max_rounds = a.log_len - (a.pending ? 1 : 0);
     if (a.pending) a.ft = host_fold_table(f, r);
     fill_tail_consts<FID>(a, f, 1);
@@ -534,7 +547,7 @@ template <int FID, int P, int D> static int run_sharded_product(int n, int g, in
     for (int t = 0; t < T; ++t) a.tp.t[t] = full[t].data();
     const uint64_t flen = (cur / 2) * G;
     a.log_len = 0; while ((1ull << a.log_len) < flen) ++a.log_len;
-    a.pending = 0; a.mode = zk::kDevProduct; a.seq = 12; a.world = 1; a.max_rounds = a.log_len;
+    a.pending = 0; a.mode = zk::kDevProduct; a.seq = 12; a.world = 1; a.max_rounds = a.log_len; a.final_fold = 1;
     fill_tail_consts<FID>(a, f, D);
     memcpy(&a.sponge, &outs[G - 1].sponge, sizeof a.sponge);
     a.out = &out;
@@ -574,7 +587,7 @@ template <int FID> static int run_tails() {
     // several ranks exchanging partial evaluations through peer slots, then the collapse
     for (int g = 1; g <= 3; ++g)
         for (int nb : {1, 3})
-            for (int sr = 1; sr <= 3; ++sr) {
+            for (int sr = 1; sr <= 4; ++sr) {   // sr == 4: the sharded rounds exhaust the LOCAL tables (collapse_len == 1)
                 bad += run_sharded_product<FID, 1, 2>(g + 4, g, sr, nb);
                 if (g < 3) bad += run_sharded_product<FID, 2, 2>(g + 3, g, sr > 2 ? 2 : sr, nb);
             }

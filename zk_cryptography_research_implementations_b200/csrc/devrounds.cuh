@@ -76,6 +76,9 @@ struct DevArgs {
     uint32_t seq;          // value to publish in out->seq
     uint32_t max_rounds;   // stop after this many rounds even if the tables are not exhausted (the last challenge is then
                            // left pending: sharded provers stop at the collapse point)
+    uint32_t final_fold;   // 1: when the rounds end with two entries per table and a pending challenge, do that last
+                           // partial_evaluate and report the single entries (an unsharded prove); 0: leave it pending (a rank's
+                           // shard: more rounds follow after the collapse even if the LOCAL tables are exhausted)
     uint32_t world, rank;  // world > 1: the tables are this rank's shard, partial evaluations are exchanged per round
     uint32_t xseq;         // sequence number of the round before this launch's first one (agreed by all ranks)
     FoldTable ft;          // fold table of the pending challenge
@@ -366,14 +369,14 @@ template <int FID, int P, int D, int NLIN, class Exec> struct DevRounds {
     // leader, after the last round: the last partial_evaluate, results, re-arm the global state, publish
     ZK_DEV void finish_launch(uint32_t status) {
         const int tid = ex.tid(), nt = ex.nthreads();
-        if (status == kDevOk && pending && len == 2) {
+        if (status == kDevOk && a.final_fold && pending && len == 2) {
             for (int t = tid; t < T; t += nt) {
                 Fe lo = ex.load(a.tp.t[t]), hi = ex.load(a.tp.t[t] + 1), o;
                 FoldScalar<FID>::fold(o, lo, hi, sh.ft);
                 ex.store(a.tp.t[t], o);
                 a.out->finals[t] = o;
             }
-        } else if (status == kDevOk && !pending && len == 1) {
+        } else if (status == kDevOk && a.final_fold && !pending && len == 1) {
             for (int t = tid; t < T; t += nt) a.out->finals[t] = ex.load(a.tp.t[t]);
         }
         for (int i = tid; i < 25; i += nt) a.out->sponge.s[i] = sh.sponge.s[i];

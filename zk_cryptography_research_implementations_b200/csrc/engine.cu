@@ -470,6 +470,7 @@ int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int
     a.out = ctx->dev_dev;
     a.g = ctx->dev_global;
     a.world = 1;
+    a.final_fold = sharded ? 0u : 1u;
     if (sharded) {
         a.world = (uint32_t)ctx->world;
         a.rank = (uint32_t)ctx->rank;
@@ -536,7 +537,7 @@ int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int
         memcpy(vals_out + (size_t)k * NE * 4, o->round_vals[k], (size_t)NE * sizeof(Fe));
         if (chal_out) memcpy(chal_out + (size_t)k * 4, &o->challenges[k], sizeof(Fe));
     }
-    if (finals && a.max_rounds == all_rounds) memcpy(finals, o->finals, (size_t)T * sizeof(Fe));
+    if (finals && a.final_fold && a.max_rounds == all_rounds) memcpy(finals, o->finals, (size_t)T * sizeof(Fe));
     tr.import_state(o->sponge.s, o->sponge.pos);
     if (sharded) ctx->xseq += o->rounds;
     if (rounds_run) *rounds_run = o->rounds;
