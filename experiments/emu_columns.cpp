@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "fp_columns.cuh"
+#include "fp_karatsuba.cuh"
 #include "../oracle/zkoracle.h"
 
 static uint64_t rng_state = 0x1234567ull;
@@ -65,6 +66,19 @@ template <int FID> static int run() {
             }
             C::cols29_flush(acc29, cc);
             if (memcmp(acc29, accw, sizeof accw)) { ++bad; printf("radix-2^29 accumulator differs from the chained accumulator (it=%d)\n", it); }
+        }
+        // one-level Karatsuba product against the schoolbook one, limb for limb (edge operands included above: 0, 1, p-1, all ones)
+        {
+            uint32_t t1[16], t2[16];
+            P::mul_wide(t1, A, B);
+            zk::FpKaratsuba<FID>::mul_wide_karatsuba(t2, A, B);
+            if (memcmp(t1, t2, sizeof t1)) { ++bad; printf("karatsuba product differs from the schoolbook product \n"); }
+            zk::Fe X = A, Y = to_fe(c);          // halves that make a1 - a0 / b1 - b0 negative, zero, extreme
+            for (int k = 0; k < 4; ++k) { X.v[k + 4] = A.v[k]; Y.v[k] = 0xffffffffu; }
+            if (it & 1) for (int k = 0; k < 4; ++k) X.v[k] = 0xffffffffu;
+            P::mul_wide(t1, X, Y);
+            zk::FpKaratsuba<FID>::mul_wide_karatsuba(t2, X, Y);
+            if (memcmp(t1, t2, sizeof t1)) { ++bad; printf("karatsuba product differs on the edge halves \n"); }
         }
         {   // column form of the fold: out = a + b (c - a)
             zk::FoldTable tab;

@@ -50,19 +50,6 @@ template <int FID> static int run() {
             P::redc_wide(R, acc);
             if (!eq(R, s)) { ++bad; printf("redc_wide mismatch\n"); }
         }
-        // one-level Karatsuba product against the schoolbook one, limb for limb (edge operands included above: 0, 1, p-1, all ones)
-        {
-            uint32_t t1[16], t2[16];
-            P::mul_wide(t1, A, B);
-            P::mul_wide_karatsuba(t2, A, B);
-            if (memcmp(t1, t2, sizeof t1)) { ++bad; printf("karatsuba product differs from the schoolbook product (it=%d)\n", it); }
-            zk::Fe X = A, Y = to_fe(c);          // halves that make a1 - a0 / b1 - b0 negative, zero, extreme
-            for (int k = 0; k < 4; ++k) { X.v[k + 4] = A.v[k]; Y.v[k] = 0xffffffffu; }
-            if (it & 1) for (int k = 0; k < 4; ++k) X.v[k] = 0xffffffffu;
-            P::mul_wide(t1, X, Y);
-            P::mul_wide_karatsuba(t2, X, Y);
-            if (memcmp(t1, t2, sizeof t1)) { ++bad; printf("karatsuba product differs on the edge halves (it=%d)\n", it); }
-        }
         // fold by scalar table: out = lo + r*(hi-lo); r = b, lo = a, hi = c
         {
             zk::FoldTable tab;
