@@ -892,6 +892,9 @@ def run_ours(args, wl, name=None, log2=None, steps=None, warmup=None):
         d2h = (n_rounds * (D + 1 if D > 1 else 2) + T + 1) * 32
         e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Melems/s", "h2d_bytes_per_step": T * m * 32 * world,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
+               # the step is the upload followed by the prove on one stream: what the host link delivered per GPU while it ran
+               "pcie_h2d_GBps_per_gpu": T * m * 32 / max(ms_e2e - ms, 1e-6) / 1e6,
+               "pcie_note": "h2d bytes of one rank / (e2e ms - resident prove ms); all ranks upload concurrently from pinned host memory",
                "call": "zk_table_upload_into (pinned host -> HBM) + %s" % ("zk_prove_basic_device incl. the Keccak absorb of the table"
                                                                            if D == 1 else "zk_prove_product_sharded")}
         for p in host:

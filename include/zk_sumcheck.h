@@ -38,6 +38,10 @@ enum {
                                   earlier rounds ran in a previous call -- the two phases of a sparse GKR layer) */
     ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
+    ZK_FLAG_TRUSTED_CLAIM = 32, /* zk_prove_product[_sharded]: the caller guarantees that claimed_sum IS the sum of the polynomial over
+                                  the hypercube (the GKR layer prover computed it): round 0 may then derive s(1) = claimed_sum - s(0)
+                                  like every later round instead of summing it.  The reference always sums (sumcheck_gkr_protocol.rs:
+                                  127-137); with a true claim the proof is identical, with a false one it would differ -- hence opt-in */
     ZK_FLAG_HOST_ROUNDS = 16   /* keep every round on the host-driven path: one kernel + one host Fiat-Shamir step per
                                   round.  Default: once tables x entries <= 2^tail_log (zk_ctx_set_tail_log, default 20)
                                   ONE persistent launch runs all remaining rounds with the transcript on the device

@@ -341,8 +341,9 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
         int rc0 = agree_xseq(ctx);
         if (rc0) return rc0;
     }
+    const bool trusted0 = (flags & ZK_FLAG_TRUSTED_CLAIM) && !(flags & ZK_FLAG_DIRECT_S1) && round_evals_skip1_supported(P, D, NL);
     for (uint32_t k = 0; k < n; ++k) {
-        const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
+        const bool skip1 = (k > 0 || trusted0) && !(flags & ZK_FLAG_DIRECT_S1);
         int rc;
         bool need_plain_evals = (k == 0);
         // the remaining SHARDED rounds in one persistent launch per rank: partial evaluations go from kernel to kernel
@@ -385,8 +386,11 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
             return ZK_OK;
         }
         const bool shared = sharded && ctx->xmail_host != nullptr && !(flags & ZK_FLAG_NCCL_EXCHANGE);
+        // a round that only evaluates (round 0, or the first one after the collapse): s(1) can be left out whenever the
+        // running claim is trustworthy -- always after round 0, in round 0 only on the caller's word -- and a kernel exists
+        const bool skip_now = skip1 && round_evals_skip1_supported(P, D, NL);
         if (need_plain_evals) {
-            rc = launch_round_evals(ctx, tp, P, D, sp->len, shared, NL);
+            rc = launch_round_evals(ctx, tp, P, D, sp->len, shared, NL, skip_now);
         } else {
             rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1, shared, NL);
             set_len(sp, sp->len / 2);
@@ -395,7 +399,7 @@ extern "C" int zk_prove_product_sharded(zk_ctx* ctx, zk_sumpoly* sp, const uint6
         if (sharded) rc = exchange_sum(ctx, evals, NE);
         else rc = fetch_result(ctx, evals, NE);
         if (rc) return rc;
-        if (skip1 && !need_plain_evals) evals[1] = f.sub(running, evals[0]);
+        if (need_plain_evals ? skip_now : skip1) evals[1] = f.sub(running, evals[0]);
         ip.coefficients(evals, coeffs);
         uint8_t bytes[32 * kMaxEvals];
         for (int i = 0; i < NE; ++i) f.to_bytes_le(coeffs[i], bytes + 32 * i);

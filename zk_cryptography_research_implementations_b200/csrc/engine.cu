@@ -411,10 +411,10 @@ int fetch_result(zk_ctx* ctx, HFe* out, int ne) {
     return ZK_OK;
 }
 
-int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared, int nlin) {
+int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared, int nlin, bool skip1) {
     prof_begin(ctx);
     int rc;
-    ZK_DISPATCH_FID(ctx, rc = launch_round_evals_pd<FID>(ctx, tp, P, D, nlin, len / 2, shared));
+    ZK_DISPATCH_FID(ctx, rc = launch_round_evals_pd<FID>(ctx, tp, P, D, nlin, len / 2, shared, skip1));
     prof_end(ctx, 32.0 * (P * D + nlin) * (double)len);
     return rc;
 }
@@ -751,8 +751,10 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
     TablePtrs tp = ptrs_of(sp);
     HFe evals[kMaxEvals], coeffs[kMaxEvals], r = f.zero();
     HFe running = claim;  // s_{k-1}(r_{k-1}); only trusted from round 1 on
+    // the caller vouches for claimed_sum (the GKR layer prover computed it): round 0 can derive s(1) like every later round
+    const bool trusted0 = (flags & ZK_FLAG_TRUSTED_CLAIM) && !(flags & ZK_FLAG_DIRECT_S1) && round_evals_skip1_supported(P, D, NL);
     for (uint32_t k = 0; k < n; ++k) {                                           // :37
-        const bool skip1 = k > 0 && !(flags & ZK_FLAG_DIRECT_S1);
+        const bool skip1 = (k > 0 || trusted0) && !(flags & ZK_FLAG_DIRECT_S1);
         int rc;
         if (dev_rounds_apply(ctx, sp->len, T, flags)) {   // rounds k..n-1 and the last fold in one launch, transcript on the device
             rc = run_dev_rounds(ctx, tp, P, D, NL, kDevProduct, sp->len, k > 0 ? &r : nullptr, tr->t,
@@ -762,7 +764,7 @@ extern "C" int zk_prove_product(zk_ctx* ctx, zk_sumpoly* sp, const uint64_t clai
             return ZK_OK;
         }
         if (k == 0) {
-            rc = launch_round_evals(ctx, tp, P, D, sp->len, false, NL);          // :41 generate_round_univariate
+            rc = launch_round_evals(ctx, tp, P, D, sp->len, false, NL, skip1);   // :41 generate_round_univariate
         } else {
             rc = launch_fold_evals(ctx, tp, P, D, sp->len, make_fold_table(f, r), skip1, false, NL);   // :57 fused with :41
             set_len(sp, sp->len / 2);

@@ -418,7 +418,8 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
     HFe claim = w0[0];
 
     // how the layer sumchecks run their rounds / exchange their partial sums is the caller's choice; the proof does not depend on it
-    const uint32_t sc_flags = flags & (ZK_FLAG_HOST_ROUNDS | ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_DIRECT_S1);
+    // (the claims handed to them are sums this prover computed itself: round 0 may derive s(1) from them)
+    const uint32_t sc_flags = (flags & (ZK_FLAG_HOST_ROUNDS | ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_DIRECT_S1)) | ZK_FLAG_TRUSTED_CLAIM;
     // ---- scratch tables
     DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
 

@@ -17,7 +17,9 @@ int ensure_pool(zk_ctx* ctx, size_t bytes);   // persistent table pool of the de
 int tensor_into(zk_ctx* ctx, const zk::Fe* wb, const zk::Fe* wc, uint64_t n, zk::Fe* out, int op);
 namespace zk {
 int fetch_result(zk_ctx* ctx, HFe* out, int ne);
-int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared = false, int nlin = 0);
+int launch_round_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, bool shared = false, int nlin = 0, bool skip1 = false);
+// the shapes for which a round-0 kernel without s(1) exists (ZK_FLAG_TRUSTED_CLAIM)
+inline bool round_evals_skip1_supported(int P, int D, int nlin) { return P == 1 && D == 2 && nlin == 1; }
 int launch_fold_evals(zk_ctx* ctx, const TablePtrs& tp, int P, int D, uint64_t len, const FoldTable& ft, bool skip1, bool shared = false, int nlin = 0);
 // spin until `box` carries sequence number `seq` (watchdog: stream errors, 120 s wall clock)
 int wait_mailbox(zk_ctx* ctx, const volatile Mailbox* box, unsigned seq, bool own);

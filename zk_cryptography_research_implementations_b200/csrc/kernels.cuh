@@ -183,10 +183,11 @@ template <class RA> __device__ __forceinline__ void publish_round(const RA& ra, 
 }
 
 // Round 0: evaluations only.  half = N/2 pairs (j, j + half).
-template <int FID, int P, int D, int NLIN = 0>
+// SKIP1: s(1) is left out (the caller derives it from a claimed sum it knows to be true: the GKR layer prover).
+template <int FID, int P, int D, int NLIN = 0, bool SKIP1 = false>
 __global__ void __launch_bounds__(kThreads, (P * D + NLIN <= ZK_TWO_BLOCK_TABLES && D <= 2) ? 2 : 1) round_evals_kernel(TablePtrs tp, uint64_t half, ReduceScratch rs) {
     constexpr int T = P * D + NLIN;
-    RoundAcc<FID, P, D, false, NLIN> ra;
+    RoundAcc<FID, P, D, SKIP1, NLIN> ra;
     ra.init();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {

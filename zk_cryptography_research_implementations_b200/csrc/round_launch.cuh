@@ -48,16 +48,19 @@ inline int round_blocks_per_sm(int tables) { return (tables >= 4) ? 2 : ZK_ROUND
 
 #define ZK_PD_CASES ZK_CASE(1, 1) ZK_CASE(1, 2) ZK_CASE(2, 2) ZK_CASE(1, 3) ZK_CASE(2, 3) ZK_CASE(3, 2) ZK_CASE(4, 2)
 
-template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t half, bool shared);
+template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t half, bool shared, bool skip1);
 template <int FID> int launch_fold_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t q, const FoldTable& ft, bool skip1, bool shared);
 
 #ifdef ZK_INSTANTIATE_ROUND_EVALS
-template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t half, bool shared) {
+// skip1 is honoured for the GKR phase shape only (one product + one linear table); see round_evals_skip1_supported
+template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, uint64_t half, bool shared, bool skip1) {
     if (nlin != 0 && !(P == 1 && D == 2 && nlin == 1)) return unsupported_pd(ctx);
+    if (skip1 && nlin != 1) return unsupported_pd(ctx);
     ReduceScratch rs = reduce_scratch(ctx, shared);
     int grid = launch_grid(ctx, half, round_blocks_per_sm(P * D + nlin));
     if (nlin == 1) {
-        round_evals_kernel<FID, 1, 2, 1><<<grid, kThreads, 0, ctx->stream>>>(tp, half, rs);
+        if (skip1) round_evals_kernel<FID, 1, 2, 1, true><<<grid, kThreads, 0, ctx->stream>>>(tp, half, rs);
+        else round_evals_kernel<FID, 1, 2, 1><<<grid, kThreads, 0, ctx->stream>>>(tp, half, rs);
         return launch_check(ctx);
     }
 #define ZK_CASE(PP, DD)                                                                    \
@@ -69,7 +72,7 @@ template <int FID> int launch_round_evals_pd(zk_ctx* ctx, const TablePtrs& tp, i
 #undef ZK_CASE
     return unsupported_pd(ctx);
 }
-template int launch_round_evals_pd<ZK_INSTANTIATE_ROUND_EVALS>(zk_ctx*, const TablePtrs&, int, int, int, uint64_t, bool);
+template int launch_round_evals_pd<ZK_INSTANTIATE_ROUND_EVALS>(zk_ctx*, const TablePtrs&, int, int, int, uint64_t, bool, bool);
 #endif
 
 #ifdef ZK_INSTANTIATE_FOLD_EVALS
