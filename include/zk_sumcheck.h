@@ -38,6 +38,8 @@ enum {
                                   earlier rounds ran in a previous call -- the two phases of a sparse GKR layer) */
     ZK_FLAG_NCCL_EXCHANGE = 4, /* sharded provers: exchange the per-round partials with ncclAllGather even if the
                                   shared mailboxes are attached (for comparison) */
+    ZK_FLAG_HOST_EXCHANGE = 64, /* sharded provers: exchange the per-round partials through the host (shared mailboxes, or
+                                  ncclAllGather when they are not attached) even if the ranks' exchange slots are peer-mapped */
     ZK_FLAG_TRUSTED_CLAIM = 32, /* zk_prove_product[_sharded]: the caller guarantees that claimed_sum IS the sum of the polynomial over
                                   the hypercube (the GKR layer prover computed it): round 0 may then derive s(1) = claimed_sum - s(0)
                                   like every later round instead of summing it.  The reference always sums (sumcheck_gkr_protocol.rs:

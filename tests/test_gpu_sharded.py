@@ -57,8 +57,8 @@ def _worker(rank, world, port, q):
             co.set_threads(1)
             # native driver, shard generated on the device; flags: 0 = default exchange (in-kernel over peer memory when the
             # peers could be mapped), 16 = host-driven rounds with the shared mailboxes, 4 = ncclAllGather per round,
-            # 1 = s(1) summed directly
-            for flags in (0, 16, 4, 1):
+            # 1 = s(1) summed directly, 64 = host exchange for the sharded rounds, device rounds after the collapse
+            for flags in (0, 16, 4, 1, 64):
                 tabs = [ctx.generate(5, i, N // world, first=rank, step=world) for i in range(P * D)]
                 arr = (C.c_void_p * (P * D))(*[t.release() for t in tabs])
                 sp = C.c_void_p()
@@ -115,8 +115,12 @@ def _worker(rank, world, port, q):
             sc = co.SparseCircuit(bits, layers)
             want = co.gkr_prove_sparse(fid, sc, inputs)
             wc = gkr.WideCircuit(ctx, bits, layers)
-            for flags in (0, 16, 4):
+            for flags in (0, 16, 4, "peer"):
+                if flags == "peer":          # the sharded phase rounds inside the persistent kernels, NVLink exchange
+                    os.environ["ZKB200_GKR_PEER_EXCHANGE"] = "1"
+                    flags = 0
                 proof = gkr.prove_wide(ctx, wc, dev_in, flags=flags, sharded=True, collapse_len=collapse)
+                os.environ.pop("ZKB200_GKR_PEER_EXCHANGE", None)
                 got = np.concatenate([np.stack([p_.coefficients for p_ in sp_.round_univariate_polynomials]) for sp_ in proof.sumcheck_proofs])
                 same = (np.array_equal(got, want.coeffs[: got.shape[0]]) and np.array_equal(proof.claimed_sum, want.claimed_sum)
                         and np.array_equal(proof.wb_evaluations, want.wb[: depth - 1]) and np.array_equal(proof.wc_evaluations, want.wc[: depth - 1])

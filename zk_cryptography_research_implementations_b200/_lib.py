@@ -17,7 +17,7 @@ u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
 ZK_OK, ZK_ERR_ASSERT, ZK_ERR_CUDA, ZK_ERR_ARG = 0, -1, -2, -3
-FLAG_DIRECT_S1, FLAG_SKIP_ABSORB, FLAG_NCCL_EXCHANGE, FLAG_NO_CLAIM_ABSORB, FLAG_HOST_ROUNDS, FLAG_TRUSTED_CLAIM = 1, 2, 4, 8, 16, 32
+FLAG_DIRECT_S1, FLAG_SKIP_ABSORB, FLAG_NCCL_EXCHANGE, FLAG_NO_CLAIM_ABSORB, FLAG_HOST_ROUNDS, FLAG_TRUSTED_CLAIM, FLAG_HOST_EXCHANGE = 1, 2, 4, 8, 16, 32, 64
 
 # name -> (restype, argtypes); every symbol include/zk_sumcheck.h declares
 SIGNATURES = {

@@ -442,7 +442,7 @@ extern "C" int zk_prove_basic_sharded(zk_ctx* ctx, zk_table* local, zk_transcrip
     sp.tabs.assign(1, local);
     HFe evals[2], r = f.zero();
     bool sharded = G > 1;
-    const bool dev_exchange = G > 1 && ctx->peers_attached && !(flags & (ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_HOST_ROUNDS));
+    const bool dev_exchange = G > 1 && ctx->peers_attached && !(flags & (ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_HOST_ROUNDS | ZK_FLAG_HOST_EXCHANGE));
     if (dev_exchange) {
         int rc0 = agree_xseq(ctx);
         if (rc0) return rc0;

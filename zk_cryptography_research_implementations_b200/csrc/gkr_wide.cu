@@ -419,7 +419,14 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
 
     // how the layer sumchecks run their rounds / exchange their partial sums is the caller's choice; the proof does not depend on it
     // (the claims handed to them are sums this prover computed itself: round 0 may derive s(1) from them)
-    const uint32_t sc_flags = (flags & (ZK_FLAG_HOST_ROUNDS | ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_DIRECT_S1)) | ZK_FLAG_TRUSTED_CLAIM;
+    uint32_t sc_flags = (flags & (ZK_FLAG_HOST_ROUNDS | ZK_FLAG_NCCL_EXCHANGE | ZK_FLAG_HOST_EXCHANGE | ZK_FLAG_DIRECT_S1)) | ZK_FLAG_TRUSTED_CLAIM;
+    // sharded layers: the three-table phase rounds are latency-bound and the host's Keccak is faster than the device's, so
+    // the per-round exchange goes through the host mailboxes by default (26.9 vs 29.3 ms at 8 GPUs, profiles/r02);
+    // ZKB200_GKR_PEER_EXCHANGE=1 runs the sharded rounds in the persistent kernels with the in-kernel NVLink exchange
+    if (sharded) {
+        const char* knob = getenv("ZKB200_GKR_PEER_EXCHANGE");
+        if (!(knob && knob[0] == '1')) sc_flags |= ZK_FLAG_HOST_EXCHANGE;
+    }
     // ---- scratch tables
     DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
 
