@@ -459,6 +459,30 @@ def run_mle(args, wl, log2=None, sweep=None, steps=None, warmup=None):
     ms_eval = timed(ev, lambda: None)
     result = out.copy()
     launches = ctx.stats()["launches"]
+    # after the timed region: the same value through the other implementation of evaluate (n folds, three variables per
+    # pass: fold_multi_kernel, the reference's own pass structure) -- two independent kernels must agree limb for limb
+    os.environ["ZKB200_EVAL_FOLDS"] = "1"
+    try:
+        ev()
+    finally:
+        del os.environ["ZKB200_EVAL_FOLDS"]
+    folds_agree = bool(np.array_equal(out, result))
+    # e2e (one GPU): the table in pinned host memory -> HBM -> the value back on the host
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        pin = C.c_void_p()
+        if lib.zk_pinned_alloc(C.c_size_t(m * 32), C.byref(pin)) == 0:
+            ctx.check(lib.zk_table_download(ctx.h, table.h, C.cast(pin, C.POINTER(C.c_uint64))))
+
+            def up_and_eval():
+                ctx.check(lib.zk_table_upload_into(ctx.h, table.h, pin, m))
+                ev()
+            ms_e2e = timed(up_and_eval, lambda: None)
+            e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Melems/s", "h2d_bytes_per_step": m * 32, "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e,
+                   "pcie_h2d_GBps_per_gpu": m * 32 / max(ms_e2e - ms_eval, 1e-6) / 1e6,
+                   "call": "zk_table_upload_into (pinned host -> HBM) + zk_mle_evaluate"}
+            assert np.array_equal(out, result)
+            lib.zk_pinned_free(pin)
     # one partial_evaluate of variable 0 (in place: read N, write N/2), table refilled between steps
     r0 = np.ascontiguousarray(rs[0])
     ms_fold = timed(lambda: ctx.check(lib.zk_mle_partial_evaluate(ctx.h, table.h, 0, _ptr(r0))),
@@ -502,6 +526,7 @@ def run_mle(args, wl, log2=None, sweep=None, steps=None, warmup=None):
                    "sample": "evaluate of the first 2^%d entries of the seeded table (%.2f s), oracle C restatement, 1 thread" % (sl, t)}
             if sl == log2:      # the oracle evaluated the very table the GPU did: compare the values
                 verified = bool(np.array_equal(want, result))
+        verified = folds_agree if verified is None else (verified and folds_agree)
         line = {
             "metric": "mle_evaluate_Melems_per_s", "value": N / (ms_eval * 1e-3) / MEGA, "unit": "Melems/s", "n_gpus": world,
             "steps": n_steps, "warmup": n_warm, "ms_per_step": ms_eval, "higher_is_better": True, "scaling": "strong",
@@ -513,8 +538,10 @@ def run_mle(args, wl, log2=None, sweep=None, steps=None, warmup=None):
                          "note": "timed around the whole evaluate call (all passes + host fold tables)"},
             "partial_evaluate": {"ms": ms_fold, "Melems_per_s": N / (ms_fold * 1e-3) / MEGA, "achieved_GBps": ach_fold, "frac": ach_fold / hbm_peak,
                                  "kernel": "fold0_kernel (read N, write N/2: 48 N bytes)"},
-            "cpu_baseline": cpu, "e2e": None, "gpu_launches": launches, "clocks": clocks, "sweep": sweep,
-            "verified": verified, "verified_by": "oracle mle_evaluate on the same seeded table (only when the CPU sample is the whole table)",
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "sweep": sweep,
+            "verified": verified,
+            "verified_by": "after the timed region: the inner-product result equals the result of the fold passes (a second, independent kernel path); "
+                           "and the oracle's mle_evaluate when the CPU sample is the whole table",
             "result_digest": keccak_digest([result])}
     barrier()
     ctx.close()
@@ -817,15 +844,16 @@ def run_ours(args, wl, name=None, log2=None, steps=None, warmup=None):
     achieved = st["round_bytes"] / (st["round_ms"] * 1e-3) / 1e9 if st["round_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "fold_evals_kernel / round_evals_kernel (+ one sumcheck_tail_kernel per prove) <%s,P=%d,D=%d> (all %d launches of %d steps, rank 0)"
+                "kernel": "fold_evals_kernel / round_evals_kernel (+ the persistent sumcheck_rounds_kernel launch of each prove) <%s,P=%d,D=%d> (all %d launches of %d steps, rank 0)"
                           % (fname, P, D, st["round_launches"], args.steps),
                 "algorithmic_bytes_per_step_per_rank": st["round_bytes"] / max(args.steps, 1),
                 "kernel_ms_per_step": st["round_ms"] / max(args.steps, 1)}
     launches = st["launches"]
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (one fold_evals launch of the f*g
-    # workload, old table length 2^25: 48 * T * 2^25 algorithmic bytes) -- bytes moved per launch, to set against them
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this round (one fold_evals launch of
+    # the f*g workload, old table length 2^26: 48 * T * 2^26 algorithmic bytes) -- bytes moved per launch, to set against them.
+    # (ncu cannot run inside the timed run: a number measured under a profiler is never a bench value.)
     if P == 1 and D == 2:
-        cap = os.path.join(ROOT, "profiles", "r01b_fold_evals_2p27_ncu_full_summary.csv")
+        cap = os.path.join(ROOT, "profiles", "r02", "fold_evals_2p27_ncu_full_summary.csv")
         try:
             vals = {}
             import csv
@@ -834,8 +862,9 @@ def run_ours(args, wl, name=None, log2=None, steps=None, warmup=None):
                     vals[row[1]] = float(row[3]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[row[2]]
             if len(vals) == 2:
                 roofline["traffic"] = sum(vals.values())
-                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fold_evals_kernel<BN254_FQ,1,2> launch folding 2 x 2^25 "
-                                            "entries (ncu --set full, %s): algorithmic bytes of that launch %.4g" % (os.path.relpath(cap, ROOT), 48.0 * 2 * (1 << 25)))
+                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fold_evals_kernel<BN254_FQ,1,2> launch folding 2 x 2^26 "
+                                            "entries (ncu --set full of `bench.py --log2 27`, %s, not measured in this run): algorithmic bytes of that "
+                                            "launch %.4g" % (os.path.relpath(cap, ROOT), 48.0 * 2 * (1 << 26)))
         except OSError:
             pass
 
@@ -893,7 +922,8 @@ def run_ours(args, wl, name=None, log2=None, steps=None, warmup=None):
         e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Melems/s", "h2d_bytes_per_step": T * m * 32 * world,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
                # the step is the upload followed by the prove on one stream: what the host link delivered per GPU while it ran
-               "pcie_h2d_GBps_per_gpu": T * m * 32 / max(ms_e2e - ms, 1e-6) / 1e6,
+               # (plain sumcheck: the e2e step is dominated by the serial Keccak absorb of the table, not by the link)
+               "pcie_h2d_GBps_per_gpu": (T * m * 32 / max(ms_e2e - ms, 1e-6) / 1e6) if D > 1 else None,
                "pcie_note": "h2d bytes of one rank / (e2e ms - resident prove ms); all ranks upload concurrently from pinned host memory",
                "call": "zk_table_upload_into (pinned host -> HBM) + %s" % ("zk_prove_basic_device incl. the Keccak absorb of the table"
                                                                            if D == 1 else "zk_prove_product_sharded")}
