@@ -166,6 +166,8 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     zk_comm_destroy(ctx);
+    if (ctx->side_event) cudaEventDestroy(ctx->side_event);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pool) cudaFree(ctx->pool);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -511,6 +513,7 @@ int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int
     ZK_DISPATCH_FID(ctx, rc = launch_dev_rounds_pd<FID>(ctx, P, D, nlin, a, (int)grid, nullptr));
     prof_end(ctx, bytes);
     if (rc) return rc;
+    if (ctx->dev_hook) ctx->dev_hook(chal_out);   // the round loop is queued: the caller may queue side work behind / beside it
     rc = wait_seq(ctx, &ctx->dev_host->seq, a.seq, true);
     if (rc) { ctx->dev_global_dirty = true; return rc; }
     const DevOut* o = ctx->dev_host;

@@ -1,6 +1,7 @@
 // engine.h -- the opaque handle types of include/zk_sumcheck.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -39,6 +40,12 @@ struct zk_ctx {
     unsigned dev_seq = 0;
     int tail_log = 20;                  // ZKB200_TAIL_LOG / zk_ctx_set_tail_log; 0 = always host-driven rounds
     std::map<int, int> dev_capacity;    // co-resident blocks of the round-loop kernel per (P, D, nlin)
+    // Called right after the persistent round-loop launch has been queued (argument: where that launch's first challenge
+    // will be stored in the caller's challenge array).  The GKR prover uses it to queue work that only needs the challenges
+    // known so far on `side_stream`: it backfills the SMs the shrinking round loop leaves idle.
+    std::function<void(const uint64_t*)> dev_hook;
+    cudaStream_t side_stream = nullptr;   // created on first use
+    cudaEvent_t side_event = nullptr;
     zk::HFe pow32[8];                   // Montgomery forms of 2^(32 i)
     // general scratch (evaluate / convert_to_bytes / out-of-place folds)
     void* scratch = nullptr;

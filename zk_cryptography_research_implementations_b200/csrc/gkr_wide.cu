@@ -190,6 +190,49 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Phase 2 split at the challenges known when phase 1's rounds move into the persistent launch.  eq(u, left) factors as
+// EH[left >> lo_bits] EL[left & mask] with EH = eq(u_0..u_{k-1}, .) over the first k challenges -- known by then -- and EL over the
+// rest, known only when phase 1 ends.  While the (shrinking) round loop leaves most SMs idle, phase2_pre_kernel forms
+// P_g = w(out_g) EH[left_g >> lo_bits] per gate, in by_right order: that is where the random HBM gather of w(.) happens, off the
+// critical path.  Afterwards phase2_fin_kernel only streams P_g and looks EL up in a table of 2^(m-k) entries (L2-resident):
+//   add_u(c) = sum_{add gates g: right_g = c} P_g EL[left_g & mask],  mul_u likewise;   A = W(u) add_u,  B = add_u + W(u) mul_u.
+template <int FID>
+__global__ void __launch_bounds__(kThreads) phase2_pre_kernel(GateCsr g, const Fe* w, const Fe* eh, uint32_t lo_bits, Fe* pg, uint64_t n_gates) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_gates; i += stride) {
+        Fe wv = ld256(w + g.x[i]), e = ld256_ca(eh + (g.y[i] >> lo_bits)), t;
+        Fp<FID>::mont_mul(t, wv, e);
+        st256(pg + i, t);
+    }
+}
+template <int FID>
+__global__ void __launch_bounds__(kThreads)
+    phase2_fin_kernel(GateCsr g, const Fe* pg, const Fe* el, uint32_t lo_bits, const __grid_constant__ FoldTable Wu, Fe* A, Fe* B, uint64_t nc, uint64_t first, uint64_t step) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mask = (1u << lo_bits) - 1u;
+    Fe zero;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) zero.v[k] = 0;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += stride) {
+        const uint64_t c = first + j * step;
+        Fe addu, mulu;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) addu.v[k] = mulu.v[k] = 0;
+        for (uint64_t i = g.off[c]; i < g.off[c + 1]; ++i) {
+            Fe p = ld256(pg + i), e = ld256(el + (g.y[i] & mask)), t;
+            Fp<FID>::mont_mul(t, p, e);
+            if (g.op[i] == 0) Fp<FID>::add(addu, addu, t);
+            else Fp<FID>::add(mulu, mulu, t);
+        }
+        Fe a, m, bsum;
+        FoldScalar<FID>::fold(a, zero, addu, Wu);
+        FoldScalar<FID>::fold(m, zero, mulu, Wu);
+        Fp<FID>::add(bsum, addu, m);
+        st256(A + j, a);
+        st256(B + j, bsum);
+    }
+}
+
 // verifier: add_i / mul_i at the sumcheck point with `a` bound (gkr/src/utils.rs:84-135) from the gate list,
 //   add_r = sum over add gates of w(out_g) eq(u, left_g) eq(v, right_g),   mul_r likewise,
 // one thread per b = left index (by_left CSR: x = out, y = right); per-block partial sums, added on the host.
@@ -427,6 +470,14 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         const char* knob = getenv("ZKB200_GKR_PEER_EXCHANGE");
         if (!(knob && knob[0] == '1')) sc_flags |= ZK_FLAG_HOST_EXCHANGE;
     }
+    // overlap of the gate-wise phase-2 work with phase 1's latency rounds (ZKB200_GKR_OVERLAP=0 switches it off: A/B, tests);
+    // a traced run synchronises at every stage mark, which would serialise it anyway
+    const char* ov_knob = getenv("ZKB200_GKR_OVERLAP");
+    const bool overlap = !(ov_knob && ov_knob[0] == '0') && !trace && wc->pre_pg.p != nullptr;
+    if (overlap && !ctx->side_stream) {
+        ZK_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        ZK_CUDA(cudaEventCreateWithFlags(&ctx->side_event, cudaEventDisableTiming));
+    }
     // ---- scratch tables
     DevBuf &wtab = wc->wtab, &eqa = wc->eqa, &h1 = wc->h1, &h2 = wc->h2, &Wc = wc->Wc;
 
@@ -476,16 +527,47 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         uint64_t* chal = challenges_out + 4 * round_off;
         uint64_t* coef = coeffs_out + 12 * round_off;
         HFe fin1[4], fin2[4];
+        // When phase 1's rounds move into the persistent launch, the challenges u_0..u_{k-1} are known and most SMs fall idle:
+        // queue the gate-wise half of the phase-2 build (phase2_pre_kernel) on the side stream behind that launch.
+        uint32_t pre_k = 0;
+        int pre_rc = ZK_OK;
+        if (overlap && wl.n_gates > 0) {
+            ctx->dev_hook = [&](const uint64_t* first_chal) {
+                if (pre_k || pre_rc) return;
+                const uint32_t k = (uint32_t)((first_chal - chal) / 4);
+                if (k < 2 || k + 2 > m || k > (uint32_t)kEqHalfBits) return;
+                cudaStream_t main_stream = ctx->stream;
+                ctx->stream = ctx->side_stream;   // the eq helpers launch on the context's stream
+                std::vector<HFe> uk(reinterpret_cast<const HFe*>(chal), reinterpret_cast<const HFe*>(chal) + k);
+                pre_rc = launch_eq_halves(ctx, uk, f.one(), wc->pre_eh.p, wc->half_lo2.p, k, 0);
+                if (!pre_rc) {
+                    ZK_FID_SWITCH(ctx, (phase2_pre_kernel<FID><<<grid_of(ctx, wl.n_gates, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, wc->pre_eh.p, m - k, wc->pre_pg.p, wl.n_gates)));
+                    ctx->launches++;
+                    if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->side_event, ctx->stream) != cudaSuccess) pre_rc = ZK_ERR_CUDA;
+                }
+                ctx->stream = main_stream;
+                if (!pre_rc) pre_k = k;
+            };
+        }
         if (G > 1) rc = zk_prove_product_sharded(ctx, &sp1, claim.l, &wrap, coef, chal, fin1[0].l, sc_flags, collapse_len);
         else rc = zk_prove_product(ctx, &sp1, claim.l, &wrap, coef, chal, fin1[0].l, sc_flags);          // rounds 0..m-1
+        ctx->dev_hook = nullptr;
         if (rc) return rc;
+        if (pre_rc) return fail(ctx, ZK_ERR_CUDA, "GKR: the overlapped phase-2 precomputation failed to launch");
         mark(3);
         const HFe Wu = fin1[1];                                                                           // W(r_b)
         std::vector<HFe> u(reinterpret_cast<HFe*>(chal), reinterpret_cast<HFe*>(chal) + m);
         // ---- phase 2 tables and sumcheck over c
-        if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
         const FoldTable Wu_ft = make_fold_table(f, Wu);
-        ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nl, q, G)));
+        if (pre_k) {   // the gate-wise products are (being) computed on the side stream: only the low part of eq(u, .) is missing
+            std::vector<HFe> ulo(u.begin() + pre_k, u.end());
+            if ((rc = build_eq2(ctx, wc, ulo, f.one(), nullptr, f.one(), eqa.p))) return rc;
+            ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->side_event, 0));
+            ZK_FID_SWITCH(ctx, (phase2_fin_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wc->pre_pg.p, eqa.p, m - pre_k, Wu_ft, h1.p, h2.p, nl, q, G)));
+        } else {
+            if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
+            ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nl, q, G)));
+        }
         ctx->launches += 1;
         ZK_CUDA(cudaGetLastError());
         mark(4);

@@ -37,5 +37,6 @@ struct zk_wide_circuit {
     // prover workspace, allocated with the circuit so a prove never calls cudaMalloc/cudaFree:
     std::vector<DevBuf> W;        // all layer values (Circuit::evaluate result), resident
     DevBuf wtab, eqa, h1, h2, Wc, half_hi, half_lo, half_hi2, half_lo2;
+    DevBuf pre_pg, pre_eh;        // overlapped phase-2 precomputation: one product per gate (widest layer), eq over the known challenges
 };
 

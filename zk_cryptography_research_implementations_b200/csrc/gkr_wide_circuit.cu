@@ -305,9 +305,10 @@ extern "C" int zk_wide_circuit_create(zk_ctx* ctx, uint32_t n_layers, const uint
         DevBuf* bufs[] = {&wc->wtab, &wc->eqa, &wc->h1, &wc->h2, &wc->Wc};
         for (DevBuf* b : bufs)
             if (e == cudaSuccess) e = b->alloc(maxn);
-        DevBuf* halves[] = {&wc->half_hi, &wc->half_lo, &wc->half_hi2, &wc->half_lo2};   // half_hi doubles as the slice scratch of evaluate
+        DevBuf* halves[] = {&wc->half_hi, &wc->half_lo, &wc->half_hi2, &wc->half_lo2, &wc->pre_eh};   // half_hi doubles as the slice scratch of evaluate
         for (DevBuf* b : halves)
             if (e == cudaSuccess) e = b->alloc(1ull << 16);
+        if (e == cudaSuccess) e = wc->pre_pg.alloc(max_gates ? max_gates : 1);
         if (e != cudaSuccess) {
             ctx->err = std::string("cudaMalloc (GKR workspace): ") + cudaGetErrorString(e);
             zk_wide_circuit_free(ctx, wc);
