@@ -257,7 +257,9 @@ def test_wide_prover_limb_for_limb_against_the_gate_list_oracle(zk, co, ctx_for,
     # tail_log 13 / 9: the phase sumchecks run 5 / 9 host-driven rounds before the persistent launch, so the overlapped
     # gate-wise phase-2 precomputation (phase2_pre_kernel on the side stream, phase2_fin_kernel) is what builds A and B;
     # ZKB200_GKR_OVERLAP=0: the one-kernel build.  All must give the oracle's proof.
-    for knobs, tail_log in (({"ZKB200_EQ_ROWS": "1"}, 20), ({"ZKB200_EQ_ROWS": "0"}, 20), ({}, 13), ({}, 9), ({"ZKB200_GKR_OVERLAP": "0"}, 13)):
+    # ZKB200_GKR_SEG=0: the wire-per-thread table builders instead of the warp-segmented gate-parallel ones.
+    for knobs, tail_log in (({"ZKB200_EQ_ROWS": "1"}, 20), ({"ZKB200_EQ_ROWS": "0"}, 20), ({}, 13), ({}, 9), ({"ZKB200_GKR_OVERLAP": "0"}, 13),
+                            ({"ZKB200_GKR_SEG": "0"}, 20), ({"ZKB200_GKR_SEG": "0"}, 13)):
         os.environ.update(knobs)
         ctx.set_tail_log(tail_log)
         try:

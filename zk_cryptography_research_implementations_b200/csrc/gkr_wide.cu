@@ -132,6 +132,153 @@ template <int FID> __global__ void __launch_bounds__(kThreads) sum_slices_kernel
     }
 }
 
+// ---------------------------------------------------------------- warp-segmented bucket sums
+// The table builders sum, per wire, a value over that wire's gates (its CSR bucket).  One thread per wire with a loop over
+// its bucket wastes most of a warp: bucket lengths are Poisson-like (a third of the wires have no gate, a few have five), the
+// warp runs max-over-lanes iterations with a dependent load chain each, and the random gathers -- what these kernels are
+// made of -- are issued at a quarter of the possible rate (phase2_kernel: 410 us where a gate-parallel pass with the same
+// gathers takes ~150 us, profiles/r02).  Here a WARP owns 32 consecutive wires, i.e. one contiguous range of gates, and
+// walks that range gate-parallel (lane l takes gates S + l, S + l + 32, ...: coalesced index loads, every lane busy, all
+// gathers in flight at once).  A gate's value goes to its wire's accumulator in shared memory as 32-bit limb columns
+// (atomicAdd on the low word, the rare carry into a high word: exact integer sums, so the order is irrelevant and the
+// result is the canonical field sum after ONE Barrett step per wire); the owning lane is found by a 5-step binary search
+// over the 32 bucket starts held in the warp's registers.
+constexpr int kSegWarps = kThreads / 32;
+template <int FID, class Op>
+__global__ void __launch_bounds__(kThreads) seg_bucket_kernel(GateCsr g, uint64_t n_keys, const __grid_constant__ Op op) {
+    constexpr int NV = Op::NV;
+    __shared__ uint32_t acc_lo[kSegWarps][NV][8][32];
+    __shared__ uint32_t acc_hi[kSegWarps][NV][8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_tiles = (n_keys + 31) / 32;
+    for (uint64_t tile = (uint64_t)blockIdx.x * kSegWarps + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * kSegWarps) {
+        const uint64_t key = tile * 32 + lane;
+        const uint64_t s = g.off[key < n_keys ? key : n_keys];                 // this lane's bucket start (sorted over the warp)
+        const uint64_t e = g.off[key + 1 < n_keys ? key + 1 : n_keys];
+        const uint64_t S = __shfl_sync(0xffffffffu, s, 0), E = __shfl_sync(0xffffffffu, e, 31);
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc_lo[warp][v][k][lane] = acc_hi[warp][v][k][lane] = 0;
+        __syncwarp();
+        for (uint64_t base = S; base < E; base += 32) {
+            const uint64_t i = base + lane;
+            const bool active = i < E;
+            // owner = the last lane whose bucket starts at or before gate i
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
+                const int mid = (lo + hi + 1) >> 1;
+                const uint64_t sm = __shfl_sync(0xffffffffu, s, mid);
+                if (sm <= i) lo = mid;
+                else hi = mid - 1;
+            }
+            if (active) {
+                Fe val[NV];
+                uint32_t present = 0;
+                op.template gate<FID>(i, g.x[i], g.y[i], g.op[i], val, present);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    if (!((present >> v) & 1u)) continue;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t x = val[v].v[k];
+                        const uint32_t old = atomicAdd(&acc_lo[warp][v][k][lo], x);
+                        if (old + x < old) atomicAdd(&acc_hi[warp][v][k][lo], 1u);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (key < n_keys) {
+            Fe sum[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                uint32_t limbs[9];
+                unsigned long long c = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    c += (unsigned long long)acc_lo[warp][v][k][lane] + ((unsigned long long)acc_hi[warp][v][k][lane] << 32);
+                    limbs[k] = (uint32_t)c;
+                    c >>= 32;
+                }
+                limbs[8] = (uint32_t)c;
+                Fp<FID>::reduce9(sum[v], limbs);
+            }
+            op.template finish<FID>(key, sum);
+        }
+        __syncwarp();
+    }
+}
+// phase 1: h1(b) = sum_{left = b} w(out) (add ? 1 : W(right)),  h2(b) = sum_{add, left = b} w(out) W(right)     (x = out, y = right)
+struct Phase1Op {
+    static constexpr int NV = 2;
+    const Fe *w, *W;
+    Fe *h1, *h2;
+    template <int FID> __device__ __forceinline__ void gate(uint64_t, uint32_t x, uint32_t y, uint8_t op, Fe (&val)[2], uint32_t& present) const {
+        const Fe wv = ld256(w + x), wr = ld256(W + y);
+        Fe t;
+        Fp<FID>::mont_mul(t, wv, wr);
+        if (op == 0) { val[0] = wv; val[1] = t; present = 3u; }
+        else { val[0] = t; present = 1u; }
+    }
+    template <int FID> __device__ __forceinline__ void finish(uint64_t b, const Fe (&sum)[2]) const {
+        st256(h1 + b, sum[0]);
+        st256(h2 + b, sum[1]);
+    }
+};
+// phase 2: add_u(c) = sum_{add, right = c} w(out) eq(u, left), mul_u likewise; A = W(u) add_u, B = add_u + W(u) mul_u   (x = out, y = left)
+struct Phase2Op {
+    static constexpr int NV = 2;
+    const Fe *w, *equ;
+    Fe *A, *B;
+    FoldTable Wu;
+    template <int FID> __device__ __forceinline__ void gate(uint64_t, uint32_t x, uint32_t y, uint8_t op, Fe (&val)[2], uint32_t& present) const {
+        const Fe wv = ld256(w + x), e = ld256(equ + y);
+        Fp<FID>::mont_mul(val[op ? 1 : 0], wv, e);
+        present = op ? 2u : 1u;
+    }
+    template <int FID> __device__ __forceinline__ void finish(uint64_t c, const Fe (&sum)[2]) const {
+        Fe zero, a, m, bsum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) zero.v[k] = 0;
+        FoldScalar<FID>::fold(a, zero, sum[0], Wu);   // W(u) * add_u(c): a product by a per-launch constant
+        FoldScalar<FID>::fold(m, zero, sum[1], Wu);
+        Fp<FID>::add(bsum, sum[0], m);
+        st256(A + c, a);
+        st256(B + c, bsum);
+    }
+};
+// phase 2 after the overlapped gate-wise half (phase2_pre_kernel): P_g EL[left & mask]
+struct Phase2FinOp {
+    static constexpr int NV = 2;
+    const Fe *pg, *el;
+    uint32_t mask;
+    Fe *A, *B;
+    FoldTable Wu;
+    template <int FID> __device__ __forceinline__ void gate(uint64_t i, uint32_t, uint32_t y, uint8_t op, Fe (&val)[2], uint32_t& present) const {
+        const Fe p = ld256(pg + i), e = ld256(el + (y & mask));
+        Fp<FID>::mont_mul(val[op ? 1 : 0], p, e);
+        present = op ? 2u : 1u;
+    }
+    template <int FID> __device__ __forceinline__ void finish(uint64_t c, const Fe (&sum)[2]) const {
+        Fe zero, a, m, bsum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) zero.v[k] = 0;
+        FoldScalar<FID>::fold(a, zero, sum[0], Wu);
+        FoldScalar<FID>::fold(m, zero, sum[1], Wu);
+        Fp<FID>::add(bsum, sum[0], m);
+        st256(A + c, a);
+        st256(B + c, bsum);
+    }
+};
+inline int seg_grid(const zk_ctx* ctx, uint64_t n_keys) {
+    uint64_t blocks = ((n_keys + 31) / 32 + kSegWarps - 1) / kSegWarps, cap = (uint64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (ctx->grid_cap > 0 && blocks > (uint64_t)ctx->grid_cap) blocks = ctx->grid_cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
 // phase-1 tables: one thread per b.  (first, step): the b this launch covers are first + j * step, j < nb, written to
 // position j -- a rank's shard of the phase tables (low index bits, comm.cu) or, with (0, 1), the whole table.
 template <int FID>
@@ -472,6 +619,8 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
     }
     // overlap of the gate-wise phase-2 work with phase 1's latency rounds (ZKB200_GKR_OVERLAP=0 switches it off: A/B, tests);
     // a traced run synchronises at every stage mark, which would serialise it anyway
+    const char* seg_knob = getenv("ZKB200_GKR_SEG");   // 0: the wire-per-thread builders (A/B, tests)
+    const bool seg_buckets = !(seg_knob && seg_knob[0] == '0');
     const char* ov_knob = getenv("ZKB200_GKR_OVERLAP");
     const bool overlap = !(ov_knob && ov_knob[0] == '0') && !trace && wc->pre_pg.p != nullptr;
     if (overlap && !ctx->side_stream) {
@@ -503,7 +652,12 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
         const uint64_t G = (sharded && nm >= 2 * (uint64_t)ctx->world) ? (uint64_t)ctx->world : 1, q = G > 1 ? (uint64_t)ctx->rank : 0;
         const uint64_t nl = nm / G;   // this rank's wires: b = q + j G
         // ---- phase 1 tables and sumcheck over b
-        ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nl, q, G)));
+        if (G == 1 && seg_buckets) {   // a warp per 32 wires, gate-parallel (a rank's strided shard keeps the wire-per-thread kernel)
+            const Phase1Op op1{wtab.p, W[li + 1].p, h1.p, h2.p};
+            ZK_FID_SWITCH(ctx, (seg_bucket_kernel<FID, Phase1Op><<<seg_grid(ctx, nm), kThreads, 0, ctx->stream>>>(wl.by_left, nm, op1)));
+        } else {
+            ZK_FID_SWITCH(ctx, (phase1_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_left, wtab.p, W[li + 1].p, h1.p, h2.p, nl, q, G)));
+        }
         ctx->launches++;
         if (G > 1) {
             strided_copy_kernel<<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(W[li + 1].p, Wc.p, nl, q, G);
@@ -563,10 +717,20 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
             std::vector<HFe> ulo(u.begin() + pre_k, u.end());
             if ((rc = build_eq2(ctx, wc, ulo, f.one(), nullptr, f.one(), eqa.p))) return rc;
             ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->side_event, 0));
-            ZK_FID_SWITCH(ctx, (phase2_fin_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wc->pre_pg.p, eqa.p, m - pre_k, Wu_ft, h1.p, h2.p, nl, q, G)));
+            if (G == 1 && seg_buckets) {
+                const Phase2FinOp opf{wc->pre_pg.p, eqa.p, (1u << (m - pre_k)) - 1u, h1.p, h2.p, Wu_ft};
+                ZK_FID_SWITCH(ctx, (seg_bucket_kernel<FID, Phase2FinOp><<<seg_grid(ctx, nm), kThreads, 0, ctx->stream>>>(wl.by_right, nm, opf)));
+            } else {
+                ZK_FID_SWITCH(ctx, (phase2_fin_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wc->pre_pg.p, eqa.p, m - pre_k, Wu_ft, h1.p, h2.p, nl, q, G)));
+            }
         } else {
             if ((rc = build_eq2(ctx, wc, u, f.one(), nullptr, f.one(), eqa.p))) return rc;
-            ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nl, q, G)));
+            if (G == 1 && seg_buckets) {
+                const Phase2Op op2{wtab.p, eqa.p, h1.p, h2.p, Wu_ft};
+                ZK_FID_SWITCH(ctx, (seg_bucket_kernel<FID, Phase2Op><<<seg_grid(ctx, nm), kThreads, 0, ctx->stream>>>(wl.by_right, nm, op2)));
+            } else {
+                ZK_FID_SWITCH(ctx, (phase2_kernel<FID><<<grid_of(ctx, nl, 4), kThreads, 0, ctx->stream>>>(wl.by_right, wtab.p, eqa.p, Wu_ft, h1.p, h2.p, nl, q, G)));
+            }
         }
         ctx->launches += 1;
         ZK_CUDA(cudaGetLastError());
