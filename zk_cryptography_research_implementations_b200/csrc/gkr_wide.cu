@@ -144,8 +144,11 @@ template <int FID> __global__ void __launch_bounds__(kThreads) sum_slices_kernel
 // result is the canonical field sum after ONE Barrett step per wire); the owning lane is found by a 5-step binary search
 // over the 32 bucket starts held in the warp's registers.
 constexpr int kSegWarps = kThreads / 32;
+#ifndef ZK_SEG_MIN_BLOCKS
+#define ZK_SEG_MIN_BLOCKS 4   // these kernels are chains of dependent loads per tile: resident warps, not registers, buy throughput
+#endif
 template <int FID, class Op>
-__global__ void __launch_bounds__(kThreads) seg_bucket_kernel(GateCsr g, uint64_t n_keys, const __grid_constant__ Op op) {
+__global__ void __launch_bounds__(kThreads, ZK_SEG_MIN_BLOCKS) seg_bucket_kernel(GateCsr g, uint64_t n_keys, const __grid_constant__ Op op) {
     constexpr int NV = Op::NV;
     __shared__ uint32_t acc_lo[kSegWarps][NV][8][32];
     __shared__ uint32_t acc_hi[kSegWarps][NV][8][32];
