@@ -436,3 +436,109 @@ def table_generate(fid: int, seed: int, table_id: int, n: int, first: int = 0, s
     out = np.zeros((n, 4), dtype=np.uint64)
     lib().zko_table_generate(fid, C.c_uint64(seed), C.c_uint64(table_id), C.c_uint64(n), C.c_uint64(first), C.c_uint64(step), _p(out))
     return out
+
+
+# ------------------------------------------------------------------ multilinear KZG over BLS12-381 G1 (zkoracle_kzg.c)
+FR = 2   # ZKO_BLS12_381_FR: the scalar field of every KZG call
+
+
+def g1_from_ints(points) -> np.ndarray:
+    """[(x, y) | None, ...] canonical Python ints -> (len, 12) Montgomery limb array (None = infinity = all zero)"""
+    out = np.zeros((len(points), 12), dtype=np.uint64)
+    tmp = np.zeros(6, dtype=np.uint64)
+    for i, pt in enumerate(points):
+        if pt is None:
+            continue
+        for c in range(2):
+            for k in range(6):
+                tmp[k] = (pt[c] >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+            lib().zko_fq_from_canonical(_p(tmp), _p(out[i, 6 * c:6 * c + 6]))
+    return out
+
+
+def g1_to_ints(a: np.ndarray):
+    a = _arr(a).reshape(-1, 12)
+    tmp = np.zeros(6, dtype=np.uint64)
+    res = []
+    for i in range(a.shape[0]):
+        if not a[i].any():
+            res.append(None)
+            continue
+        xy = []
+        for c in range(2):
+            lib().zko_fq_to_canonical(_p(np.ascontiguousarray(a[i, 6 * c:6 * c + 6])), _p(tmp))
+            xy.append(sum(int(tmp[k]) << (64 * k) for k in range(6)))
+        res.append(tuple(xy))
+    return res
+
+
+def g1_generator() -> np.ndarray:
+    out = np.zeros(12, dtype=np.uint64)
+    lib().zko_g1_generator(_p(out))
+    return out
+
+
+def g1_is_on_curve(p: np.ndarray) -> bool:
+    return bool(lib().zko_g1_is_on_curve(_p(_arr(p).reshape(12))))
+
+
+def g1_add(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    out = np.zeros(12, dtype=np.uint64)
+    lib().zko_g1_add(_p(_arr(a).reshape(12)), _p(_arr(b).reshape(12)), _p(out))
+    return out
+
+
+def g1_mul(p: np.ndarray, k: int) -> np.ndarray:
+    """mul_bigint by the canonical integer k < 2^256"""
+    out = np.zeros(12, dtype=np.uint64)
+    kk = np.array([(k >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    lib().zko_g1_mul(_p(_arr(p).reshape(12)), _p(kk), _p(out))
+    return out
+
+
+def kzg_setup_g1(taus: np.ndarray) -> np.ndarray:
+    """trusted_setup.rs:26-63: g1_powers_of_tau for taus (n, 4) -> (2^n, 12)"""
+    taus = _arr(taus).reshape(-1, 4)
+    n = taus.shape[0]
+    out = np.zeros((1 << n, 12), dtype=np.uint64)
+    rc = lib().zko_kzg_setup_g1(_p(taus), C.c_uint32(n), _p(out))
+    if rc:
+        raise AssertionError("requires at least one variable")
+    return out
+
+
+def kzg_commit(vals: np.ndarray, g1: np.ndarray) -> np.ndarray:
+    """multilinear_kzg.rs:25-46"""
+    vals = _arr(vals).reshape(-1, 4)
+    g1 = _arr(g1).reshape(-1, 12)
+    out = np.zeros(12, dtype=np.uint64)
+    rc = lib().zko_kzg_commit(_p(vals), C.c_uint64(vals.shape[0]), _p(g1), C.c_uint64(g1.shape[0]), _p(out))
+    if rc:
+        raise AssertionError("Polynomial evaluation must match g1 length")
+    return out
+
+
+def kzg_open(vals: np.ndarray, g1: np.ndarray, opening: np.ndarray):
+    """multilinear_kzg.rs:51-127 -> (evaluation (4,), proofs (n, 12))"""
+    vals = _arr(vals).reshape(-1, 4)
+    g1 = _arr(g1).reshape(-1, 12)
+    opening = _arr(opening).reshape(-1, 4)
+    nvars = vals.shape[0].bit_length() - 1
+    ev = np.zeros(4, dtype=np.uint64)
+    proofs = np.zeros((max(nvars, 1), 12), dtype=np.uint64)
+    rc = lib().zko_kzg_open(_p(vals), C.c_uint32(nvars), _p(g1), C.c_uint64(g1.shape[0]), _p(opening),
+                            C.c_uint32(opening.shape[0]), _p(ev), _p(proofs))
+    if rc == -1:
+        raise AssertionError("number of polynomial variables must match length of opening values")
+    if rc:
+        raise AssertionError("Opening values must match number of variables from trusted setup")
+    return ev, proofs[:nvars]
+
+
+def kzg_verify_trapdoor(taus: np.ndarray, commitment: np.ndarray, opening: np.ndarray, evaluation: np.ndarray,
+                        proofs: np.ndarray) -> bool:
+    """multilinear_kzg.rs:132-159 checked in G1 with the toxic waste known (no pairing)"""
+    taus = _arr(taus).reshape(-1, 4)
+    return bool(lib().zko_kzg_verify_trapdoor(_p(taus), C.c_uint32(taus.shape[0]), _p(_arr(commitment).reshape(12)),
+                                              _p(_arr(opening).reshape(-1, 4)), _p(_arr(evaluation).reshape(4)),
+                                              _p(_arr(proofs).reshape(-1, 12))))

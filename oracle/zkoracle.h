@@ -148,6 +148,23 @@ int  zko_gkr_verify_sparse(int fid, uint32_t n_layers, const uint32_t *layer_bit
 /* ---- the bench workload's seeded tables, as the CUDA generator makes them ---- */
 void zko_table_generate(int fid, uint64_t seed, uint64_t table_id, uint64_t n, uint64_t first, uint64_t step, uint64_t *out);
 
+/* ---- multilinear KZG over BLS12-381 G1 (multilinear_kzg/src/{trusted_setup,multilinear_kzg}.rs; zkoracle_kzg.c) ----
+ * Points: affine (x, y) as 6 + 6 uint64 little-endian limbs, Montgomery form (R = 2^384), infinity = all zero.
+ * Scalars: BLS12-381 Fr elements (4 limbs, Montgomery).  zko_set_threads applies to the sums over the setup. */
+void zko_g1_generator(uint64_t out[12]);
+void zko_fq_from_canonical(const uint64_t in[6], uint64_t out[6]);
+void zko_fq_to_canonical(const uint64_t in[6], uint64_t out[6]);
+int  zko_g1_is_on_curve(const uint64_t p[12]);
+void zko_g1_add(const uint64_t a[12], const uint64_t b[12], uint64_t out[12]);
+void zko_g1_neg(const uint64_t a[12], uint64_t out[12]);
+void zko_g1_mul(const uint64_t p[12], const uint64_t k_canonical[4], uint64_t out[12]);   /* mul_bigint */
+int  zko_kzg_setup_g1(const uint64_t *taus, uint32_t n, uint64_t *g1_out /* 12 * 2^n */);
+int  zko_kzg_commit(const uint64_t *vals, uint64_t len, const uint64_t *g1, uint64_t g1_len, uint64_t out[12]);
+int  zko_kzg_open(const uint64_t *vals, uint32_t nvars, const uint64_t *g1, uint64_t g1_len, const uint64_t *opening,
+                  uint32_t n_opening, uint64_t eval[4], uint64_t *proofs /* 12 * nvars */);
+int  zko_kzg_verify_trapdoor(const uint64_t *taus, uint32_t n, const uint64_t commitment[12], const uint64_t *opening,
+                             const uint64_t eval[4], const uint64_t *proofs);
+
 #ifdef __cplusplus
 }
 #endif
