@@ -275,6 +275,38 @@ int  zk_gkr_prove_wide_sharded(zk_ctx *, const zk_wide_circuit *, const zk_table
 /* MultilinearPolynomial::evaluate over a sharded table (values: all log2(global length) challenges) */
 int  zk_mle_evaluate_sharded(zk_ctx *, const zk_table *local, const uint64_t *values, uint32_t n_values, uint64_t out[4]);
 
+/* ---- multilinear KZG over BLS12-381 G1: the input commitment of succinct GKR ----
+ * Replaces multilinear_kzg/src/trusted_setup.rs:12-63 (TrustedSetup::initialize_setup, G1 side),
+ * multilinear_kzg/src/multilinear_kzg.rs:25-46 (commit_to_polynomial) and :51-127 (open_and_prove), the calls
+ * gkr/src/succinct_gkr_protocol.rs:43-44 and :151-154 make.  The context must be a BLS12-381 Fr one (the curve's scalar
+ * field).  G1 points cross the boundary in affine form: x then y, 6 + 6 uint64 little-endian limbs, Montgomery form with
+ * R = 2^384 -- arkworks' `G1Affine` coordinates byte for byte (`P::G1` values via `into_affine()`); the point at infinity
+ * is all zero.  Scalars are Fr elements in Montgomery form like every other table.
+ * Every sum over the setup is one bucket-method multi-scalar multiplication on the GPU; the "blown up" quotients of
+ * open_and_prove (multilinear_kzg.rs:93-108, :183-214) are summed against the setup folded over its leading variables
+ * (built once per setup), so an opening costs 2^n point additions instead of n 2^n scalar multiplications. */
+typedef struct zk_kzg_setup zk_kzg_setup;
+/* initialize_setup(taus): g1_powers_of_tau[i] = lagrange_basis(taus)[i] * G, computed on the GPU.
+ * ZK_ERR_ASSERT "requires at least one variable" (trusted_setup.rs:28). */
+int  zk_kzg_setup_create(zk_ctx *, const uint64_t *taus /* 4*n */, uint32_t n, zk_kzg_setup **out);
+/* an existing g1_powers_of_tau (2^n points, checked to be on the curve: ZK_ERR_ARG otherwise) */
+int  zk_kzg_setup_from_points(zk_ctx *, const uint64_t *g1_points /* 12 * 2^n */, uint32_t n, zk_kzg_setup **out);
+void zk_kzg_setup_free(zk_ctx *, zk_kzg_setup *);
+uint32_t zk_kzg_setup_num_vars(const zk_kzg_setup *);
+/* level 0: g1_powers_of_tau (2^n points); level k: the setup summed over its first k variables (2^(n-k) points) */
+int  zk_kzg_setup_points(zk_ctx *, const zk_kzg_setup *, uint32_t level, uint64_t *out /* 12 * 2^(n-level) */);
+/* commit_to_polynomial.  ZK_ERR_ASSERT "Polynomial evaluation must match g1 length". */
+int  zk_kzg_commit(zk_ctx *, zk_kzg_setup *, const uint64_t *evaluated_values, uint64_t len, uint64_t commitment[12]);
+int  zk_kzg_commit_device(zk_ctx *, zk_kzg_setup *, const zk_table *, uint64_t commitment[12]);   /* the table is not modified */
+/* open_and_prove -> MultilinearKZGProof{evaluation, proofs[n]}.  ZK_ERR_ASSERT "number of polynomial variables must match
+ * length of opening values" / "Opening values must match number of variables from trusted setup". */
+int  zk_kzg_open(zk_ctx *, zk_kzg_setup *, const uint64_t *evaluated_values, uint64_t len, const uint64_t *opening_values,
+                 uint32_t n_opening, uint64_t evaluation[4], uint64_t *proofs /* 12 * n */);
+int  zk_kzg_open_device(zk_ctx *, zk_kzg_setup *, const zk_table *, const uint64_t *opening_values, uint32_t n_opening,
+                        uint64_t evaluation[4], uint64_t *proofs);
+/* sum_i scalars[i] * points[i] over caller-supplied host arrays (`.map(mul_bigint).sum()`); any n, points checked */
+int  zk_g1_msm(zk_ctx *, const uint64_t *scalars /* 4*n */, const uint64_t *points /* 12*n */, uint64_t n, uint64_t out[12]);
+
 /* ---- measurement: register-resident field arithmetic, no memory traffic (the IMAD-pipe ceiling) ----
  * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate. */
 int  zk_arith_probe(zk_ctx *, int kind, uint32_t iters, int blocks_per_sm, double *ops_per_s, double *ms);

@@ -154,6 +154,7 @@ void zko_table_generate(int fid, uint64_t seed, uint64_t table_id, uint64_t n, u
 void zko_g1_generator(uint64_t out[12]);
 void zko_fq_from_canonical(const uint64_t in[6], uint64_t out[6]);
 void zko_fq_to_canonical(const uint64_t in[6], uint64_t out[6]);
+void zko_fq_op(int op, const uint64_t a[6], const uint64_t b[6], uint64_t out[6]);   /* 0 add, 1 sub, 2 Montgomery mul */
 int  zko_g1_is_on_curve(const uint64_t p[12]);
 void zko_g1_add(const uint64_t a[12], const uint64_t b[12], uint64_t out[12]);
 void zko_g1_neg(const uint64_t a[12], uint64_t out[12]);

@@ -221,6 +221,15 @@ void zko_fq_to_canonical(const uint64_t in[6], uint64_t out[6]) {
     q_mul(&r, &a, &one);
     memcpy(out, r.l, 48);
 }
+void zko_fq_op(int op, const uint64_t a[6], const uint64_t b[6], uint64_t out[6]) {   /* 0 add, 1 sub, 2 mul (Montgomery) */
+    fq x, y, r;
+    memcpy(x.l, a, 48);
+    memcpy(y.l, b, 48);
+    if (op == 0) q_add(&r, &x, &y);
+    else if (op == 1) q_sub(&r, &x, &y);
+    else q_mul(&r, &x, &y);
+    memcpy(out, r.l, 48);
+}
 int zko_g1_is_on_curve(const uint64_t p[12]) {
     fq x, y, l, r, b;
     memcpy(x.l, p, 48);

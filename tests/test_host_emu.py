@@ -23,6 +23,20 @@ def test_fp_cuh_host_emulation(tmp_path):
     assert out.stdout.count("ok") == 10, out.stdout[-2000:]
 
 
+def test_fq381_and_g1_host_emulation(tmp_path):
+    """csrc/fq381.cuh (12-limb Montgomery product of the BLS12-381 base field) and csrc/g1.cuh (XYZZ group law, inversion,
+    affine conversion) compiled for the host, against the C oracle's 6x64-limb field and Jacobian arithmetic"""
+    exe = str(tmp_path / "emu_g1")
+    cmd = ["g++", "-O1", "-std=c++17", "-DZK_HOST_EMU", "-x", "c++",
+           "-I", os.path.join(ROOT, "zk_cryptography_research_implementations_b200", "csrc"),
+           os.path.join(ROOT, "tests", "host_emu", "emu_g1.cpp"), os.path.join(ROOT, "oracle", "zkoracle.c"),
+           os.path.join(ROOT, "oracle", "zkoracle_kzg.c"), "-o", exe]
+    subprocess.check_call(cmd)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert out.stdout.count("ok") == 3, out.stdout[-2000:]
+
+
 def test_warp_keccak_lane_tables_match_their_generator():
     """the packed lane-routing words in csrc/dev_transcript.cuh are exactly what tools/gen_keccak_lanes.py derives (and
     checks against a textbook Keccak-f[1600] and hashlib's SHA3-256)"""

@@ -104,6 +104,16 @@ SIGNATURES = {
     "zk_prove_basic_sharded": (C.c_int, [vp, vp, vp, u64p, u64p, u64p, u64p, C.c_uint32, C.c_uint64]),
     "zk_gkr_prove_wide_sharded": (C.c_int, [vp, vp, vp, u64p, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint32, C.c_uint64]),
     "zk_mle_evaluate_sharded": (C.c_int, [vp, vp, u64p, C.c_uint32, u64p]),
+    "zk_kzg_setup_create": (C.c_int, [vp, u64p, C.c_uint32, C.POINTER(vp)]),
+    "zk_kzg_setup_from_points": (C.c_int, [vp, u64p, C.c_uint32, C.POINTER(vp)]),
+    "zk_kzg_setup_free": (None, [vp, vp]),
+    "zk_kzg_setup_num_vars": (C.c_uint32, [vp]),
+    "zk_kzg_setup_points": (C.c_int, [vp, vp, C.c_uint32, u64p]),
+    "zk_kzg_commit": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p]),
+    "zk_kzg_commit_device": (C.c_int, [vp, vp, vp, u64p]),
+    "zk_kzg_open": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint32, u64p, u64p]),
+    "zk_kzg_open_device": (C.c_int, [vp, vp, vp, u64p, C.c_uint32, u64p, u64p]),
+    "zk_g1_msm": (C.c_int, [vp, u64p, u64p, C.c_uint64, u64p]),
     "zk_arith_probe": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

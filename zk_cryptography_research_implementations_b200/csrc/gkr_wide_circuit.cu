@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "gkr_wide.h"
+#include "scan.cuh"
 
 using namespace zk;
 
@@ -26,9 +27,8 @@ using namespace zk;
     } while (0)
 
 namespace {
-typedef unsigned long long u64;
-constexpr int kScanItems = 8;                          // items per thread of the scan kernels
-constexpr int kScanChunk = kThreads * kScanItems;      // items per block
+using zk::scan::u64;
+using zk::scan::kScanChunk;
 
 inline int blocks_for(const zk_ctx* ctx, uint64_t work, int bps = 8) {
     uint64_t blocks = (work + kThreads - 1) / kThreads, cap = (uint64_t)ctx->sm_count * bps;
@@ -81,66 +81,6 @@ __global__ void __launch_bounds__(kThreads) histogram_kernel(const uint32_t* key
         if (key[i] < n_keys) atomicAdd(off + key[i] + 1, 1ull);   // an out-of-range key was flagged by validate_gates_kernel: never an array position
 }
 
-// inclusive scan of `data[0..n)` in three launches: per-chunk totals, a one-block scan of the totals, the chunks again
-__device__ __forceinline__ u64 block_exclusive_scan(u64 v, u64* total) {   // v: this thread's value; returns the sum of all lower threads'
-    __shared__ u64 warp_tot[kThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        u64 o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-    }
-    __syncthreads();   // protects warp_tot against the previous call's readers
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    u64 base = 0, all = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-        if (w < warp) base += warp_tot[w];
-        all += warp_tot[w];
-    }
-    *total = all;
-    return base + inc - v;
-}
-__global__ void __launch_bounds__(kThreads) scan_chunk_totals_kernel(const u64* data, uint64_t n, u64* chunk_tot) {
-    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk + (uint64_t)threadIdx.x * kScanItems;
-    u64 s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
-        if (base + k < n) s += data[base + k];
-    u64 total;
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) chunk_tot[blockIdx.x] = total;
-}
-__global__ void __launch_bounds__(kThreads) scan_totals_kernel(u64* chunk_tot, uint64_t n_chunks) {   // one block: exclusive scan in place
-    u64 carry = 0;
-    for (uint64_t t0 = 0; t0 < n_chunks; t0 += kThreads) {
-        const uint64_t i = t0 + threadIdx.x;
-        const u64 v = i < n_chunks ? chunk_tot[i] : 0;
-        u64 total;
-        const u64 ex = block_exclusive_scan(v, &total);
-        if (i < n_chunks) chunk_tot[i] = carry + ex;
-        carry += total;
-    }
-}
-__global__ void __launch_bounds__(kThreads) scan_apply_kernel(u64* data, uint64_t n, const u64* chunk_prefix) {
-    const uint64_t base = (uint64_t)blockIdx.x * kScanChunk + (uint64_t)threadIdx.x * kScanItems;
-    u64 v[kScanItems], s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        v[k] = base + k < n ? data[base + k] : 0;
-        s += v[k];
-    }
-    u64 total;
-    u64 run = chunk_prefix[blockIdx.x] + block_exclusive_scan(s, &total);
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        run += v[k];
-        if (base + k < n) data[base + k] = run;
-    }
-}
-
 // gate i goes to the next free place of its bucket (cursor starts as a copy of off[0..n_keys))
 __global__ void __launch_bounds__(kThreads) scatter_gates_kernel(const uint32_t* key, const uint32_t* x, const uint32_t* y, const uint8_t* op, uint64_t n,
                                                                  uint64_t n_keys, u64* cursor, uint32_t* sx, uint32_t* sy, uint8_t* so) {
@@ -170,10 +110,7 @@ int build_csr_device(zk_ctx* ctx, Staging& st, uint64_t n_keys, uint64_t n, cons
     u64* off = reinterpret_cast<u64*>(out->off);
     ZK_CUDA(cudaMemsetAsync(off, 0, (n_keys + 1) * sizeof(u64), ctx->stream));
     if (n) histogram_kernel<<<blocks_for(ctx, n), kThreads, 0, ctx->stream>>>(key, n, n_keys, off);
-    const uint64_t total = n_keys + 1, n_chunks = (total + kScanChunk - 1) / kScanChunk;
-    scan_chunk_totals_kernel<<<(unsigned)n_chunks, kThreads, 0, ctx->stream>>>(off, total, st.chunk_tot);
-    scan_totals_kernel<<<1, kThreads, 0, ctx->stream>>>(st.chunk_tot, n_chunks);
-    scan_apply_kernel<<<(unsigned)n_chunks, kThreads, 0, ctx->stream>>>(off, total, st.chunk_tot);
+    zk::scan::inclusive_scan(ctx->stream, off, n_keys + 1, st.chunk_tot);
     ZK_CUDA(cudaMemcpyAsync(st.cursor, off, n_keys * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
     if (n) scatter_gates_kernel<<<blocks_for(ctx, n), kThreads, 0, ctx->stream>>>(key, x, y, st.op, n, n_keys, st.cursor, out->x, out->y, out->op);
     ctx->launches += 5;

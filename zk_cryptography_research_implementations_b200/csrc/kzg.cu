@@ -1,0 +1,634 @@
+// kzg.cu -- multilinear KZG over BLS12-381 G1 on the GPU: the input commitment of succinct GKR
+// (gkr/src/succinct_gkr_protocol.rs:35-169 -> multilinear_kzg/src/multilinear_kzg.rs:25-127, trusted_setup.rs:12-63).
+//
+// The reference commits with `sum_i power_i.mul_bigint(value_i)` -- 2^n independent double-and-add scalar
+// multiplications -- and opens with n more such sums over the full setup, each against a quotient "blown up" to 2^n
+// entries (multilinear_kzg.rs:93-108, :183-214).  Here:
+//   * every sum is one bucket-method multi-scalar multiplication: signed c-bit digits of the canonical scalars, a
+//     histogram / scan / scatter that groups the (window, digit) occurrences (no sort), one thread per bucket adding
+//     affine points into an XYZZ accumulator (g1.cuh), running sums per bucket chunk, and a host finish of ~300 group
+//     operations (window combine + one inversion for the affine result);
+//   * the blow-up is never materialised: the quotient of round k repeats with period 2^(n-k-1), so its sum against the
+//     setup equals its sum against the setup FOLDED k+1 times (S_{k+1}[j] = S_k[j] + S_k[j + half]) -- the Lagrange basis
+//     of the remaining variables -- which is built once per setup.  Openings cost 2^n point additions in total, not n 2^n;
+//   * f - v is never formed: the quotient hi - lo does not see the constant, and v falls out of the last fold.
+// Group elements leave in affine form (canonical), so neither the coordinate system nor the order of the additions can show
+// in a result: outputs are bit-identical to the reference's `P::G1` values converted with `into_affine()`.
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+#include "g1.cuh"
+#include "host_curve.h"
+#include "scan.cuh"
+
+using namespace zk;
+
+#define ZK_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) {                                            \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); \
+            return ZK_ERR_CUDA;                                              \
+        }                                                                    \
+    } while (0)
+
+namespace {
+typedef Fp<BLS12_381_FR> Fr;
+typedef unsigned long long u64;
+constexpr int kMsmThreads = 128;     // the group law needs ~200 registers: small blocks keep the SMs evenly filled
+constexpr int kFixedWindows = 32;    // fixed-base table of the generator: 32 windows of 8 bits
+
+struct MsmPlan {
+    int c;            // window width in bits (signed digits in [-2^(c-1), 2^(c-1)])
+    int W;            // windows = ceil(256 / c): the top window also takes the last carry (scalars are < 2^255)
+    uint32_t B;       // buckets per window = 2^(c-1); bucket b holds the points whose digit is +-(b + 1)
+    uint32_t S;       // buckets per running-sum chunk
+};
+MsmPlan plan_for(uint64_t n) {
+    int c = n >= (1u << 20) ? 16 : n >= (1u << 16) ? 13 : n >= (1u << 12) ? 10 : n >= (1u << 8) ? 7 : 4;
+    if (const char* e = getenv("ZKB200_MSM_WINDOW")) {
+        const int v = atoi(e);
+        if (v >= 2 && v <= 16) c = v;
+    }
+    MsmPlan p;
+    p.c = c;
+    p.W = (256 + c - 1) / c;
+    p.B = 1u << (c - 1);
+    p.S = p.B >= 4096 ? 128 : p.B >= 64 ? 16 : p.B;
+    return p;
+}
+
+// ---------------------------------------------------------------- 16-byte vector moves of points
+__device__ __forceinline__ G1Affine load_affine(const G1Affine* p) {
+    G1Affine r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d[i] = __ldg(s + i);
+    return r;
+}
+__device__ __forceinline__ void store_affine(G1Affine* p, const G1Affine& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d[i] = s[i];
+}
+__device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz* p) {
+    G1Xyzz r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) d[i] = s[i];
+    return r;
+}
+__device__ __forceinline__ void store_xyzz(G1Xyzz* p, const G1Xyzz& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------- scalars -> signed digits
+// `into_bigint()`: the canonical integer of a Montgomery-form scalar
+__device__ __forceinline__ void canonical_scalar(uint32_t k[8], const Fe& s) {
+    Fe one, r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) one.v[i] = i == 0 ? 1u : 0u;
+    Fr::mont_mul(r, s, one);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k[i] = r.v[i];
+}
+__device__ __forceinline__ uint32_t window_bits(const uint32_t k[8], int lo, int c) {
+    const int word = lo >> 5, sh = lo & 31;
+    uint64_t v = k[word];
+    if (word + 1 < 8) v |= (uint64_t)k[word + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+// calls f(window, bucket, negative) for every non-zero digit of k
+template <typename Fn> __device__ __forceinline__ void for_each_digit(const uint32_t k[8], const MsmPlan& pl, Fn f) {
+    uint32_t carry = 0;
+    for (int w = 0; w < pl.W; ++w) {
+        uint32_t d = window_bits(k, w * pl.c, pl.c) + carry;
+        carry = 0;
+        bool neg = false;
+        if (d > pl.B) {
+            d = (1u << pl.c) - d;
+            neg = true;
+            carry = 1;
+        }
+        if (d) f(w, d - 1u, neg);
+    }
+}
+
+// off[key + 1] += 1 for every non-zero digit (off zeroed before); key = window * B + bucket
+__global__ void __launch_bounds__(kThreads) msm_count_kernel(const Fe* scalars, uint64_t n, MsmPlan pl, u64* off) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t k[8];
+        canonical_scalar(k, scalars[i]);
+        for_each_digit(k, pl, [&](int w, uint32_t b, bool) { atomicAdd(off + (uint64_t)w * pl.B + b + 1, 1ull); });
+    }
+}
+// entry = point index | sign << 31, to the next free place of its bucket (cursor starts as a copy of off[0..W*B))
+__global__ void __launch_bounds__(kThreads) msm_scatter_kernel(const Fe* scalars, uint64_t n, MsmPlan pl, u64* cursor, uint32_t* sorted) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t k[8];
+        canonical_scalar(k, scalars[i]);
+        for_each_digit(k, pl, [&](int w, uint32_t b, bool neg) {
+            const u64 p = atomicAdd(cursor + (uint64_t)w * pl.B + b, 1ull);
+            sorted[p] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+        });
+    }
+}
+
+// ---------------------------------------------------------------- bucket sums: one thread per (window, bucket)
+__global__ void __launch_bounds__(kMsmThreads) msm_bucket_kernel(const u64* off, const uint32_t* sorted, const G1Affine* bases, uint64_t n_keys,
+                                                                 G1Xyzz* buckets) {
+    const uint64_t key = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    G1Xyzz acc = G1::infinity();
+    const u64 lo = off[key], hi = off[key + 1];
+#pragma unroll 1
+    for (u64 e = lo; e < hi; ++e) {
+        const uint32_t v = sorted[e];
+        const G1Affine p = load_affine(bases + (v & 0x7fffffffu));
+        G1::add_affine(acc, p, (v >> 31) != 0);
+    }
+    store_xyzz(buckets + key, acc);
+}
+
+// ---------------------------------------------------------------- window sums: sum_b (b + 1) bucket[b]
+// level 1: one thread per chunk of S buckets: run = sum of the chunk, acc = sum (b - lo + 1) bucket[b]
+__global__ void __launch_bounds__(kMsmThreads) msm_chunk_kernel(const G1Xyzz* buckets, uint64_t n_chunks, uint32_t S, G1Xyzz* chunk_acc,
+                                                                G1Xyzz* chunk_run) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_chunks) return;
+    G1Xyzz run = G1::infinity(), acc = G1::infinity();
+    const G1Xyzz* b = buckets + t * S;
+#pragma unroll 1
+    for (int i = (int)S - 1; i >= 0; --i) {
+        const G1Xyzz v = load_xyzz(b + i);
+        G1::add(run, v);
+        G1::add(acc, run);
+    }
+    store_xyzz(chunk_acc + t, acc);
+    store_xyzz(chunk_run + t, run);
+}
+// level 2: one thread per window over its nT chunks: sum_t acc_t + S * sum_t t run_t   (S a power of two)
+__global__ void __launch_bounds__(32) msm_window_kernel(const G1Xyzz* chunk_acc, const G1Xyzz* chunk_run, uint32_t nT, uint32_t S, G1Xyzz* win) {
+    const int w = blockIdx.x;   // one block (one working thread) per window: the windows run on different SMs
+    if (threadIdx.x != 0) return;
+    G1Xyzz a = G1::infinity(), run = G1::infinity(), t_sum = G1::infinity();
+    const G1Xyzz* ca = chunk_acc + (uint64_t)w * nT;
+    const G1Xyzz* cr = chunk_run + (uint64_t)w * nT;
+#pragma unroll 1
+    for (int t = (int)nT - 1; t >= 0; --t) {
+        const G1Xyzz va = load_xyzz(ca + t);
+        G1::add(a, va);
+        if (t >= 1) {
+            const G1Xyzz vr = load_xyzz(cr + t);
+            G1::add(run, vr);
+            G1::add(t_sum, run);
+        }
+    }
+#pragma unroll 1
+    for (uint32_t s = S; s > 1; s >>= 1) G1::dbl(t_sum, t_sum);
+    G1::add(a, t_sum);
+    store_xyzz(win + w, a);
+}
+
+// ---------------------------------------------------------------- trusted setup on the GPU
+// compute_lagrange_basis (trusted_setup.rs:26-52): basis[index] = prod_i (bit_i(index) ? tau_i : 1 - tau_i), variable 0 = top bit
+__global__ void __launch_bounds__(kThreads) lagrange_basis_kernel(const Fe* taus, uint32_t n, const __grid_constant__ Fe one, Fe* out) {
+    const uint64_t len = 1ull << n, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t index = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; index < len; index += stride) {
+        Fe e = one;
+        for (uint32_t i = 0; i < n; ++i) {
+            Fe f = taus[i];
+            if (!((index >> (n - 1 - i)) & 1)) Fr::sub(f, one, f);
+            Fr::mont_mul(e, e, f);
+        }
+        out[index] = e;
+    }
+}
+// compute_g1_powers_of_tau (trusted_setup.rs:54-63): out[i] = scalar_i * G from the byte-window table of the generator
+// (table[w][d] = d * 256^w * G, d = 0 unused), then one inversion per point for the affine form
+__global__ void __launch_bounds__(kMsmThreads) fixed_base_kernel(const Fe* scalars, uint64_t n, const G1Affine* table, G1Affine* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[8];
+    canonical_scalar(k, scalars[i]);
+    G1Xyzz acc = G1::infinity();
+#pragma unroll 1
+    for (int w = 0; w < kFixedWindows; ++w) {
+        const uint32_t d = (k[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+        if (d) {
+            const G1Affine p = load_affine(table + w * 256 + d);
+            G1::add_affine(acc, p);
+        }
+    }
+    G1Affine r;
+    if (G1::is_inf(acc)) {
+        r.x = Fq381::zero();
+        r.y = Fq381::zero();
+    } else {
+        Fq i3;
+        G1::inv(i3, acc.zzz);
+        G1::to_affine_with_inverse(r, acc, i3);
+    }
+    store_affine(out + i, r);
+}
+// the setup folded once more: out[j] = in[j] + in[j + half]
+__global__ void __launch_bounds__(kMsmThreads) fold_points_kernel(const G1Affine* in, uint64_t half, G1Affine* out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= half) return;
+    G1Xyzz acc = G1::from_affine(load_affine(in + j));
+    G1::add_affine(acc, load_affine(in + j + half));
+    G1Affine r;
+    if (G1::is_inf(acc)) {
+        r.x = Fq381::zero();
+        r.y = Fq381::zero();
+    } else {
+        Fq i3;
+        G1::inv(i3, acc.zzz);
+        G1::to_affine_with_inverse(r, acc, i3);
+    }
+    store_affine(out + j, r);
+}
+// flags |= 1 if a point is neither infinity nor on the curve (coordinates canonical and y^2 == x^3 + 4)
+__global__ void __launch_bounds__(kThreads) check_points_kernel(const G1Affine* pts, uint64_t n, unsigned* flags) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const G1Affine p = load_affine(pts + i);
+        if (G1::is_inf(p)) continue;
+        Fq l, r, b, t;
+        // canonical: adding zero through the reducing adder leaves a canonical value unchanged
+        Fq z = Fq381::zero();
+        Fq381::add(t, p.x, z);
+        bool ok = Fq381::eq(t, p.x);
+        Fq381::add(t, p.y, z);
+        ok = ok && Fq381::eq(t, p.y);
+        {
+            constexpr uint32_t bm[12] = ZKC_B_32;   // 4 in Montgomery form
+#pragma unroll
+            for (int k = 0; k < 12; ++k) b.v[k] = bm[k];
+        }
+        Fq381::sqr(l, p.y);
+        Fq381::sqr(r, p.x);
+        Fq381::mul(r, r, p.x);
+        Fq381::add(r, r, b);
+        if (!ok || !Fq381::eq(l, r)) atomicOr(flags, 1u);
+    }
+}
+
+// one round of open_and_prove (multilinear_kzg.rs:78-119): q[j] = hi - lo (the quotient, :166-181) and, in place,
+// cur[j] = lo + r (hi - lo) (the remainder, partial_evaluate at variable 0)
+__global__ void __launch_bounds__(kThreads) quotient_fold_kernel(Fe* cur, uint64_t half, const __grid_constant__ Fe r, Fe* q) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += stride) {
+        const Fe lo = cur[j], hi = cur[j + half];
+        Fe d, m;
+        Fr::sub(d, hi, lo);
+        Fr::mont_mul(m, d, r);
+        Fr::add(m, m, lo);
+        q[j] = d;
+        cur[j] = m;
+    }
+}
+
+int blocks_for(const zk_ctx* ctx, uint64_t work, int threads, int bps) {
+    uint64_t blocks = (work + threads - 1) / threads, cap = (uint64_t)ctx->sm_count * bps;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+}  // namespace
+
+// ---------------------------------------------------------------- the setup object
+struct zk_kzg_setup {
+    uint32_t n = 0;                       // variables
+    int device = 0;
+    std::vector<G1Affine*> level;         // level[k]: the setup folded k times, 2^(n-k) points (level[0] = g1_powers_of_tau)
+    G1Affine* storage = nullptr;          // all levels, 2^(n+1) points
+    // workspace of the multi-scalar multiplication, sized for 2^n points
+    u64 *off = nullptr, *cursor = nullptr, *scan_scratch = nullptr;
+    uint32_t* sorted = nullptr;
+    G1Xyzz *buckets = nullptr, *chunk_acc = nullptr, *chunk_run = nullptr, *win = nullptr;
+    HG1Xyzz* win_host = nullptr;          // pinned
+    Fe *cur = nullptr, *quot = nullptr;   // open_and_prove: the remainder and quotient tables
+    uint64_t cap_points = 0, cap_keys = 0, cap_chunks = 0;
+};
+
+namespace {
+int msm_reserve(zk_ctx* ctx, zk_kzg_setup* s, uint64_t max_points) {
+    uint64_t keys = 0, entries = 0, chunks = 0;
+    for (uint64_t p2 = 1; p2 / 2 < max_points; p2 <<= 1) {   // every size open_and_prove will use, and max_points itself
+        const uint64_t n = std::min(p2, max_points);
+        const MsmPlan pl = plan_for(n);
+        keys = std::max<uint64_t>(keys, (uint64_t)pl.W * pl.B);
+        entries = std::max<uint64_t>(entries, n * pl.W);
+        chunks = std::max<uint64_t>(chunks, (uint64_t)pl.W * (pl.B / pl.S));
+    }
+    if (getenv("ZKB200_MSM_WINDOW")) {   // a forced window width: size for the widest plan
+        keys = std::max<uint64_t>(keys, 128ull * 32768);
+        entries = std::max<uint64_t>(entries, max_points * 128);
+        chunks = std::max<uint64_t>(chunks, 128ull * 32768);
+    }
+    if (max_points <= s->cap_points && keys <= s->cap_keys && chunks <= s->cap_chunks) return ZK_OK;
+    if (s->cap_points) return fail(ctx, ZK_ERR_ARG, "multi-scalar multiplication workspace is sized once");
+    ZK_CUDA(cudaMalloc(&s->off, (keys + 1) * sizeof(u64)));
+    ZK_CUDA(cudaMalloc(&s->cursor, keys * sizeof(u64)));
+    ZK_CUDA(cudaMalloc(&s->scan_scratch, (scan::scan_chunks(keys + 1) + 1) * sizeof(u64)));
+    ZK_CUDA(cudaMalloc(&s->sorted, entries * sizeof(uint32_t)));
+    ZK_CUDA(cudaMalloc(&s->buckets, keys * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaMalloc(&s->chunk_acc, chunks * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaMalloc(&s->chunk_run, chunks * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaMalloc(&s->win, 128 * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaHostAlloc(&s->win_host, 128 * sizeof(HG1Xyzz), cudaHostAllocDefault));
+    s->cap_points = max_points;
+    s->cap_keys = keys;
+    s->cap_chunks = chunks;
+    return ZK_OK;
+}
+
+// sum_i scalars[i] * bases[i] over n device-resident pairs -> affine result on the host
+int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* bases, uint64_t n, HG1Affine* out) {
+    static_assert(sizeof(HG1Xyzz) == sizeof(G1Xyzz) && sizeof(HG1Affine) == sizeof(G1Affine), "host and device point layouts");
+    if (n >= (1ull << 31)) return fail(ctx, ZK_ERR_ARG, "multi-scalar multiplication over 2^31 or more points");
+    const MsmPlan pl = plan_for(n);
+    const uint64_t keys = (uint64_t)pl.W * pl.B;
+    const uint32_t nT = pl.B / pl.S;
+    cudaStream_t st = ctx->stream;
+    ZK_CUDA(cudaMemsetAsync(s->off, 0, (keys + 1) * sizeof(u64), st));
+    msm_count_kernel<<<blocks_for(ctx, n, kThreads, 8), kThreads, 0, st>>>(scalars, n, pl, s->off);
+    scan::inclusive_scan(st, s->off, keys + 1, s->scan_scratch);
+    ZK_CUDA(cudaMemcpyAsync(s->cursor, s->off, keys * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    msm_scatter_kernel<<<blocks_for(ctx, n, kThreads, 8), kThreads, 0, st>>>(scalars, n, pl, s->cursor, s->sorted);
+    msm_bucket_kernel<<<(unsigned)((keys + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->off, s->sorted, bases, keys, s->buckets);
+    const uint64_t n_chunks = (uint64_t)pl.W * nT;
+    msm_chunk_kernel<<<(unsigned)((n_chunks + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->buckets, n_chunks, pl.S, s->chunk_acc, s->chunk_run);
+    msm_window_kernel<<<pl.W, 32, 0, st>>>(s->chunk_acc, s->chunk_run, nT, pl.S, s->win);
+    ctx->launches += 8;
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpyAsync(s->win_host, s->win, (size_t)pl.W * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    // result = sum_w 2^(c w) window_w, most significant window first
+    HG1Xyzz acc = HostG1::infinity();
+    for (int w = pl.W - 1; w >= 0; --w) {
+        for (int k = 0; k < pl.c; ++k) acc = HostG1::dbl(acc);
+        acc = HostG1::add(acc, s->win_host[w]);
+    }
+    *out = HostG1::to_affine(acc);
+    return ZK_OK;
+}
+
+int require_fr(zk_ctx* ctx) {
+    if (ctx->fid != BLS12_381_FR) return fail(ctx, ZK_ERR_ARG, "multilinear KZG needs a BLS12-381 Fr context (the scalar field of the curve)");
+    return ZK_OK;
+}
+
+// level[k + 1] from level[k], k = 0..n-1
+int fold_levels(zk_ctx* ctx, zk_kzg_setup* s) {
+    for (uint32_t k = 0; k < s->n; ++k) {
+        const uint64_t half = 1ull << (s->n - k - 1);
+        fold_points_kernel<<<(unsigned)((half + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, ctx->stream>>>(s->level[k], half, s->level[k + 1]);
+        ++ctx->launches;
+    }
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+int setup_alloc(zk_ctx* ctx, uint32_t n, std::unique_ptr<zk_kzg_setup, void (*)(zk_kzg_setup*)>& s) {
+    s->n = n;
+    s->device = ctx->device;
+    const uint64_t len = 1ull << n;
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaMalloc(&s->storage, 2 * len * sizeof(G1Affine)));
+    s->level.resize(n + 1);
+    uint64_t o = 0;
+    for (uint32_t k = 0; k <= n; ++k) {
+        s->level[k] = s->storage + o;
+        o += len >> k;
+    }
+    ZK_CUDA(cudaMalloc(&s->cur, len * sizeof(Fe)));
+    ZK_CUDA(cudaMalloc(&s->quot, (len / 2 + 1) * sizeof(Fe)));
+    return msm_reserve(ctx, s.get(), len);
+}
+void setup_delete(zk_kzg_setup* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaFree(s->storage); cudaFree(s->off); cudaFree(s->cursor); cudaFree(s->scan_scratch); cudaFree(s->sorted);
+    cudaFree(s->buckets); cudaFree(s->chunk_acc); cudaFree(s->chunk_run); cudaFree(s->win); cudaFree(s->cur); cudaFree(s->quot);
+    if (s->win_host) cudaFreeHost(s->win_host);
+    delete s;
+}
+
+// table[w][d] = d * 256^w * G in affine form (d = 0: infinity), built on the host with one shared inversion
+void generator_table(std::vector<HG1Affine>& table) {
+    typedef HostFq F;
+    std::vector<HG1Xyzz> pts((size_t)kFixedWindows * 256, HostG1::infinity());
+    HG1Xyzz base = HostG1::from_affine(HostG1::generator());
+    for (int w = 0; w < kFixedWindows; ++w) {
+        HG1Xyzz cur = base;
+        for (int d = 1; d < 256; ++d) {
+            pts[(size_t)w * 256 + d] = cur;
+            cur = HostG1::add(cur, base);
+        }
+        base = cur;   // 256 * base
+    }
+    // Montgomery's trick over the ZZZ coordinates of the finite points
+    std::vector<HFq> prefix(pts.size());
+    HFq run = F::one();
+    for (size_t i = 0; i < pts.size(); ++i) {
+        prefix[i] = run;
+        if (!pts[i].is_inf()) run = F::mul(run, pts[i].zzz);
+    }
+    HFq inv = F::inv(run);
+    table.assign(pts.size(), HG1Affine{F::zero(), F::zero()});
+    for (size_t i = pts.size(); i-- > 0;) {
+        if (pts[i].is_inf()) continue;
+        const HFq i3 = F::mul(inv, prefix[i]);
+        inv = F::mul(inv, pts[i].zzz);
+        const HFq izz = F::mul(F::sqr(i3), F::sqr(pts[i].zz));
+        table[i] = HG1Affine{F::mul(pts[i].x, izz), F::mul(pts[i].y, i3)};
+    }
+}
+}  // namespace
+
+// ---------------------------------------------------------------- C-ABI
+extern "C" int zk_kzg_setup_create(zk_ctx* ctx, const uint64_t* taus, uint32_t n, zk_kzg_setup** out) {
+    int rc = require_fr(ctx);
+    if (rc) return rc;
+    if (n == 0) return fail(ctx, ZK_ERR_ASSERT, "requires at least one variable");   // trusted_setup.rs:28
+    if (n > 28) return fail(ctx, ZK_ERR_ARG, "trusted setup over more than 28 variables");
+    std::unique_ptr<zk_kzg_setup, void (*)(zk_kzg_setup*)> s(new zk_kzg_setup(), setup_delete);
+    rc = setup_alloc(ctx, n, s);
+    if (rc) return rc;
+    const uint64_t len = 1ull << n;
+    std::vector<HG1Affine> table;
+    generator_table(table);
+    G1Affine* d_table = nullptr;
+    Fe* d_taus = nullptr;
+    ZK_CUDA(cudaMalloc(&d_table, table.size() * sizeof(G1Affine)));
+    std::unique_ptr<G1Affine, void (*)(G1Affine*)> g1(d_table, [](G1Affine* p) { cudaFree(p); });
+    ZK_CUDA(cudaMalloc(&d_taus, (size_t)n * sizeof(Fe)));
+    std::unique_ptr<Fe, void (*)(Fe*)> g2(d_taus, [](Fe* p) { cudaFree(p); });
+    ZK_CUDA(cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(d_taus, taus, (size_t)n * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    Fe one;
+    {
+        const HFe h = ctx->field.one();
+        memcpy(one.v, h.l, sizeof one);
+    }
+    lagrange_basis_kernel<<<blocks_for(ctx, len, kThreads, 8), kThreads, 0, ctx->stream>>>(d_taus, n, one, s->cur);
+    fixed_base_kernel<<<(unsigned)((len + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, ctx->stream>>>(s->cur, len, d_table, s->level[0]);
+    ctx->launches += 2;
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    rc = fold_levels(ctx, s.get());
+    if (rc) return rc;
+    *out = s.release();
+    return ZK_OK;
+}
+
+extern "C" int zk_kzg_setup_from_points(zk_ctx* ctx, const uint64_t* g1_points, uint32_t n, zk_kzg_setup** out) {
+    int rc = require_fr(ctx);
+    if (rc) return rc;
+    if (n == 0) return fail(ctx, ZK_ERR_ASSERT, "requires at least one variable");
+    if (n > 28) return fail(ctx, ZK_ERR_ARG, "trusted setup over more than 28 variables");
+    std::unique_ptr<zk_kzg_setup, void (*)(zk_kzg_setup*)> s(new zk_kzg_setup(), setup_delete);
+    rc = setup_alloc(ctx, n, s);
+    if (rc) return rc;
+    const uint64_t len = 1ull << n;
+    ZK_CUDA(cudaMemcpyAsync(s->level[0], g1_points, len * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned* flags = reinterpret_cast<unsigned*>(s->off);
+    ZK_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned), ctx->stream));
+    check_points_kernel<<<blocks_for(ctx, len, kThreads, 8), kThreads, 0, ctx->stream>>>(s->level[0], len, flags);
+    ++ctx->launches;
+    unsigned h = 0;
+    ZK_CUDA(cudaMemcpyAsync(&h, flags, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h) return fail(ctx, ZK_ERR_ARG, "a setup point is not on the curve");
+    rc = fold_levels(ctx, s.get());
+    if (rc) return rc;
+    *out = s.release();
+    return ZK_OK;
+}
+
+extern "C" void zk_kzg_setup_free(zk_ctx* ctx, zk_kzg_setup* s) {
+    if (!s) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    setup_delete(s);
+}
+extern "C" uint32_t zk_kzg_setup_num_vars(const zk_kzg_setup* s) { return s->n; }
+
+extern "C" int zk_kzg_setup_points(zk_ctx* ctx, const zk_kzg_setup* s, uint32_t level, uint64_t* out) {
+    if (level > s->n) return fail(ctx, ZK_ERR_ARG, "setup level out of range");
+    ZK_CUDA(cudaMemcpyAsync(out, s->level[level], ((size_t)1 << (s->n - level)) * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+extern "C" int zk_kzg_commit_device(zk_ctx* ctx, zk_kzg_setup* s, const zk_table* t, uint64_t out[12]) {
+    int rc = require_fr(ctx);
+    if (rc) return rc;
+    if (t->len != (1ull << s->n)) return fail(ctx, ZK_ERR_ASSERT, "Polynomial evaluation must match g1 length");   // multilinear_kzg.rs:29-33
+    HG1Affine r;
+    rc = g1_msm(ctx, s, t->d, s->level[0], t->len, &r);
+    if (rc) return rc;
+    memcpy(out, &r, sizeof r);
+    return ZK_OK;
+}
+extern "C" int zk_kzg_commit(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* vals, uint64_t len, uint64_t out[12]) {
+    int rc = require_fr(ctx);
+    if (rc) return rc;
+    if (len != (1ull << s->n)) return fail(ctx, ZK_ERR_ASSERT, "Polynomial evaluation must match g1 length");
+    ZK_CUDA(cudaMemcpyAsync(s->cur, vals, (size_t)len * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    zk_table t;
+    t.d = s->cur;
+    t.len = t.cap = len;
+    t.owned = false;
+    return zk_kzg_commit_device(ctx, s, &t, out);
+}
+
+namespace {
+// `cur` holds the polynomial (it is consumed)
+int open_impl(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* opening, uint64_t eval[4], uint64_t* proofs) {
+    const uint32_t n = s->n;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t half = 1ull << (n - i - 1);
+        Fe r;
+        memcpy(r.v, opening + 4 * i, sizeof r);
+        quotient_fold_kernel<<<blocks_for(ctx, half, kThreads, 8), kThreads, 0, ctx->stream>>>(s->cur, half, r, s->quot);
+        ++ctx->launches;
+        HG1Affine pr;
+        int rc = g1_msm(ctx, s, s->quot, s->level[i + 1], half, &pr);
+        if (rc) return rc;
+        memcpy(proofs + 12 * i, &pr, sizeof pr);
+    }
+    ZK_CUDA(cudaMemcpyAsync(eval, s->cur, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+int open_checks(zk_ctx* ctx, const zk_kzg_setup* s, uint64_t len, uint32_t n_opening) {
+    int rc = require_fr(ctx);
+    if (rc) return rc;
+    if (len == 0 || (len & (len - 1))) return fail(ctx, ZK_ERR_ASSERT, "Evaluated values must be a power of 2");
+    uint32_t nv = 0;
+    while ((1ull << nv) < len) ++nv;
+    if (nv != n_opening) return fail(ctx, ZK_ERR_ASSERT, "number of polynomial variables must match length of opening values");   // :56-60
+    if (n_opening != s->n) return fail(ctx, ZK_ERR_ASSERT, "Opening values must match number of variables from trusted setup"); // :61-65
+    return ZK_OK;
+}
+}  // namespace
+
+extern "C" int zk_kzg_open_device(zk_ctx* ctx, zk_kzg_setup* s, const zk_table* t, const uint64_t* opening, uint32_t n_opening,
+                                  uint64_t eval[4], uint64_t* proofs) {
+    int rc = open_checks(ctx, s, t->len, n_opening);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(s->cur, t->d, (size_t)t->len * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
+    return open_impl(ctx, s, opening, eval, proofs);
+}
+extern "C" int zk_kzg_open(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* vals, uint64_t len, const uint64_t* opening, uint32_t n_opening,
+                           uint64_t eval[4], uint64_t* proofs) {
+    int rc = open_checks(ctx, s, len, n_opening);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(s->cur, vals, (size_t)len * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    return open_impl(ctx, s, opening, eval, proofs);
+}
+
+// sum_i scalars[i] * points[i] for caller-supplied points (host arrays; any n >= 1)
+extern "C" int zk_g1_msm(zk_ctx* ctx, const uint64_t* scalars, const uint64_t* points, uint64_t n, uint64_t out[12]) {
+    int rc = require_fr(ctx);
+    if (rc) return rc;
+    if (n == 0) {
+        memset(out, 0, 96);
+        return ZK_OK;
+    }
+    std::unique_ptr<zk_kzg_setup, void (*)(zk_kzg_setup*)> s(new zk_kzg_setup(), setup_delete);
+    s->device = ctx->device;
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    ZK_CUDA(cudaMalloc(&s->storage, n * sizeof(G1Affine)));
+    ZK_CUDA(cudaMalloc(&s->cur, n * sizeof(Fe)));
+    rc = msm_reserve(ctx, s.get(), n);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(s->storage, points, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(s->cur, scalars, n * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned* flags = reinterpret_cast<unsigned*>(s->off);
+    ZK_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned), ctx->stream));
+    check_points_kernel<<<blocks_for(ctx, n, kThreads, 8), kThreads, 0, ctx->stream>>>(s->storage, n, flags);
+    unsigned h = 0;
+    ZK_CUDA(cudaMemcpyAsync(&h, flags, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h) return fail(ctx, ZK_ERR_ARG, "a point is not on the curve");
+    HG1Affine r;
+    rc = g1_msm(ctx, s.get(), s->cur, s->storage, n, &r);
+    if (rc) return rc;
+    memcpy(out, &r, sizeof r);
+    return ZK_OK;
+}
