@@ -304,6 +304,18 @@ int  zk_kzg_open(zk_ctx *, zk_kzg_setup *, const uint64_t *evaluated_values, uin
                  uint32_t n_opening, uint64_t evaluation[4], uint64_t *proofs /* 12 * n */);
 int  zk_kzg_open_device(zk_ctx *, zk_kzg_setup *, const zk_table *, const uint64_t *opening_values, uint32_t n_opening,
                         uint64_t evaluation[4], uint64_t *proofs);
+/* The verifier's half, host only (no context, no GPU; the prover never calls these).  G2 points: affine x.c0, x.c1, y.c0,
+ * y.c1 (4 x 6 limbs, Montgomery; `G2Affine`'s coordinates), infinity all zero.
+ * compute_g2_powers_of_tau (trusted_setup.rs:65-78): out[i] = taus[i] * G2.  ZK_ERR_ASSERT for n == 0. */
+int  zk_kzg_g2_powers_of_tau(const uint64_t *taus, uint32_t n, uint64_t *out /* 24 * n */);
+/* MultilinearKZG::verify (multilinear_kzg.rs:132-159): e(C - v G1, G2) == prod_i e(Q_i, tau_i G2 - r_i G2), one product of
+ * Miller loops and one final exponentiation.  ZK_ERR_ASSERT "Number of opening values must match number of proofs". */
+int  zk_kzg_verify(const uint64_t *g2_powers_of_tau, uint32_t n_g2, const uint64_t commitment[12],
+                   const uint64_t *opening_values, uint32_t n_opening, const uint64_t evaluation[4], const uint64_t *proofs,
+                   uint32_t n_proofs, int *ok);
+int  zk_g1_is_on_curve(const uint64_t point[12]);
+void zk_g1_generator(uint64_t out[12]);
+void zk_g2_generator(uint64_t out[24]);
 /* sum_i scalars[i] * points[i] over caller-supplied host arrays (`.map(mul_bigint).sum()`); any n, points checked */
 int  zk_g1_msm(zk_ctx *, const uint64_t *scalars /* 4*n */, const uint64_t *points /* 12*n */, uint64_t n, uint64_t out[12]);
 

@@ -149,6 +149,29 @@ def test_small_valued_and_constant_polynomials(co, ctx_for, kzg):
         co.set_threads(1)
 
 
+def test_one_giant_bucket(co, ctx_for, kzg):
+    """2^16 equal scalars: every point lands in one bucket of the lowest window (all three levels of the bucket sum in
+    use); the Lagrange basis sums to one, so the commitment of the constant 3 is 3 G.  Two values = two giant buckets:
+    the polynomial is 5 - 2 x_last, checked through its opening."""
+    ctx = ctx_for(FR)
+    n = 16
+    rnd = random.Random(3)
+    taus = _fe(co, [rnd.randrange(R) for _ in range(n)])
+    setup = kzg.TrustedSetup.initialize_setup(ctx, taus)
+    three = _fe(co, [3])[0]
+    c = kzg.MultilinearKZG.commit_to_polynomial(np.tile(three, (1 << n, 1)), setup)
+    assert co.g1_to_ints(c)[0] == pk.g1_mul(pk.G1_GEN, 3)
+    vals = np.tile(three, (1 << n, 1))
+    vals[::2] = _fe(co, [5])[0]
+    opening = _fe(co, [rnd.randrange(R) for _ in range(n)])
+    c = kzg.MultilinearKZG.commit_to_polynomial(vals, setup)
+    tau_last = co.to_ints(FR, taus)[-1]
+    assert co.g1_to_ints(c)[0] == pk.g1_mul(pk.G1_GEN, (5 - 2 * tau_last) % R)
+    proof = kzg.MultilinearKZG.open_and_prove(vals, setup, opening)
+    assert co.to_ints(FR, proof.evaluation)[0] == (5 - 2 * co.to_ints(FR, opening)[-1]) % R
+    assert co.kzg_verify_trapdoor(taus, c, opening, proof.evaluation, proof.proofs)
+
+
 def test_degenerate_taus_put_infinity_into_the_setup(co, ctx_for, kzg):
     ctx = ctx_for(FR)
     taus = _fe(co, [0, 1, 5])

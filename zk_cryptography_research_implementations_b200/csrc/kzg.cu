@@ -6,8 +6,9 @@
 // entries (multilinear_kzg.rs:93-108, :183-214).  Here:
 //   * every sum is one bucket-method multi-scalar multiplication: signed c-bit digits of the canonical scalars, a
 //     histogram / scan / scatter that groups the (window, digit) occurrences (no sort), one thread per bucket adding
-//     affine points into an XYZZ accumulator (g1.cuh), running sums per bucket chunk, and a host finish of ~300 group
-//     operations (window combine + one inversion for the affine result);
+//     affine points into an XYZZ accumulator (g1.cuh), running sums per chunk of 16 buckets, the chunk results summed by
+//     bit planes of the chunk index (one warp per plane), and a host finish of ~450 group operations (one doubling per
+//     scalar bit, one addition per plane, one inversion for the affine result);
 //   * the blow-up is never materialised: the quotient of round k repeats with period 2^(n-k-1), so its sum against the
 //     setup equals its sum against the setup FOLDED k+1 times (S_{k+1}[j] = S_k[j] + S_k[j + half]) -- the Lagrange basis
 //     of the remaining variables -- which is built once per setup.  Openings cost 2^n point additions in total, not n 2^n;
@@ -38,7 +39,14 @@ using namespace zk;
 namespace {
 typedef Fp<BLS12_381_FR> Fr;
 typedef unsigned long long u64;
-constexpr int kMsmThreads = 128;     // the group law needs ~200 registers: small blocks keep the SMs evenly filled
+#ifndef ZK_MSM_THREADS
+#define ZK_MSM_THREADS 128
+#endif
+#ifndef ZK_MSM_MIN_BLOCKS
+#define ZK_MSM_MIN_BLOCKS 3
+#endif
+constexpr int kMsmThreads = ZK_MSM_THREADS;   // the group law needs ~150-250 registers: small blocks keep the SMs evenly filled
+constexpr int kMaxPlanes = 128 * 16;  // windows x (bit planes of the chunk index + 1), widest plan
 constexpr int kFixedWindows = 32;    // fixed-base table of the generator: 32 windows of 8 bits
 
 struct MsmPlan {
@@ -57,7 +65,7 @@ MsmPlan plan_for(uint64_t n) {
     p.c = c;
     p.W = (256 + c - 1) / c;
     p.B = 1u << (c - 1);
-    p.S = p.B >= 4096 ? 128 : p.B >= 64 ? 16 : p.B;
+    p.S = p.B >= 16 ? 16 : p.B;
     return p;
 }
 
@@ -145,20 +153,104 @@ __global__ void __launch_bounds__(kThreads) msm_scatter_kernel(const Fe* scalars
     }
 }
 
-// ---------------------------------------------------------------- bucket sums: one thread per (window, bucket)
-__global__ void __launch_bounds__(kMsmThreads) msm_bucket_kernel(const u64* off, const uint32_t* sorted, const G1Affine* bases, uint64_t n_keys,
-                                                                 G1Xyzz* buckets) {
-    const uint64_t key = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (key >= n_keys) return;
+// ---------------------------------------------------------------- bucket sums
+// A bucket can hold anything from nothing to every point (small or equal scalars put whole tables into a handful of buckets,
+// and the top window of a width that does not divide 256 has only a few buckets in use), so the work is cut into pieces of
+// bounded size in three levels, none of which needs the host:
+//   level 0: every bucket is split into segments of <= kCap0 entries; one thread per segment adds its affine points;
+//   level 1: the segment sums of a bucket are grouped <= kCap1 at a time; one thread per group adds them;
+//   level 2: one thread per bucket takes its single group sum -- or, where a bucket still has several, its warp adds them
+//            lane-strided and folds the lanes with a butterfly.
+// In the common case (every bucket within kCap0) levels 1 and 2 are copies.
+constexpr uint32_t kCap0 = 128, kCap1 = 32;
+
+// seg[b + 1] = ceil((off[b + 1] - off[b]) / cap), seg[0] = 0; an inclusive scan turns it into segment offsets
+__global__ void __launch_bounds__(kThreads) msm_segments_kernel(const u64* off, uint64_t n_keys, uint32_t cap, u64* seg) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_keys; b += stride) {
+        seg[b + 1] = (off[b + 1] - off[b] + cap - 1) / cap;
+        if (b == 0) seg[0] = 0;
+    }
+}
+// the bucket that owns segment s: the largest b with seg[b] <= s (s < seg[n_keys])
+__device__ __forceinline__ uint64_t owner_of(const u64* seg, uint64_t n_keys, u64 s) {
+    uint64_t lo = 0, hi = n_keys;   // invariant: seg[lo] <= s < seg[hi]
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (seg[mid] <= s) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(kMsmThreads, ZK_MSM_MIN_BLOCKS) msm_bucket_kernel(const u64* off, const u64* seg0, const uint32_t* sorted,
+                                                                                      const G1Affine* bases, uint64_t n_keys, uint64_t max_segments,
+                                                                                      G1Xyzz* part0) {
+    const uint64_t sidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= max_segments || sidx >= seg0[n_keys]) return;
+    const uint64_t b = owner_of(seg0, n_keys, sidx);
+    const u64 lo = off[b] + (sidx - seg0[b]) * kCap0;
+    const u64 hi = min(lo + (u64)kCap0, off[b + 1]);
     G1Xyzz acc = G1::infinity();
-    const u64 lo = off[key], hi = off[key + 1];
 #pragma unroll 1
     for (u64 e = lo; e < hi; ++e) {
         const uint32_t v = sorted[e];
         const G1Affine p = load_affine(bases + (v & 0x7fffffffu));
         G1::add_affine(acc, p, (v >> 31) != 0);
     }
-    store_xyzz(buckets + key, acc);
+    store_xyzz(part0 + sidx, acc);
+}
+__global__ void __launch_bounds__(kMsmThreads) msm_merge_kernel(const u64* seg0, const u64* seg1, const G1Xyzz* part0, uint64_t n_keys,
+                                                                uint64_t max_segments, G1Xyzz* part1) {
+    const uint64_t sidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= max_segments || sidx >= seg1[n_keys]) return;
+    const uint64_t b = owner_of(seg1, n_keys, sidx);
+    const u64 lo = seg0[b] + (sidx - seg1[b]) * kCap1;
+    const u64 hi = min(lo + (u64)kCap1, seg0[b + 1]);
+    G1Xyzz acc = load_xyzz(part0 + lo);
+#pragma unroll 1
+    for (u64 e = lo + 1; e < hi; ++e) {
+        const G1Xyzz v = load_xyzz(part0 + e);
+        G1::add(acc, v);
+    }
+    store_xyzz(part1 + sidx, acc);
+}
+__device__ __forceinline__ G1Xyzz shfl_xyzz(const G1Xyzz& v, int src, bool down) {
+    G1Xyzz r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 48; ++i) d[i] = down ? __shfl_down_sync(0xffffffffu, s[i], src) : __shfl_sync(0xffffffffu, s[i], src);
+    return r;
+}
+__global__ void __launch_bounds__(kMsmThreads) msm_finish_kernel(const u64* seg1, const G1Xyzz* part1, uint64_t n_keys, G1Xyzz* buckets) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = b < n_keys;
+    const u64 lo = valid ? seg1[b] : 0;
+    const uint32_t cnt = valid ? (uint32_t)(seg1[b + 1] - lo) : 0;
+    G1Xyzz acc = G1::infinity();
+    if (cnt == 1) acc = load_xyzz(part1 + lo);
+    unsigned big = __ballot_sync(0xffffffffu, cnt > 1);
+    while (big) {   // the warp adds one oversized bucket at a time
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const u64 slo = __shfl_sync(0xffffffffu, lo, src);
+        const uint32_t scnt = __shfl_sync(0xffffffffu, cnt, src);
+        G1Xyzz part = G1::infinity();
+#pragma unroll 1
+        for (uint32_t t = lane; t < scnt; t += 32) {
+            const G1Xyzz v = load_xyzz(part1 + slo + t);
+            G1::add(part, v);
+        }
+#pragma unroll 1
+        for (int delta = 16; delta >= 1; delta >>= 1) {
+            const G1Xyzz o = shfl_xyzz(part, delta, true);
+            if (lane < delta) G1::add(part, o);
+        }
+        const G1Xyzz total = shfl_xyzz(part, 0, false);
+        if (lane == src) acc = total;
+    }
+    if (valid) store_xyzz(buckets + b, acc);
 }
 
 // ---------------------------------------------------------------- window sums: sum_b (b + 1) bucket[b]
@@ -178,27 +270,30 @@ __global__ void __launch_bounds__(kMsmThreads) msm_chunk_kernel(const G1Xyzz* bu
     store_xyzz(chunk_acc + t, acc);
     store_xyzz(chunk_run + t, run);
 }
-// level 2: one thread per window over its nT chunks: sum_t acc_t + S * sum_t t run_t   (S a power of two)
-__global__ void __launch_bounds__(32) msm_window_kernel(const G1Xyzz* chunk_acc, const G1Xyzz* chunk_run, uint32_t nT, uint32_t S, G1Xyzz* win) {
-    const int w = blockIdx.x;   // one block (one working thread) per window: the windows run on different SMs
-    if (threadIdx.x != 0) return;
-    G1Xyzz a = G1::infinity(), run = G1::infinity(), t_sum = G1::infinity();
-    const G1Xyzz* ca = chunk_acc + (uint64_t)w * nT;
-    const G1Xyzz* cr = chunk_run + (uint64_t)w * nT;
+// level 2: sum_t acc_t and sum_t t run_t over a window's nT chunks, the second as bit planes of t:
+//   plane p < nb:  P_p = sum of run_t over the t whose bit p is set   (sum_t t run_t = sum_p 2^p P_p)
+//   plane nb:      A   = sum of acc_t
+// One warp per (window, plane): every lane adds its share of the chunks, then a five-step butterfly over the lanes.
+__global__ void __launch_bounds__(kMsmThreads) msm_plane_kernel(const G1Xyzz* chunk_acc, const G1Xyzz* chunk_run, uint32_t n_warps, uint32_t nT,
+                                                                uint32_t nb, G1Xyzz* planes) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_warps) return;   // whole warps leave together
+    const uint32_t w = warp / (nb + 1), p = warp % (nb + 1);
+    const G1Xyzz* src = (p == nb ? chunk_acc : chunk_run) + (uint64_t)w * nT;
+    G1Xyzz acc = G1::infinity();
 #pragma unroll 1
-    for (int t = (int)nT - 1; t >= 0; --t) {
-        const G1Xyzz va = load_xyzz(ca + t);
-        G1::add(a, va);
-        if (t >= 1) {
-            const G1Xyzz vr = load_xyzz(cr + t);
-            G1::add(run, vr);
-            G1::add(t_sum, run);
+    for (uint32_t t = lane; t < nT; t += 32) {
+        if (p == nb || ((t >> p) & 1u)) {
+            const G1Xyzz v = load_xyzz(src + t);
+            G1::add(acc, v);
         }
     }
 #pragma unroll 1
-    for (uint32_t s = S; s > 1; s >>= 1) G1::dbl(t_sum, t_sum);
-    G1::add(a, t_sum);
-    store_xyzz(win + w, a);
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        const G1Xyzz o = shfl_xyzz(acc, delta, true);
+        if ((int)lane < delta) G1::add(acc, o);
+    }
+    if (lane == 0) store_xyzz(planes + warp, acc);
 }
 
 // ---------------------------------------------------------------- trusted setup on the GPU
@@ -314,9 +409,9 @@ struct zk_kzg_setup {
     std::vector<G1Affine*> level;         // level[k]: the setup folded k times, 2^(n-k) points (level[0] = g1_powers_of_tau)
     G1Affine* storage = nullptr;          // all levels, 2^(n+1) points
     // workspace of the multi-scalar multiplication, sized for 2^n points
-    u64 *off = nullptr, *cursor = nullptr, *scan_scratch = nullptr;
+    u64 *off = nullptr, *cursor = nullptr, *scan_scratch = nullptr, *seg0 = nullptr, *seg1 = nullptr;
     uint32_t* sorted = nullptr;
-    G1Xyzz *buckets = nullptr, *chunk_acc = nullptr, *chunk_run = nullptr, *win = nullptr;
+    G1Xyzz *buckets = nullptr, *part0 = nullptr, *part1 = nullptr, *chunk_acc = nullptr, *chunk_run = nullptr, *win = nullptr;
     HG1Xyzz* win_host = nullptr;          // pinned
     Fe *cur = nullptr, *quot = nullptr;   // open_and_prove: the remainder and quotient tables
     uint64_t cap_points = 0, cap_keys = 0, cap_chunks = 0;
@@ -343,11 +438,15 @@ int msm_reserve(zk_ctx* ctx, zk_kzg_setup* s, uint64_t max_points) {
     ZK_CUDA(cudaMalloc(&s->cursor, keys * sizeof(u64)));
     ZK_CUDA(cudaMalloc(&s->scan_scratch, (scan::scan_chunks(keys + 1) + 1) * sizeof(u64)));
     ZK_CUDA(cudaMalloc(&s->sorted, entries * sizeof(uint32_t)));
+    ZK_CUDA(cudaMalloc(&s->seg0, (keys + 1) * sizeof(u64)));
+    ZK_CUDA(cudaMalloc(&s->seg1, (keys + 1) * sizeof(u64)));
     ZK_CUDA(cudaMalloc(&s->buckets, keys * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaMalloc(&s->part0, (keys + entries / kCap0 + 1) * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaMalloc(&s->part1, (keys + (keys + entries / kCap0) / kCap1 + 1) * sizeof(G1Xyzz)));
     ZK_CUDA(cudaMalloc(&s->chunk_acc, chunks * sizeof(G1Xyzz)));
     ZK_CUDA(cudaMalloc(&s->chunk_run, chunks * sizeof(G1Xyzz)));
-    ZK_CUDA(cudaMalloc(&s->win, 128 * sizeof(G1Xyzz)));
-    ZK_CUDA(cudaHostAlloc(&s->win_host, 128 * sizeof(HG1Xyzz), cudaHostAllocDefault));
+    ZK_CUDA(cudaMalloc(&s->win, kMaxPlanes * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaHostAlloc(&s->win_host, kMaxPlanes * sizeof(HG1Xyzz), cudaHostAllocDefault));
     s->cap_points = max_points;
     s->cap_keys = keys;
     s->cap_chunks = chunks;
@@ -367,19 +466,43 @@ int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* base
     scan::inclusive_scan(st, s->off, keys + 1, s->scan_scratch);
     ZK_CUDA(cudaMemcpyAsync(s->cursor, s->off, keys * sizeof(u64), cudaMemcpyDeviceToDevice, st));
     msm_scatter_kernel<<<blocks_for(ctx, n, kThreads, 8), kThreads, 0, st>>>(scalars, n, pl, s->cursor, s->sorted);
-    msm_bucket_kernel<<<(unsigned)((keys + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->off, s->sorted, bases, keys, s->buckets);
+    // bucket sums in three bounded levels (see msm_bucket_kernel); the segment counts never come to the host, the grids
+    // are sized by their upper bounds
+    const uint64_t max0 = keys + n * (uint64_t)pl.W / kCap0, max1 = keys + max0 / kCap1;
+    msm_segments_kernel<<<blocks_for(ctx, keys, kThreads, 8), kThreads, 0, st>>>(s->off, keys, kCap0, s->seg0);
+    scan::inclusive_scan(st, s->seg0, keys + 1, s->scan_scratch);
+    msm_segments_kernel<<<blocks_for(ctx, keys, kThreads, 8), kThreads, 0, st>>>(s->seg0, keys, kCap1, s->seg1);
+    scan::inclusive_scan(st, s->seg1, keys + 1, s->scan_scratch);
+    msm_bucket_kernel<<<(unsigned)((max0 + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->off, s->seg0, s->sorted, bases, keys, max0, s->part0);
+    msm_merge_kernel<<<(unsigned)((max1 + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->seg0, s->seg1, s->part0, keys, max1, s->part1);
+    msm_finish_kernel<<<(unsigned)((keys + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->seg1, s->part1, keys, s->buckets);
     const uint64_t n_chunks = (uint64_t)pl.W * nT;
     msm_chunk_kernel<<<(unsigned)((n_chunks + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->buckets, n_chunks, pl.S, s->chunk_acc, s->chunk_run);
-    msm_window_kernel<<<pl.W, 32, 0, st>>>(s->chunk_acc, s->chunk_run, nT, pl.S, s->win);
-    ctx->launches += 8;
+    uint32_t nb = 0, log_s = 0;
+    while ((1u << nb) < nT) ++nb;
+    while ((1u << log_s) < pl.S) ++log_s;
+    const uint32_t n_planes = (uint32_t)pl.W * (nb + 1);
+    msm_plane_kernel<<<(n_planes * 32 + kMsmThreads - 1) / kMsmThreads, kMsmThreads, 0, st>>>(s->chunk_acc, s->chunk_run, n_planes, nT, nb, s->win);
+    ctx->launches += 18;
     ZK_CUDA(cudaGetLastError());
-    ZK_CUDA(cudaMemcpyAsync(s->win_host, s->win, (size_t)pl.W * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaMemcpyAsync(s->win_host, s->win, (size_t)n_planes * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
     ZK_CUDA(cudaStreamSynchronize(st));
-    // result = sum_w 2^(c w) window_w, most significant window first
+    // window_w = A_w + S sum_p 2^p P_{w,p};  result = sum_w 2^(c w) window_w = sum over bit positions: A_w sits at c w and
+    // P_{w,p} at c w + log2(S) + p < c (w + 1).  One pass from the top bit down: a doubling per position, an addition per term.
+    std::vector<const HG1Xyzz*> at((size_t)pl.W * pl.c, nullptr), at2((size_t)pl.W * pl.c, nullptr);
+    for (int w = 0; w < pl.W; ++w) {
+        const HG1Xyzz* base = s->win_host + (size_t)w * (nb + 1);
+        at[(size_t)w * pl.c] = base + nb;
+        for (uint32_t p = 0; p < nb; ++p) {
+            const size_t pos = (size_t)w * pl.c + log_s + p;
+            (at[pos] ? at2[pos] : at[pos]) = base + p;
+        }
+    }
     HG1Xyzz acc = HostG1::infinity();
-    for (int w = pl.W - 1; w >= 0; --w) {
-        for (int k = 0; k < pl.c; ++k) acc = HostG1::dbl(acc);
-        acc = HostG1::add(acc, s->win_host[w]);
+    for (size_t pos = at.size(); pos-- > 0;) {
+        acc = HostG1::dbl(acc);
+        if (at[pos]) acc = HostG1::add(acc, *at[pos]);
+        if (at2[pos]) acc = HostG1::add(acc, *at2[pos]);
     }
     *out = HostG1::to_affine(acc);
     return ZK_OK;
@@ -422,6 +545,7 @@ void setup_delete(zk_kzg_setup* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaFree(s->storage); cudaFree(s->off); cudaFree(s->cursor); cudaFree(s->scan_scratch); cudaFree(s->sorted);
+    cudaFree(s->seg0); cudaFree(s->seg1); cudaFree(s->part0); cudaFree(s->part1);
     cudaFree(s->buckets); cudaFree(s->chunk_acc); cudaFree(s->chunk_run); cudaFree(s->win); cudaFree(s->cur); cudaFree(s->quot);
     if (s->win_host) cudaFreeHost(s->win_host);
     delete s;
