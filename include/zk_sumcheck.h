@@ -238,6 +238,14 @@ int  zk_gkr_verify_wide(zk_ctx *, const zk_wide_circuit *, const uint64_t *outpu
 int  zk_gkr_verify_wide_device(zk_ctx *, const zk_wide_circuit *, const uint64_t *output, const uint64_t *layer_claims,
                                const uint64_t *coeffs, const uint64_t *wb, const uint64_t *wc, const zk_table *inputs,
                                uint32_t flags, int *ok);
+/* verify_succinct (gkr/src/succinct_gkr_protocol.rs:172-283) without its two MultilinearKZG::verify calls: the output claim,
+ * every layer's sumcheck and, for all layers but the input layer, the claim check of zk_gkr_verify_wide.  last_challenges
+ * (may be NULL) receives the input layer's 2 * layer_bits[n_layers] challenges: (rb, rc), the points the committed input
+ * polynomial must open at (:262-275; zk_kzg_verify).  input_evals == NULL is the reference's behaviour (the opened values
+ * are not compared with the last sumcheck claim); with input_evals = {W(rb), W(rc)} as opened, that check is made too. */
+int  zk_gkr_verify_wide_succinct(zk_ctx *, const zk_wide_circuit *, const uint64_t *output, const uint64_t *layer_claims,
+                                 const uint64_t *coeffs, const uint64_t *wb, const uint64_t *wc, const uint64_t *input_evals,
+                                 uint32_t flags, uint64_t *last_challenges, int *ok);
 
 /* ---- one process per GPU: tables sharded on the LOW index bits (rank q holds entries q, q+G, q+2G, ...) ----
  * NCCL over NVLink/NVSwitch carries one all-gather of (D+1) elements per round; folds stay local.

@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out/r02_s16
 mkdir -p $OUT
-timeout 900 python -m pytest tests/test_gpu_kzg.py -x -q -m gpu > $OUT/pytest_kzg.log 2>&1 ; echo "pytest kzg rc=$?"
+timeout 900 python -m pytest tests/test_gpu_kzg.py tests/test_gpu_succinct_gkr.py -x -q -m gpu > $OUT/pytest_kzg.log 2>&1 ; echo "pytest kzg rc=$?"
 tail -5 $OUT/pytest_kzg.log
 for v in ""; do
   lib=""; [ -n "$v" ] && lib="$PWD/zk_cryptography_research_implementations_b200/libzkb200_$v.so"

@@ -92,6 +92,7 @@ SIGNATURES = {
     "zk_gkr_prove_wide_device": (C.c_int, [vp, vp, vp, u64p, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint32]),
     "zk_gkr_verify_wide": (C.c_int, [vp, vp, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint32, C.POINTER(C.c_int)]),
     "zk_gkr_verify_wide_device": (C.c_int, [vp, vp, u64p, u64p, u64p, u64p, u64p, vp, C.c_uint32, C.POINTER(C.c_int)]),
+    "zk_gkr_verify_wide_succinct": (C.c_int, [vp, vp, u64p, u64p, u64p, u64p, u64p, u64p, C.c_uint32, u64p, C.POINTER(C.c_int)]),
     "zk_comm_unique_id": (C.c_int, [C.c_char_p]),
     "zk_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
     "zk_comm_attach_mailboxes": (C.c_int, [vp, C.c_char_p, C.c_int]),

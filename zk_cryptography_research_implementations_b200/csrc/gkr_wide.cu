@@ -789,7 +789,8 @@ static int gkr_prove_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const ui
 // return true.  `flags` must match the prover's (ZK_FLAG_SKIP_ABSORB).
 static int gkr_verify_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const uint64_t* output, const uint64_t* layer_claims,
                                 const uint64_t* coeffs, const uint64_t* wb, const uint64_t* wcv_in, const uint64_t* inputs,
-                                const zk_table* device_inputs, uint64_t n_inputs, uint32_t flags, int* ok) {
+                                const zk_table* device_inputs, uint64_t n_inputs, uint32_t flags, int* ok, bool succinct = false,
+                                const uint64_t* input_evals = nullptr, uint64_t* last_challenges = nullptr) {
     zk_wide_circuit* wc = const_cast<zk_wide_circuit*>(wc_);
     const HostField& f = ctx->field;
     const uint32_t L = wc->L;
@@ -833,7 +834,16 @@ static int gkr_verify_wide_impl(zk_ctx* ctx, const zk_wide_circuit* wc_, const u
         if (!valid) return ZK_OK;                                                                            // :172-176
         std::vector<HFe> u(chal.begin(), chal.begin() + m), v(chal.begin() + m, chal.end());
         HFe wbv, wcv;
-        if (li + 1 < L) {                                                                                    // :183-187
+        if (succinct && li + 1 == L) {
+            // succinct_gkr_protocol.rs:205-262: the input layer is not evaluated -- the caller checks the KZG openings of the
+            // committed input polynomial at (rb, rc) = the two halves of this layer's challenges.  The reference stops here
+            // without tying the opened values to this sumcheck's last claim; with `input_evals` (the two opened values) that
+            // check is made as for every other layer.
+            if (last_challenges) memcpy(last_challenges, chal[0].l, (size_t)rounds * 32);
+            if (!input_evals) break;
+            memcpy(wbv.l, input_evals, 32);
+            memcpy(wcv.l, input_evals + 4, 32);
+        } else if (li + 1 < L) {                                                                             // :183-187
             memcpy(wbv.l, wb + 4 * li, 32);
             memcpy(wcv.l, wcv_in + 4 * li, 32);
         } else {                                                                                             // :188-194
@@ -885,6 +895,12 @@ extern "C" int zk_gkr_verify_wide(zk_ctx* ctx, const zk_wide_circuit* wc, const 
                                   const uint64_t* coeffs, const uint64_t* wb, const uint64_t* wcv, const uint64_t* inputs,
                                   uint64_t n_inputs, uint32_t flags, int* ok) {
     return gkr_verify_wide_impl(ctx, wc, output, layer_claims, coeffs, wb, wcv, inputs, nullptr, n_inputs, flags, ok);
+}
+// verify_succinct's sumcheck half (succinct_gkr_protocol.rs:172-262): everything of zk_gkr_verify_wide except the input layer
+extern "C" int zk_gkr_verify_wide_succinct(zk_ctx* ctx, const zk_wide_circuit* wc, const uint64_t* output, const uint64_t* layer_claims,
+                                           const uint64_t* coeffs, const uint64_t* wb, const uint64_t* wcv, const uint64_t* input_evals,
+                                           uint32_t flags, uint64_t* last_challenges, int* ok) {
+    return gkr_verify_wide_impl(ctx, wc, output, layer_claims, coeffs, wb, wcv, nullptr, nullptr, 0, flags, ok, true, input_evals, last_challenges);
 }
 extern "C" int zk_gkr_verify_wide_device(zk_ctx* ctx, const zk_wide_circuit* wc, const uint64_t* output, const uint64_t* layer_claims,
                                          const uint64_t* coeffs, const uint64_t* wb, const uint64_t* wcv, const zk_table* inputs,

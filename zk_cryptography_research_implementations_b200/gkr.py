@@ -1,4 +1,5 @@
-"""`gkr` crate mirror: gkr/src/gkr_protocol.rs `prove` + `Proof` on the GPU (verifier: parity harness only)."""
+"""`gkr` crate mirror: gkr/src/gkr_protocol.rs `prove` / `verify` + `Proof`, and gkr/src/succinct_gkr_protocol.rs
+`prove_succinct` / `verify_succinct` + `SuccinctProof` (the input layer behind a multilinear KZG commitment)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -186,3 +187,66 @@ def verify_wide(ctx: Context, circuit: WideCircuit, proof: Proof, inputs, flags:
         ctx.check(lib.zk_gkr_verify_wide(ctx.h, circuit.h, _ptr(out), _ptr(claims), _ptr(coeffs), _ptr(wb), _ptr(wc),
                                          _ptr(inputs), inputs.shape[0], flags, C.byref(ok)))
     return bool(ok.value)
+
+
+# ------------------------------------------------------------------ succinct GKR (gkr/src/succinct_gkr_protocol.rs)
+@dataclass
+class SuccinctProof:                           # succinct_gkr_protocol.rs:22-32
+    circuit_output: np.ndarray
+    claimed_sum: np.ndarray
+    sumcheck_proofs: List[SumcheckProverProof]
+    wb_evaluations: np.ndarray
+    wc_evaluations: np.ndarray
+    input_polynomial_commitment: np.ndarray    # (12,) affine G1
+    input_rb_proof: "MultilinearKZGProof"
+    input_rc_proof: "MultilinearKZGProof"
+
+
+def prove_succinct(ctx: Context, circuit: WideCircuit, inputs, trusted_setup, flags: int = 0) -> SuccinctProof:
+    """succinct_gkr_protocol.rs:35-169.  The transcript flow is gkr_protocol::prove's (the commitment is not absorbed, :46-66);
+    on top of it the input polynomial is committed (:43-44) and opened at rb and rc, the two halves of the input layer's
+    sumcheck challenges (:118-123, :151-154).  `ctx` must be a BLS12-381 Fr context; `inputs` host limbs or a DeviceTable."""
+    from .core import DeviceTable
+    from .multilinear_kzg import MultilinearKZG
+    table = inputs if isinstance(inputs, DeviceTable) else ctx.upload(as_elems(inputs).reshape(-1, 4))
+    commitment = MultilinearKZG.commit_to_polynomial(table, trusted_setup)
+    base = prove_wide(ctx, circuit, table, flags)
+    chal = base.sumcheck_proofs[-1].random_challenges
+    mid = chal.shape[0] // 2
+    rb_proof = MultilinearKZG.open_and_prove(table, trusted_setup, chal[:mid])
+    rc_proof = MultilinearKZG.open_and_prove(table, trusted_setup, chal[mid:])
+    return SuccinctProof(base.circuit_output, base.claimed_sum, base.sumcheck_proofs, base.wb_evaluations, base.wc_evaluations,
+                         commitment, rb_proof, rc_proof)
+
+
+def verify_succinct(ctx: Context, circuit: WideCircuit, proof: SuccinctProof, trusted_setup, flags: int = 0,
+                    bind_input_openings: bool = False) -> bool:
+    """succinct_gkr_protocol.rs:172-283: the layer sumchecks and claim checks on the GPU (wiring predicates from the gate
+    list), the two input openings by the pairing check on the host.  bind_input_openings=True additionally requires the
+    opened values W(rb), W(rc) to satisfy the input layer's last sumcheck claim -- a check the reference does not make."""
+    from .multilinear_kzg import MultilinearKZG
+    lib = ctx.lib
+    L = circuit.n_layers
+    out = np.ascontiguousarray(as_elems(proof.circuit_output).reshape(-1, 4))
+    if out.shape[0] != (1 << circuit.layer_bits[0]):
+        return False
+    claims = np.ascontiguousarray(np.stack([sp.claimed_sum for sp in proof.sumcheck_proofs]))
+    coeffs = np.ascontiguousarray(np.concatenate([np.stack([p.coefficients for p in sp.round_univariate_polynomials])
+                                                  for sp in proof.sumcheck_proofs]))
+    pad = np.zeros((1, 4), dtype=np.uint64)
+    wb = np.ascontiguousarray(np.concatenate([as_elems(proof.wb_evaluations).reshape(-1, 4), pad]))
+    wc = np.ascontiguousarray(np.concatenate([as_elems(proof.wc_evaluations).reshape(-1, 4), pad]))
+    m = circuit.layer_bits[L]
+    last = np.zeros((2 * m, 4), dtype=np.uint64)
+    evals = None
+    if bind_input_openings:
+        evals = np.ascontiguousarray(np.stack([as_elems(proof.input_rb_proof.evaluation).reshape(4),
+                                               as_elems(proof.input_rc_proof.evaluation).reshape(4)]))
+    ok = C.c_int(0)
+    ctx.check(lib.zk_gkr_verify_wide_succinct(ctx.h, circuit.h, _ptr(out), _ptr(claims), _ptr(coeffs), _ptr(wb), _ptr(wc),
+                                              _ptr(evals) if evals is not None else None, flags, _ptr(last), C.byref(ok)))
+    if not ok.value:
+        return False
+    rb, rc = last[:m], last[m:]                                                            # :262-264
+    return (MultilinearKZG.verify(trusted_setup, proof.input_polynomial_commitment, rb, proof.input_rb_proof)
+            and MultilinearKZG.verify(trusted_setup, proof.input_polynomial_commitment, rc, proof.input_rc_proof))

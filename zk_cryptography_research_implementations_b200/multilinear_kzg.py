@@ -1,7 +1,8 @@
 """`multilinear_kzg` crate mirror: the input commitment of succinct GKR on the GPU.
 
-  TrustedSetup            multilinear_kzg/src/trusted_setup.rs:5-24   (G1 side: g1_powers_of_tau)
-  MultilinearKZG          multilinear_kzg/src/multilinear_kzg.rs:10-13, commit_to_polynomial :25-46, open_and_prove :51-127
+  TrustedSetup            multilinear_kzg/src/trusted_setup.rs:5-24   (g1_powers_of_tau in HBM, g2_powers_of_tau on the host)
+  MultilinearKZG          multilinear_kzg/src/multilinear_kzg.rs:10-13, commit_to_polynomial :25-46, open_and_prove :51-127,
+                          verify :132-159 (host only: pairing check)
   MultilinearKZGProof     multilinear_kzg/src/multilinear_kzg.rs:15-19
 
 Same names, argument meaning and panic messages as the reference.  The curve is BLS12-381 (the only pairing the
@@ -31,9 +32,10 @@ def as_points(a) -> np.ndarray:
 class TrustedSetup:
     """`TrustedSetup<P>`: g1_powers_of_tau lives in HBM together with its partial sums over the leading variables."""
 
-    def __init__(self, ctx: Context, handle):
+    def __init__(self, ctx: Context, handle, g2_powers_of_tau: Optional[np.ndarray] = None):
         self.ctx = ctx
         self._h = handle
+        self.g2_powers_of_tau = g2_powers_of_tau     # (n, 24) or None (a prover-only setup)
 
     @property
     def h(self):
@@ -47,18 +49,22 @@ class TrustedSetup:
         t = as_elems(taus).reshape(-1, 4)
         h = vp()
         ctx.check(ctx.lib.zk_kzg_setup_create(ctx.h, _ptr(t) if t.size else None, t.shape[0], C.byref(h)))
-        return cls(ctx, h)
+        g2 = np.zeros((t.shape[0], 24), dtype=np.uint64)                                    # trusted_setup.rs:65-78
+        if ctx.lib.zk_kzg_g2_powers_of_tau(_ptr(t), t.shape[0], _ptr(g2)) != 0:
+            raise ReferencePanic("requires at least one variable")
+        return cls(ctx, h, g2)
 
     @classmethod
-    def from_g1_powers_of_tau(cls, ctx: Context, points) -> "TrustedSetup":
-        """an existing setup (e.g. a ceremony's): 2^n affine points"""
+    def from_g1_powers_of_tau(cls, ctx: Context, points, g2_powers_of_tau=None) -> "TrustedSetup":
+        """an existing setup (e.g. a ceremony's): 2^n affine G1 points (and, for verification, the n G2 points)"""
         pts = as_points(points).reshape(-1, 12)
         n = pts.shape[0].bit_length() - 1
         if pts.shape[0] == 0 or pts.shape[0] != 1 << n:
             raise ReferencePanic("Evaluated values must be a power of 2")
         h = vp()
         ctx.check(ctx.lib.zk_kzg_setup_from_points(ctx.h, _ptr(pts), n, C.byref(h)))
-        return cls(ctx, h)
+        g2 = None if g2_powers_of_tau is None else np.ascontiguousarray(g2_powers_of_tau, dtype=np.uint64).reshape(-1, 24)
+        return cls(ctx, h, g2)
 
     def number_of_variables(self) -> int:
         return int(self.ctx.lib.zk_kzg_setup_num_vars(self.h))
@@ -132,6 +138,26 @@ class MultilinearKZG:
             ctx.check(ctx.lib.zk_kzg_open(ctx.h, trusted_setup.h, _ptr(ev), ev.shape[0], _ptr(op) if op.size else None,
                                           op.shape[0], _ptr(ev_out), _ptr(proofs)))
         return MultilinearKZGProof(ev_out, proofs[:op.shape[0]])
+
+
+    @staticmethod
+    def verify(trusted_setup: TrustedSetup, commitment, opening_values, proof: MultilinearKZGProof) -> bool:
+        """multilinear_kzg.rs:132-159: e(C - v G1, G2) == prod e(Q_i, tau_i G2 - r_i G2); host only"""
+        lib = trusted_setup.ctx.lib
+        g2 = trusted_setup.g2_powers_of_tau
+        if g2 is None:
+            raise ValueError("this TrustedSetup carries no g2_powers_of_tau (prover-only)")
+        op = as_elems(opening_values).reshape(-1, 4)
+        pr = as_points(proof.proofs).reshape(-1, 12)
+        ok = C.c_int(0)
+        rc = lib.zk_kzg_verify(_ptr(g2), g2.shape[0], _ptr(as_points(commitment).reshape(12)), _ptr(op) if op.size else None,
+                               op.shape[0], _ptr(as_elems(proof.evaluation).reshape(4)), _ptr(pr) if pr.size else None,
+                               pr.shape[0], C.byref(ok))
+        if rc == -1:
+            raise ReferencePanic("Number of opening values must match number of proofs")
+        if rc:
+            return False            # a point that is not on its curve
+        return bool(ok.value)
 
 
 def g1_msm(ctx: Context, scalars, points) -> np.ndarray:
