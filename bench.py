@@ -48,6 +48,9 @@ WORKLOADS = {
     # --log2 is the circuit depth L here: reference-shaped layered circuit, layer i has 2^i gates over 2^(i+1) wires,
     # 2^L inputs; the layer-i sumcheck runs over 4^(i+1) entries x 4 tables
     "gkr": (0, "BN254_FQ", 2, 2, 12, "GKR prove of a reference-shaped layered add/mul circuit (gkr_protocol::prove)"),
+    # --log2 = number of variables of the committed polynomial (the input commitment of succinct GKR for the
+    # 2^22-wide input layer of configs[3])
+    "kzg": (2, "BLS12_381_FR", 1, 1, 22, "multilinear KZG over BLS12-381 G1: commit_to_polynomial + open_and_prove of a 2^22-entry polynomial (succinct GKR's input commitment)"),
 }
 
 
@@ -548,6 +551,142 @@ def run_mle(args, wl, log2=None, sweep=None, steps=None, warmup=None):
     return line
 
 
+def run_kzg(args, wl, log2=None, steps=None, warmup=None):
+    """SURVEY 8 f4: MultilinearKZG::commit_to_polynomial (one 2^n-point G1 multi-scalar multiplication) and open_and_prove
+    (n more over the folded setup).  value = points committed per second; the bucket kernel is integer-multiplier bound, so
+    the roofline is the register-resident mixed-addition rate measured by zk_g1_arith_probe in the same run."""
+    field, fname, P, D, log2_default, desc = wl
+    log2 = log2 or (args.log2 if args.workload == "kzg" else 0) or log2_default
+    n_steps = steps or args.steps
+    n_warm = args.warmup if warmup is None else warmup
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    N = 1 << log2
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+    def cpu_commit(sample_log2, threads):
+        import coracle as co
+        taus = co.table_generate(field, SEED, 98, 64)[:sample_log2].copy()
+        vals = co.table_generate(field, SEED, 0, 1 << sample_log2)
+        co.set_threads(os.cpu_count() or 1)
+        try:
+            g1 = co.kzg_setup_g1(taus)           # building the setup is not the reference's timed path
+        finally:
+            co.set_threads(threads)
+        try:
+            t0 = time.perf_counter()
+            c = co.kzg_commit(vals, g1)
+            return time.perf_counter() - t0, c, taus
+        finally:
+            co.set_threads(1)
+
+    if args.impl == "reference":
+        sl = min(log2, 11)
+        th = max(1, args.cpu_threads)
+        times = [cpu_commit(sl, th)[0] for _ in range(max(args.steps, 1))]
+        t = statistics.mean(times)
+        v = (1 << sl) / t / MEGA
+        return {"impl": "reference", "metric": "kzg_commit_Mpoints_per_s", "value": v, "unit": "Mpoints/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u384 / u256 (6x u64 Montgomery base field, 4x u64 scalars)", "data": "synthetic",
+                "config": {"workload": "kzg: " + desc, "field": fname, "log2_entries": log2, "cpu_sample_log2": sl},
+                "cpu_baseline": {"value": v, "unit": "Mpoints/s", "cores": th, "kind": "port",
+                                 "sample": "commit_to_polynomial of the first 2^%d entries: one double-and-add mul_bigint per point as the reference "
+                                           "(multilinear_kzg.rs:39-43), oracle C restatement, %d thread(s)" % (sl, th)},
+                "e2e": {"value": v, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    import torch
+    import zk_cryptography_research_implementations_b200 as zk
+    from zk_cryptography_research_implementations_b200.multilinear_kzg import MultilinearKZG, MultilinearKZGProof, TrustedSetup
+    torch.cuda.set_device(0)
+    ctx = zk.Context(field, 0, stream=torch.cuda.current_stream().cuda_stream)
+    lib = ctx.lib
+    taus = np.ascontiguousarray(ctx.generate(SEED, 98, 64).download()[:log2])
+    opening = np.ascontiguousarray(ctx.generate(SEED, 99, 64).download()[:log2])
+    t0 = time.perf_counter()
+    setup = TrustedSetup.initialize_setup(ctx, taus)
+    ctx.synchronize()
+    setup_s = time.perf_counter() - t0
+    table = ctx.generate(SEED, 0, N)
+    ctx.synchronize()
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        ts = []
+        for _ in range(k):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return statistics.mean(ts)
+
+    sampler = ClockSampler(0)
+    ctx.reset_stats()
+    box = {}
+    ms_commit = timed(lambda: box.__setitem__("c", MultilinearKZG.commit_to_polynomial(table, setup)), n_steps, n_warm)
+    launches = ctx.stats()["launches"] // max(n_steps + n_warm, 1)
+    ms_open = timed(lambda: box.__setitem__("p", MultilinearKZG.open_and_prove(table, setup, opening)), max(1, n_steps // 2), 1)
+    clocks = sampler.stop()
+    commitment, proof = box["c"], box["p"]
+    # e2e: evaluations in pinned host memory -> commitment on the host
+    e2e = None
+    if not args.no_e2e:
+        host_vals = table.download()
+        ms_e2e = timed(lambda: MultilinearKZG.commit_to_polynomial(host_vals, setup), max(1, min(n_steps, 3)), 1)
+        e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Mpoints/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": 96,
+               "ms_per_step": ms_e2e, "call": "zk_kzg_commit (host evaluations -> HBM -> commitment on the host)"}
+    # the multiplier ceiling: register-resident mixed additions and 381-bit products on the full grid
+    peak_madd = peak_mul = None
+    if not args.no_probe:
+        ops, ms = C.c_double(), C.c_double()
+        ctx.check(lib.zk_g1_arith_probe(ctx.h, 1, 2000, 4, C.byref(ops), C.byref(ms)))
+        peak_madd = ops.value
+        ctx.check(lib.zk_g1_arith_probe(ctx.h, 0, 4000, 4, C.byref(ops), C.byref(ms)))
+        peak_mul = ops.value
+    windows = (256 + 15) // 16 if N >= (1 << 20) else None
+    madds = N * windows if windows else None
+    ach = madds / (ms_commit * 1e-3) if madds else None
+    # after the timed region: the pairing check of the reference's verify() on the commitment and the opening, and the
+    # evaluation against zk's own evaluate
+    t0 = time.perf_counter()
+    verified = bool(MultilinearKZG.verify(setup, commitment, opening, proof))
+    verify_s = time.perf_counter() - t0
+    from zk_cryptography_research_implementations_b200.polynomials import MultilinearPolynomial
+    verified = verified and bool(np.array_equal(MultilinearPolynomial(ctx, table).evaluate(opening), proof.evaluation))
+    cpu = None
+    if not args.no_cpu:
+        sl = min(log2, 11)
+        t, c_cpu, taus_cpu = cpu_commit(sl, 1)
+        cpu = {"value": (1 << sl) / t / MEGA, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+               "sample": "commit_to_polynomial of a 2^%d-entry polynomial (%.2f s): one double-and-add mul_bigint per point as the reference, "
+                         "oracle C restatement, 1 thread" % (sl, t)}
+        # the same sample through the GPU path must give the oracle's commitment
+        s2 = TrustedSetup.initialize_setup(ctx, taus_cpu)
+        t2 = ctx.generate(SEED, 0, 1 << sl)
+        verified = verified and bool(np.array_equal(MultilinearKZG.commit_to_polynomial(t2, s2), c_cpu))
+        s2.release()
+    line = {
+        "metric": "kzg_commit_Mpoints_per_s", "value": N / (ms_commit * 1e-3) / MEGA, "unit": "Mpoints/s", "n_gpus": 1, "steps": n_steps,
+        "warmup": n_warm, "ms_per_step": ms_commit, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u384 / u256 (12x u32 Montgomery base field, 8x u32 scalars; integer IMAD arithmetic)", "data": "synthetic",
+        "config": {"workload": "kzg: " + desc, "field": fname, "curve": "BLS12-381 G1", "log2_entries": log2,
+                   "timer": "host wall clock around the synchronous call (it ends with a host-side combine of the window sums)"},
+        "kzg_commit_ms": ms_commit, "kzg_open_ms": ms_open, "trusted_setup_s": setup_s, "kzg_verify_s": verify_s,
+        "roofline": {"bound": "imad", "achieved": ach, "peak": peak_madd, "unit": "mixed additions/s", "frac": (ach / peak_madd) if ach and peak_madd else None,
+                     "traffic": None, "kernel": "msm_bucket_kernel (N x %s windows mixed additions per commit over the whole call's time)" % windows,
+                     "peak_source": "zk_g1_arith_probe kind 1 in this run (register-resident XYZZ += affine, 4 blocks/SM); "
+                                    "381-bit Montgomery products: %s /s" % ("%.3g" % peak_mul if peak_mul else "n/a")},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "verified": verified,
+        "verified_by": "after the timed region: MultilinearKZG::verify (pairing check, host) accepts the commitment with the opening proof; "
+                       "the opened value equals zk_mle_evaluate; the oracle's commitment of the CPU sample equals the GPU's",
+        "result_digest": keccak_digest([np.ascontiguousarray(commitment.reshape(-1, 4)), np.ascontiguousarray(proof.proofs.reshape(-1, 4))])}
+    setup.release()
+    ctx.close()
+    return line
+
+
 def run_reference(args, wl):
     field, fname, P, D, log2_default, desc = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -1006,6 +1145,7 @@ def run_extras(args):
         attempt("gkr_wide", lambda: run_gkr_wide(args, WORKLOADS["gkr_wide"], steps=min(args.steps, 8), warmup=min(args.warmup, 3)))
         attempt("plain24", lambda: run_ours(args, WORKLOADS["plain24"], name="plain24", steps=min(args.steps, 10), warmup=min(args.warmup, 3)))
         attempt("mle", lambda: run_mle(args, WORKLOADS["mle"], log2=28, sweep="20,22,24,26,30", steps=min(args.steps, 5), warmup=min(args.warmup, 3)))
+        attempt("kzg", lambda: run_kzg(args, WORKLOADS["kzg"], log2=22, steps=min(args.steps, 4), warmup=min(args.warmup, 2)))
     else:
         lg = min(32, 29 + world.bit_length())       # 2^31 at 2 ranks, 2^32 at 4 and 8 (configs[4]: 2^32 sharded over 8 GPUs)
         attempt("mle", lambda: run_mle(args, WORKLOADS["mle"], log2=lg, sweep="", steps=min(args.steps, 5), warmup=min(args.warmup, 3)))
@@ -1042,7 +1182,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return                   # the CPU arm runs on rank 0 alone; the other ranks exit 0 without work
-        fn = {"gkr": run_gkr, "gkr_wide": run_gkr_wide, "mle": run_mle}.get(args.workload, run_reference)
+        fn = {"gkr": run_gkr, "gkr_wide": run_gkr_wide, "mle": run_mle, "kzg": run_kzg}.get(args.workload, run_reference)
         print(json.dumps(fn(args, wl)), flush=True)
         return
     if world == 1 and args.gpus > 1:
@@ -1054,7 +1194,7 @@ def main():
         local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    fn = {"gkr": run_gkr, "gkr_wide": run_gkr_wide, "mle": run_mle}.get(args.workload, run_ours)
+    fn = {"gkr": run_gkr, "gkr_wide": run_gkr_wide, "mle": run_mle, "kzg": run_kzg}.get(args.workload, run_ours)
     line = fn(args, wl)
     if args.workload == "product30" and not args.log2 and not args.no_extras:
         extras = run_extras(args)

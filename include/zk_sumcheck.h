@@ -331,6 +331,10 @@ int  zk_g1_msm(zk_ctx *, const uint64_t *scalars /* 4*n */, const uint64_t *poin
  * kind 0: Montgomery product, 1: fold by a per-round scalar, 2: unreduced multiply-accumulate. */
 int  zk_arith_probe(zk_ctx *, int kind, uint32_t iters, int blocks_per_sm, double *ops_per_s, double *ms);
 
+/* the same for the curve arithmetic of the multi-scalar multiplication: kind 0 = 381-bit Montgomery products, kind 1 = mixed
+ * point additions (XYZZ += affine), both register-resident; operations per second */
+int  zk_g1_arith_probe(zk_ctx *, int kind, uint32_t iters, int blocks_per_sm, double *ops_per_s, double *ms);
+
 #ifdef __cplusplus
 }
 #endif

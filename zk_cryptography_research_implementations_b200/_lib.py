@@ -120,6 +120,7 @@ SIGNATURES = {
     "zk_g1_is_on_curve": (C.c_int, [u64p]),
     "zk_g1_generator": (None, [u64p]),
     "zk_g2_generator": (None, [u64p]),
+    "zk_g1_arith_probe": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "zk_arith_probe": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -395,6 +395,31 @@ __global__ void __launch_bounds__(kThreads) quotient_fold_kernel(Fe* cur, uint64
     }
 }
 
+// register-resident arithmetic, no memory traffic: the ceiling the bucket kernel is measured against.
+// KIND 0: four independent chains of Fq products per thread; KIND 1: one chain of mixed additions (acc += P) per thread
+template <int KIND> __global__ void __launch_bounds__(kMsmThreads, ZK_MSM_MIN_BLOCKS) g1_probe_kernel(G1Xyzz* out, uint32_t iters, const __grid_constant__ G1Affine g) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    G1Xyzz acc = G1::from_affine(g);
+    acc.x.v[0] ^= (uint32_t)tid & 0xffu;     // per-thread data so nothing folds to a constant (not a curve point; timing only)
+    if (KIND == 0) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; ++i) {
+            Fq381::mul(acc.x, acc.x, g.x);
+            Fq381::mul(acc.y, acc.y, g.y);
+            Fq381::mul(acc.zz, acc.zz, g.x);
+            Fq381::mul(acc.zzz, acc.zzz, g.y);
+        }
+    } else {
+        G1Affine p = g;
+#pragma unroll 1
+        for (uint32_t i = 0; i < iters; ++i) {
+            G1::add_affine(acc, p);
+            p.x.v[0] ^= acc.x.v[0] & 1u;     // keeps the operand live without leaving the arithmetic
+        }
+    }
+    store_xyzz(out + tid, acc);
+}
+
 int blocks_for(const zk_ctx* ctx, uint64_t work, int threads, int bps) {
     uint64_t blocks = (work + threads - 1) / threads, cap = (uint64_t)ctx->sm_count * bps;
     if (blocks > cap) blocks = cap;
@@ -754,5 +779,38 @@ extern "C" int zk_g1_msm(zk_ctx* ctx, const uint64_t* scalars, const uint64_t* p
     rc = g1_msm(ctx, s.get(), s->cur, s->storage, n, &r);
     if (rc) return rc;
     memcpy(out, &r, sizeof r);
+    return ZK_OK;
+}
+
+// Times register-resident curve arithmetic on a full grid: kind 0 = Fq (381-bit) Montgomery products (4 * iters per thread),
+// kind 1 = mixed additions acc += P (iters per thread).  Returns operations per second: the IMAD-pipe ceiling of the MSM.
+extern "C" int zk_g1_arith_probe(zk_ctx* ctx, int kind, uint32_t iters, int blocks_per_sm, double* ops_per_s, double* ms_out) {
+    if (kind < 0 || kind > 1 || blocks_per_sm < 1 || blocks_per_sm > 16) return fail(ctx, ZK_ERR_ARG, "bad probe arguments");
+    const int grid = ctx->sm_count * blocks_per_sm;
+    int rc = ensure_scratch(ctx, (size_t)grid * kMsmThreads * sizeof(G1Xyzz));
+    if (rc) return rc;
+    G1Affine g;
+    {
+        const HG1Affine h = HostG1::generator();
+        memcpy(&g, &h, sizeof g);
+    }
+    cudaEvent_t e0, e1;
+    ZK_CUDA(cudaEventCreate(&e0));
+    ZK_CUDA(cudaEventCreate(&e1));
+    for (int pass = 0; pass < 2; ++pass) {   // first pass warms up
+        ZK_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (kind == 0) g1_probe_kernel<0><<<grid, kMsmThreads, 0, ctx->stream>>>((G1Xyzz*)ctx->scratch, iters, g);
+        else g1_probe_kernel<1><<<grid, kMsmThreads, 0, ctx->stream>>>((G1Xyzz*)ctx->scratch, iters, g);
+        ++ctx->launches;
+        ZK_CUDA(cudaGetLastError());
+        ZK_CUDA(cudaEventRecord(e1, ctx->stream));
+        ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    float ms = 0;
+    ZK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    if (ops_per_s) *ops_per_s = (double)grid * kMsmThreads * (kind == 0 ? 4.0 : 1.0) * iters / (ms * 1e-3);
     return ZK_OK;
 }
