@@ -6,8 +6,8 @@
 // entries (multilinear_kzg.rs:93-108, :183-214).  Here:
 //   * every sum is one bucket-method multi-scalar multiplication: signed c-bit digits of the canonical scalars, a
 //     histogram / scan / scatter that groups the (window, digit) occurrences (no sort), one thread per bucket adding
-//     affine points into an XYZZ accumulator (g1.cuh), running sums per chunk of 16 buckets, the chunk results summed by
-//     bit planes of the chunk index (one warp per plane), and a host finish of ~450 group operations (one doubling per
+//     affine points into an XYZZ accumulator (g1.cuh), running sums per chunk of a few buckets, the chunk results summed by
+//     bit planes of the chunk index (one block per plane), and a host finish of ~450 group operations (one doubling per
 //     scalar bit, one addition per plane, one inversion for the affine result);
 //   * the blow-up is never materialised: the quotient of round k repeats with period 2^(n-k-1), so its sum against the
 //     setup equals its sum against the setup FOLDED k+1 times (S_{k+1}[j] = S_k[j] + S_k[j + half]) -- the Lagrange basis
@@ -46,7 +46,7 @@ typedef unsigned long long u64;
 #define ZK_MSM_MIN_BLOCKS 3
 #endif
 constexpr int kMsmThreads = ZK_MSM_THREADS;   // the group law needs ~150-250 registers: small blocks keep the SMs evenly filled
-constexpr int kMaxPlanes = 128 * 16;  // windows x (bit planes of the chunk index + 1), widest plan
+constexpr int kMaxPlanes = 128 * 17;  // windows x (bit planes of the chunk index + 1), widest plan
 constexpr int kFixedWindows = 32;    // fixed-base table of the generator: 32 windows of 8 bits
 
 struct MsmPlan {
@@ -54,6 +54,7 @@ struct MsmPlan {
     int W;            // windows = ceil(256 / c): the top window also takes the last carry (scalars are < 2^255)
     uint32_t B;       // buckets per window = 2^(c-1); bucket b holds the points whose digit is +-(b + 1)
     uint32_t S;       // buckets per running-sum chunk
+    uint32_t cap0;    // entries per level-0 segment of the bucket sums
 };
 MsmPlan plan_for(uint64_t n) {
     int c = n >= (1u << 20) ? 16 : n >= (1u << 16) ? 13 : n >= (1u << 12) ? 10 : n >= (1u << 8) ? 7 : 4;
@@ -65,7 +66,12 @@ MsmPlan plan_for(uint64_t n) {
     p.c = c;
     p.W = (256 + c - 1) / c;
     p.B = 1u << (c - 1);
-    p.S = p.B >= 16 ? 16 : p.B;
+    // serial depth of the window sums: 2 S additions per chunk, then B / (128 S) + 8 in the block-per-plane reduction
+    p.S = p.B >= 16384 ? 8 : p.B >= 2048 ? 4 : p.B >= 256 ? 2 : 1;
+    // level-0 segments: long enough to amortise a thread, short enough that a small problem still fills the machine
+    const uint64_t entries = n * (uint64_t)p.W;
+    p.cap0 = 8;
+    while (p.cap0 < 128 && entries / p.cap0 > 65536) p.cap0 <<= 1;
     return p;
 }
 
@@ -157,12 +163,12 @@ __global__ void __launch_bounds__(kThreads) msm_scatter_kernel(const Fe* scalars
 // A bucket can hold anything from nothing to every point (small or equal scalars put whole tables into a handful of buckets,
 // and the top window of a width that does not divide 256 has only a few buckets in use), so the work is cut into pieces of
 // bounded size in three levels, none of which needs the host:
-//   level 0: every bucket is split into segments of <= kCap0 entries; one thread per segment adds its affine points;
+//   level 0: every bucket is split into segments of <= cap0 entries; one thread per segment adds its affine points;
 //   level 1: the segment sums of a bucket are grouped <= kCap1 at a time; one thread per group adds them;
 //   level 2: one thread per bucket takes its single group sum -- or, where a bucket still has several, its warp adds them
 //            lane-strided and folds the lanes with a butterfly.
-// In the common case (every bucket within kCap0) levels 1 and 2 are copies.
-constexpr uint32_t kCap0 = 128, kCap1 = 32;
+// In the common case (every bucket within cap0) levels 1 and 2 are copies.
+constexpr uint32_t kCap1 = 32;   // level 0's bound is MsmPlan::cap0 (8 .. 128)
 
 // seg[b + 1] = ceil((off[b + 1] - off[b]) / cap), seg[0] = 0; an inclusive scan turns it into segment offsets
 __global__ void __launch_bounds__(kThreads) msm_segments_kernel(const u64* off, uint64_t n_keys, uint32_t cap, u64* seg) {
@@ -182,14 +188,65 @@ __device__ __forceinline__ uint64_t owner_of(const u64* seg, uint64_t n_keys, u6
     }
     return lo;
 }
-__global__ void __launch_bounds__(kMsmThreads, ZK_MSM_MIN_BLOCKS) msm_bucket_kernel(const u64* off, const u64* seg0, const uint32_t* sorted,
+// Level 0 runs its segments longest first (a counting sort on the segment length, <= 128): the 32 threads of a warp then
+// add the same number of points, where bucket order would leave most of them waiting for the warp's fullest bucket.
+constexpr int kLenBins = 129;
+// where segment s starts in `sorted` and how long it is; histogram of the lengths (block-private, then global)
+__global__ void __launch_bounds__(kThreads) msm_segdesc_kernel(const u64* off, const u64* seg0, uint64_t n_keys, uint64_t max_segments, uint32_t cap0,
+                                                               u64* seg_lo, uint8_t* seg_len, unsigned* ghist) {
+    __shared__ unsigned hist[kLenBins];
+    for (int i = threadIdx.x; i < kLenBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint64_t sidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx < max_segments && sidx < seg0[n_keys]) {
+        const uint64_t b = owner_of(seg0, n_keys, sidx);
+        const u64 lo = off[b] + (sidx - seg0[b]) * cap0;
+        const uint32_t len = (uint32_t)min((u64)cap0, off[b + 1] - lo);
+        seg_lo[sidx] = lo;
+        seg_len[sidx] = (uint8_t)len;
+        atomicAdd(&hist[len], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kLenBins; i += blockDim.x)
+        if (hist[i]) atomicAdd(&ghist[i], hist[i]);
+}
+// first rank of every length, longest first
+__global__ void msm_lenscan_kernel(const unsigned* ghist, unsigned* gcursor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned run = 0;
+        for (int l = kLenBins - 1; l >= 0; --l) {
+            gcursor[l] = run;
+            run += ghist[l];
+        }
+    }
+}
+// order[rank] = segment: a block reserves a range per length, its threads take places inside
+__global__ void __launch_bounds__(kThreads) msm_segplace_kernel(const u64* seg0, uint64_t n_keys, uint64_t max_segments, const uint8_t* seg_len,
+                                                                unsigned* gcursor, uint32_t* order) {
+    __shared__ unsigned hist[kLenBins], base[kLenBins];
+    for (int i = threadIdx.x; i < kLenBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint64_t sidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = sidx < max_segments && sidx < seg0[n_keys];
+    unsigned len = 0, rank = 0;
+    if (valid) {
+        len = seg_len[sidx];
+        rank = atomicAdd(&hist[len], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kLenBins; i += blockDim.x)
+        if (hist[i]) base[i] = atomicAdd(&gcursor[i], hist[i]);
+    __syncthreads();
+    if (valid) order[base[len] + rank] = (uint32_t)sidx;
+}
+__global__ void __launch_bounds__(kMsmThreads, ZK_MSM_MIN_BLOCKS) msm_bucket_kernel(const u64* seg0, const u64* seg_lo, const uint8_t* seg_len,
+                                                                                      const uint32_t* order, const uint32_t* sorted,
                                                                                       const G1Affine* bases, uint64_t n_keys, uint64_t max_segments,
                                                                                       G1Xyzz* part0) {
-    const uint64_t sidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (sidx >= max_segments || sidx >= seg0[n_keys]) return;
-    const uint64_t b = owner_of(seg0, n_keys, sidx);
-    const u64 lo = off[b] + (sidx - seg0[b]) * kCap0;
-    const u64 hi = min(lo + (u64)kCap0, off[b + 1]);
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= max_segments || t >= seg0[n_keys]) return;
+    const uint64_t sidx = order ? order[t] : t;
+    const u64 lo = seg_lo[sidx], hi = lo + seg_len[sidx];
     G1Xyzz acc = G1::infinity();
 #pragma unroll 1
     for (u64 e = lo; e < hi; ++e) {
@@ -273,16 +330,17 @@ __global__ void __launch_bounds__(kMsmThreads) msm_chunk_kernel(const G1Xyzz* bu
 // level 2: sum_t acc_t and sum_t t run_t over a window's nT chunks, the second as bit planes of t:
 //   plane p < nb:  P_p = sum of run_t over the t whose bit p is set   (sum_t t run_t = sum_p 2^p P_p)
 //   plane nb:      A   = sum of acc_t
-// One warp per (window, plane): every lane adds its share of the chunks, then a five-step butterfly over the lanes.
-__global__ void __launch_bounds__(kMsmThreads) msm_plane_kernel(const G1Xyzz* chunk_acc, const G1Xyzz* chunk_run, uint32_t n_warps, uint32_t nT,
-                                                                uint32_t nb, G1Xyzz* planes) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n_warps) return;   // whole warps leave together
-    const uint32_t w = warp / (nb + 1), p = warp % (nb + 1);
+// One block per (window, plane): every thread adds its share of the chunks, a five-step butterfly folds each warp, and the
+// warp results meet in shared memory.
+__global__ void __launch_bounds__(kMsmThreads) msm_plane_kernel(const G1Xyzz* chunk_acc, const G1Xyzz* chunk_run, uint32_t nT, uint32_t nb,
+                                                                G1Xyzz* planes) {
+    __shared__ G1Xyzz warp_sum[kMsmThreads / 32];
+    const uint32_t plane = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t w = plane / (nb + 1), p = plane % (nb + 1);
     const G1Xyzz* src = (p == nb ? chunk_acc : chunk_run) + (uint64_t)w * nT;
     G1Xyzz acc = G1::infinity();
 #pragma unroll 1
-    for (uint32_t t = lane; t < nT; t += 32) {
+    for (uint32_t t = threadIdx.x; t < nT; t += blockDim.x) {
         if (p == nb || ((t >> p) & 1u)) {
             const G1Xyzz v = load_xyzz(src + t);
             G1::add(acc, v);
@@ -293,7 +351,13 @@ __global__ void __launch_bounds__(kMsmThreads) msm_plane_kernel(const G1Xyzz* ch
         const G1Xyzz o = shfl_xyzz(acc, delta, true);
         if ((int)lane < delta) G1::add(acc, o);
     }
-    if (lane == 0) store_xyzz(planes + warp, acc);
+    if (lane == 0) warp_sum[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int k = 1; k < kMsmThreads / 32; ++k) G1::add(acc, warp_sum[k]);
+        store_xyzz(planes + plane, acc);
+    }
 }
 
 // ---------------------------------------------------------------- trusted setup on the GPU
@@ -435,7 +499,10 @@ struct zk_kzg_setup {
     G1Affine* storage = nullptr;          // all levels, 2^(n+1) points
     // workspace of the multi-scalar multiplication, sized for 2^n points
     u64 *off = nullptr, *cursor = nullptr, *scan_scratch = nullptr, *seg0 = nullptr, *seg1 = nullptr;
-    uint32_t* sorted = nullptr;
+    uint32_t *sorted = nullptr, *order = nullptr;
+    u64* seg_lo = nullptr;
+    uint8_t* seg_len = nullptr;
+    unsigned* len_hist = nullptr;       // [2][kLenBins]: histogram of the segment lengths, then the placement cursors
     G1Xyzz *buckets = nullptr, *part0 = nullptr, *part1 = nullptr, *chunk_acc = nullptr, *chunk_run = nullptr, *win = nullptr;
     HG1Xyzz* win_host = nullptr;          // pinned
     Fe *cur = nullptr, *quot = nullptr;   // open_and_prove: the remainder and quotient tables
@@ -444,18 +511,20 @@ struct zk_kzg_setup {
 
 namespace {
 int msm_reserve(zk_ctx* ctx, zk_kzg_setup* s, uint64_t max_points) {
-    uint64_t keys = 0, entries = 0, chunks = 0;
+    uint64_t keys = 0, entries = 0, chunks = 0, segs0 = 0;
     for (uint64_t p2 = 1; p2 / 2 < max_points; p2 <<= 1) {   // every size open_and_prove will use, and max_points itself
         const uint64_t n = std::min(p2, max_points);
         const MsmPlan pl = plan_for(n);
         keys = std::max<uint64_t>(keys, (uint64_t)pl.W * pl.B);
         entries = std::max<uint64_t>(entries, n * pl.W);
         chunks = std::max<uint64_t>(chunks, (uint64_t)pl.W * (pl.B / pl.S));
+        segs0 = std::max<uint64_t>(segs0, (uint64_t)pl.W * pl.B + n * pl.W / pl.cap0);
     }
     if (getenv("ZKB200_MSM_WINDOW")) {   // a forced window width: size for the widest plan
         keys = std::max<uint64_t>(keys, 128ull * 32768);
         entries = std::max<uint64_t>(entries, max_points * 128);
         chunks = std::max<uint64_t>(chunks, 128ull * 32768);
+        segs0 = std::max<uint64_t>(segs0, keys + entries / 8);
     }
     if (max_points <= s->cap_points && keys <= s->cap_keys && chunks <= s->cap_chunks) return ZK_OK;
     if (s->cap_points) return fail(ctx, ZK_ERR_ARG, "multi-scalar multiplication workspace is sized once");
@@ -466,8 +535,12 @@ int msm_reserve(zk_ctx* ctx, zk_kzg_setup* s, uint64_t max_points) {
     ZK_CUDA(cudaMalloc(&s->seg0, (keys + 1) * sizeof(u64)));
     ZK_CUDA(cudaMalloc(&s->seg1, (keys + 1) * sizeof(u64)));
     ZK_CUDA(cudaMalloc(&s->buckets, keys * sizeof(G1Xyzz)));
-    ZK_CUDA(cudaMalloc(&s->part0, (keys + entries / kCap0 + 1) * sizeof(G1Xyzz)));
-    ZK_CUDA(cudaMalloc(&s->part1, (keys + (keys + entries / kCap0) / kCap1 + 1) * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaMalloc(&s->part0, (segs0 + 1) * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaMalloc(&s->order, (segs0 + 1) * sizeof(uint32_t)));
+    ZK_CUDA(cudaMalloc(&s->seg_lo, (segs0 + 1) * sizeof(u64)));
+    ZK_CUDA(cudaMalloc(&s->seg_len, segs0 + 1));
+    ZK_CUDA(cudaMalloc(&s->len_hist, 2 * 129 * sizeof(unsigned)));
+    ZK_CUDA(cudaMalloc(&s->part1, (keys + segs0 / kCap1 + 1) * sizeof(G1Xyzz)));
     ZK_CUDA(cudaMalloc(&s->chunk_acc, chunks * sizeof(G1Xyzz)));
     ZK_CUDA(cudaMalloc(&s->chunk_run, chunks * sizeof(G1Xyzz)));
     ZK_CUDA(cudaMalloc(&s->win, kMaxPlanes * sizeof(G1Xyzz)));
@@ -493,12 +566,20 @@ int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* base
     msm_scatter_kernel<<<blocks_for(ctx, n, kThreads, 8), kThreads, 0, st>>>(scalars, n, pl, s->cursor, s->sorted);
     // bucket sums in three bounded levels (see msm_bucket_kernel); the segment counts never come to the host, the grids
     // are sized by their upper bounds
-    const uint64_t max0 = keys + n * (uint64_t)pl.W / kCap0, max1 = keys + max0 / kCap1;
-    msm_segments_kernel<<<blocks_for(ctx, keys, kThreads, 8), kThreads, 0, st>>>(s->off, keys, kCap0, s->seg0);
+    const uint64_t max0 = keys + n * (uint64_t)pl.W / pl.cap0, max1 = keys + max0 / kCap1;
+    msm_segments_kernel<<<blocks_for(ctx, keys, kThreads, 8), kThreads, 0, st>>>(s->off, keys, pl.cap0, s->seg0);
     scan::inclusive_scan(st, s->seg0, keys + 1, s->scan_scratch);
     msm_segments_kernel<<<blocks_for(ctx, keys, kThreads, 8), kThreads, 0, st>>>(s->seg0, keys, kCap1, s->seg1);
     scan::inclusive_scan(st, s->seg1, keys + 1, s->scan_scratch);
-    msm_bucket_kernel<<<(unsigned)((max0 + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->off, s->seg0, s->sorted, bases, keys, max0, s->part0);
+    static const bool by_length = !(getenv("ZKB200_MSM_SORT") && atoi(getenv("ZKB200_MSM_SORT")) == 0);
+    ZK_CUDA(cudaMemsetAsync(s->len_hist, 0, 2 * kLenBins * sizeof(unsigned), st));
+    msm_segdesc_kernel<<<(unsigned)((max0 + kThreads - 1) / kThreads), kThreads, 0, st>>>(s->off, s->seg0, keys, max0, pl.cap0, s->seg_lo, s->seg_len, s->len_hist);
+    if (by_length) {
+        msm_lenscan_kernel<<<1, 32, 0, st>>>(s->len_hist, s->len_hist + kLenBins);
+        msm_segplace_kernel<<<(unsigned)((max0 + kThreads - 1) / kThreads), kThreads, 0, st>>>(s->seg0, keys, max0, s->seg_len, s->len_hist + kLenBins, s->order);
+    }
+    msm_bucket_kernel<<<(unsigned)((max0 + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->seg0, s->seg_lo, s->seg_len, by_length ? s->order : nullptr,
+                                                                                                   s->sorted, bases, keys, max0, s->part0);
     msm_merge_kernel<<<(unsigned)((max1 + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->seg0, s->seg1, s->part0, keys, max1, s->part1);
     msm_finish_kernel<<<(unsigned)((keys + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->seg1, s->part1, keys, s->buckets);
     const uint64_t n_chunks = (uint64_t)pl.W * nT;
@@ -507,8 +588,8 @@ int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* base
     while ((1u << nb) < nT) ++nb;
     while ((1u << log_s) < pl.S) ++log_s;
     const uint32_t n_planes = (uint32_t)pl.W * (nb + 1);
-    msm_plane_kernel<<<(n_planes * 32 + kMsmThreads - 1) / kMsmThreads, kMsmThreads, 0, st>>>(s->chunk_acc, s->chunk_run, n_planes, nT, nb, s->win);
-    ctx->launches += 18;
+    msm_plane_kernel<<<n_planes, kMsmThreads, 0, st>>>(s->chunk_acc, s->chunk_run, nT, nb, s->win);
+    ctx->launches += 21;
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaMemcpyAsync(s->win_host, s->win, (size_t)n_planes * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
     ZK_CUDA(cudaStreamSynchronize(st));
@@ -571,6 +652,7 @@ void setup_delete(zk_kzg_setup* s) {
     cudaSetDevice(s->device);
     cudaFree(s->storage); cudaFree(s->off); cudaFree(s->cursor); cudaFree(s->scan_scratch); cudaFree(s->sorted);
     cudaFree(s->seg0); cudaFree(s->seg1); cudaFree(s->part0); cudaFree(s->part1);
+    cudaFree(s->order); cudaFree(s->seg_lo); cudaFree(s->seg_len); cudaFree(s->len_hist);
     cudaFree(s->buckets); cudaFree(s->chunk_acc); cudaFree(s->chunk_run); cudaFree(s->win); cudaFree(s->cur); cudaFree(s->quot);
     if (s->win_host) cudaFreeHost(s->win_host);
     delete s;
