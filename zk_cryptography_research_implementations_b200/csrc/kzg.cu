@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -46,7 +47,8 @@ typedef unsigned long long u64;
 #define ZK_MSM_MIN_BLOCKS 3
 #endif
 constexpr int kMsmThreads = ZK_MSM_THREADS;   // the group law needs ~150-250 registers: small blocks keep the SMs evenly filled
-constexpr int kMaxPlanes = 128 * 17;  // windows x (bit planes of the chunk index + 1), widest plan
+// open_and_prove sums the quotients of its last levels (2^kBatchLog points and fewer: each too small to fill the GPU) in ONE pass
+constexpr uint32_t kBatchLog = 15;
 constexpr int kFixedWindows = 32;    // fixed-base table of the generator: 32 windows of 8 bits
 
 struct MsmPlan {
@@ -55,8 +57,11 @@ struct MsmPlan {
     uint32_t B;       // buckets per window = 2^(c-1); bucket b holds the points whose digit is +-(b + 1)
     uint32_t S;       // buckets per running-sum chunk
     uint32_t cap0;    // entries per level-0 segment of the bucket sums
+    // several sums in one pass (the small levels of an opening): `groups` consecutive index ranges of halving size, the first
+    // 2^n0_log long (2^n0_log, 2^(n0_log-1), .., 1); every group has its own windows.  groups == 1: one plain sum.
+    uint32_t groups, n0_log;
 };
-MsmPlan plan_for(uint64_t n) {
+MsmPlan plan_for(uint64_t n, uint32_t groups = 1, uint32_t n0_log = 0) {
     int c = n >= (1u << 20) ? 16 : n >= (1u << 16) ? 13 : n >= (1u << 12) ? 10 : n >= (1u << 8) ? 7 : 4;
     if (const char* e = getenv("ZKB200_MSM_WINDOW")) {
         const int v = atoi(e);
@@ -72,6 +77,8 @@ MsmPlan plan_for(uint64_t n) {
     const uint64_t entries = n * (uint64_t)p.W;
     p.cap0 = 8;
     while (p.cap0 < 128 && entries / p.cap0 > 65536) p.cap0 <<= 1;
+    p.groups = groups;
+    p.n0_log = n0_log;
     return p;
 }
 
@@ -121,9 +128,16 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t k[8], int lo, int
     if (word + 1 < 8) v |= (uint64_t)k[word + 1] << 32;
     return (uint32_t)(v >> sh) & ((1u << c) - 1u);
 }
-// calls f(window, bucket, negative) for every non-zero digit of k
-template <typename Fn> __device__ __forceinline__ void for_each_digit(const uint32_t k[8], const MsmPlan& pl, Fn f) {
+// the group of index i under the halving layout: group g covers 2^(n0_log - g) indices
+__device__ __forceinline__ uint32_t group_of(uint64_t i, const MsmPlan& pl) {
+    if (pl.groups == 1) return 0;
+    const uint64_t r = ((2ull << pl.n0_log) - 1) - i;   // counts down from 2^(n0_log+1) - 1
+    return pl.n0_log - (63 - __clzll((long long)r));
+}
+// calls f(window, bucket, negative) for every non-zero digit of k; `window` already carries the group's offset
+template <typename Fn> __device__ __forceinline__ void for_each_digit(const uint32_t k[8], const MsmPlan& pl, uint32_t group, Fn f) {
     uint32_t carry = 0;
+    const int w0 = (int)group * pl.W;
     for (int w = 0; w < pl.W; ++w) {
         uint32_t d = window_bits(k, w * pl.c, pl.c) + carry;
         carry = 0;
@@ -133,7 +147,7 @@ template <typename Fn> __device__ __forceinline__ void for_each_digit(const uint
             neg = true;
             carry = 1;
         }
-        if (d) f(w, d - 1u, neg);
+        if (d) f(w0 + w, d - 1u, neg);
     }
 }
 
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) msm_count_kernel(const Fe* scalars, 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t k[8];
         canonical_scalar(k, scalars[i]);
-        for_each_digit(k, pl, [&](int w, uint32_t b, bool) { atomicAdd(off + (uint64_t)w * pl.B + b + 1, 1ull); });
+        for_each_digit(k, pl, group_of(i, pl), [&](int w, uint32_t b, bool) { atomicAdd(off + (uint64_t)w * pl.B + b + 1, 1ull); });
     }
 }
 // entry = point index | sign << 31, to the next free place of its bucket (cursor starts as a copy of off[0..W*B))
@@ -152,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) msm_scatter_kernel(const Fe* scalars
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t k[8];
         canonical_scalar(k, scalars[i]);
-        for_each_digit(k, pl, [&](int w, uint32_t b, bool neg) {
+        for_each_digit(k, pl, group_of(i, pl), [&](int w, uint32_t b, bool neg) {
             const u64 p = atomicAdd(cursor + (uint64_t)w * pl.B + b, 1ull);
             sorted[p] = (uint32_t)i | (neg ? 0x80000000u : 0u);
         });
@@ -511,20 +525,28 @@ struct zk_kzg_setup {
 
 namespace {
 int msm_reserve(zk_ctx* ctx, zk_kzg_setup* s, uint64_t max_points) {
-    uint64_t keys = 0, entries = 0, chunks = 0, segs0 = 0;
+    uint64_t keys = 0, entries = 0, chunks = 0, segs0 = 0, planes = 0;
+    auto account = [&](const MsmPlan& pl, uint64_t n) {
+        const uint64_t k = (uint64_t)pl.groups * pl.W * pl.B, nT = pl.B / pl.S;
+        uint32_t nb = 0;
+        while ((1ull << nb) < nT) ++nb;
+        keys = std::max<uint64_t>(keys, k);
+        entries = std::max<uint64_t>(entries, n * pl.W);
+        chunks = std::max<uint64_t>(chunks, (uint64_t)pl.groups * pl.W * nT);
+        segs0 = std::max<uint64_t>(segs0, k + n * pl.W / pl.cap0);
+        planes = std::max<uint64_t>(planes, (uint64_t)pl.groups * pl.W * (nb + 1));
+    };
     for (uint64_t p2 = 1; p2 / 2 < max_points; p2 <<= 1) {   // every size open_and_prove will use, and max_points itself
         const uint64_t n = std::min(p2, max_points);
-        const MsmPlan pl = plan_for(n);
-        keys = std::max<uint64_t>(keys, (uint64_t)pl.W * pl.B);
-        entries = std::max<uint64_t>(entries, n * pl.W);
-        chunks = std::max<uint64_t>(chunks, (uint64_t)pl.W * (pl.B / pl.S));
-        segs0 = std::max<uint64_t>(segs0, (uint64_t)pl.W * pl.B + n * pl.W / pl.cap0);
+        account(plan_for(n), n);
     }
+    for (uint32_t g = 1; g <= kBatchLog + 1; ++g) account(plan_for((2ull << (g - 1)) - 1, g, g - 1), (2ull << (g - 1)) - 1);   // batched small levels
     if (getenv("ZKB200_MSM_WINDOW")) {   // a forced window width: size for the widest plan
         keys = std::max<uint64_t>(keys, 128ull * 32768);
         entries = std::max<uint64_t>(entries, max_points * 128);
         chunks = std::max<uint64_t>(chunks, 128ull * 32768);
         segs0 = std::max<uint64_t>(segs0, keys + entries / 8);
+        planes = std::max<uint64_t>(planes, (uint64_t)(kBatchLog + 1) * 128 * 17);
     }
     if (max_points <= s->cap_points && keys <= s->cap_keys && chunks <= s->cap_chunks) return ZK_OK;
     if (s->cap_points) return fail(ctx, ZK_ERR_ARG, "multi-scalar multiplication workspace is sized once");
@@ -543,20 +565,23 @@ int msm_reserve(zk_ctx* ctx, zk_kzg_setup* s, uint64_t max_points) {
     ZK_CUDA(cudaMalloc(&s->part1, (keys + segs0 / kCap1 + 1) * sizeof(G1Xyzz)));
     ZK_CUDA(cudaMalloc(&s->chunk_acc, chunks * sizeof(G1Xyzz)));
     ZK_CUDA(cudaMalloc(&s->chunk_run, chunks * sizeof(G1Xyzz)));
-    ZK_CUDA(cudaMalloc(&s->win, kMaxPlanes * sizeof(G1Xyzz)));
-    ZK_CUDA(cudaHostAlloc(&s->win_host, kMaxPlanes * sizeof(HG1Xyzz), cudaHostAllocDefault));
+    ZK_CUDA(cudaMalloc(&s->win, planes * sizeof(G1Xyzz)));
+    ZK_CUDA(cudaHostAlloc(&s->win_host, planes * sizeof(HG1Xyzz), cudaHostAllocDefault));
     s->cap_points = max_points;
     s->cap_keys = keys;
     s->cap_chunks = chunks;
     return ZK_OK;
 }
 
-// sum_i scalars[i] * bases[i] over n device-resident pairs -> affine result on the host
-int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* bases, uint64_t n, HG1Affine* out) {
+// sum_i scalars[i] * bases[i] over n device-resident pairs -> affine result on the host.  groups > 1: `groups` sums in one
+// pass over consecutive index ranges of halving size (n = 2^groups - 1, see MsmPlan); out[g] receives the sum of range g.
+int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* bases, uint64_t n, HG1Affine* out, uint32_t groups = 1) {
     static_assert(sizeof(HG1Xyzz) == sizeof(G1Xyzz) && sizeof(HG1Affine) == sizeof(G1Affine), "host and device point layouts");
     if (n >= (1ull << 31)) return fail(ctx, ZK_ERR_ARG, "multi-scalar multiplication over 2^31 or more points");
-    const MsmPlan pl = plan_for(n);
-    const uint64_t keys = (uint64_t)pl.W * pl.B;
+    if (groups > 1 && n != (1ull << groups) - 1) return fail(ctx, ZK_ERR_ARG, "grouped sum: n must be 2^groups - 1");
+    const MsmPlan pl = plan_for(n, groups, groups - 1);
+    const int WG = pl.W * (int)groups;                      // windows of all groups
+    const uint64_t keys = (uint64_t)WG * pl.B;
     const uint32_t nT = pl.B / pl.S;
     cudaStream_t st = ctx->stream;
     ZK_CUDA(cudaMemsetAsync(s->off, 0, (keys + 1) * sizeof(u64), st));
@@ -582,12 +607,12 @@ int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* base
                                                                                                    s->sorted, bases, keys, max0, s->part0);
     msm_merge_kernel<<<(unsigned)((max1 + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->seg0, s->seg1, s->part0, keys, max1, s->part1);
     msm_finish_kernel<<<(unsigned)((keys + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->seg1, s->part1, keys, s->buckets);
-    const uint64_t n_chunks = (uint64_t)pl.W * nT;
+    const uint64_t n_chunks = (uint64_t)WG * nT;
     msm_chunk_kernel<<<(unsigned)((n_chunks + kMsmThreads - 1) / kMsmThreads), kMsmThreads, 0, st>>>(s->buckets, n_chunks, pl.S, s->chunk_acc, s->chunk_run);
     uint32_t nb = 0, log_s = 0;
     while ((1u << nb) < nT) ++nb;
     while ((1u << log_s) < pl.S) ++log_s;
-    const uint32_t n_planes = (uint32_t)pl.W * (nb + 1);
+    const uint32_t n_planes = (uint32_t)WG * (nb + 1);
     msm_plane_kernel<<<n_planes, kMsmThreads, 0, st>>>(s->chunk_acc, s->chunk_run, nT, nb, s->win);
     ctx->launches += 21;
     ZK_CUDA(cudaGetLastError());
@@ -595,22 +620,35 @@ int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* base
     ZK_CUDA(cudaStreamSynchronize(st));
     // window_w = A_w + S sum_p 2^p P_{w,p};  result = sum_w 2^(c w) window_w = sum over bit positions: A_w sits at c w and
     // P_{w,p} at c w + log2(S) + p < c (w + 1).  One pass from the top bit down: a doubling per position, an addition per term.
-    std::vector<const HG1Xyzz*> at((size_t)pl.W * pl.c, nullptr), at2((size_t)pl.W * pl.c, nullptr);
-    for (int w = 0; w < pl.W; ++w) {
-        const HG1Xyzz* base = s->win_host + (size_t)w * (nb + 1);
-        at[(size_t)w * pl.c] = base + nb;
-        for (uint32_t p = 0; p < nb; ++p) {
-            const size_t pos = (size_t)w * pl.c + log_s + p;
-            (at[pos] ? at2[pos] : at[pos]) = base + p;
+    auto combine = [&](uint32_t g) {
+        std::vector<const HG1Xyzz*> at((size_t)pl.W * pl.c, nullptr), at2((size_t)pl.W * pl.c, nullptr);
+        for (int w = 0; w < pl.W; ++w) {
+            const HG1Xyzz* base = s->win_host + ((size_t)g * pl.W + w) * (nb + 1);
+            at[(size_t)w * pl.c] = base + nb;
+            for (uint32_t p = 0; p < nb; ++p) {
+                const size_t pos = (size_t)w * pl.c + log_s + p;
+                (at[pos] ? at2[pos] : at[pos]) = base + p;
+            }
         }
+        HG1Xyzz acc = HostG1::infinity();
+        for (size_t pos = at.size(); pos-- > 0;) {
+            acc = HostG1::dbl(acc);
+            if (at[pos]) acc = HostG1::add(acc, *at[pos]);
+            if (at2[pos]) acc = HostG1::add(acc, *at2[pos]);
+        }
+        out[g] = HostG1::to_affine(acc);
+    };
+    if (groups == 1) {
+        combine(0);
+    } else {   // the groups' finishes are independent: a few host threads
+        const uint32_t nthreads = std::min<uint32_t>(groups, std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
+        std::vector<std::thread> pool;
+        for (uint32_t t = 0; t < nthreads; ++t)
+            pool.emplace_back([&, t]() {
+                for (uint32_t g = t; g < groups; g += nthreads) combine(g);
+            });
+        for (std::thread& th : pool) th.join();
     }
-    HG1Xyzz acc = HostG1::infinity();
-    for (size_t pos = at.size(); pos-- > 0;) {
-        acc = HostG1::dbl(acc);
-        if (at[pos]) acc = HostG1::add(acc, *at[pos]);
-        if (at2[pos]) acc = HostG1::add(acc, *at2[pos]);
-    }
-    *out = HostG1::to_affine(acc);
     return ZK_OK;
 }
 
@@ -644,7 +682,7 @@ int setup_alloc(zk_ctx* ctx, uint32_t n, std::unique_ptr<zk_kzg_setup, void (*)(
         o += len >> k;
     }
     ZK_CUDA(cudaMalloc(&s->cur, len * sizeof(Fe)));
-    ZK_CUDA(cudaMalloc(&s->quot, (len / 2 + 1) * sizeof(Fe)));
+    ZK_CUDA(cudaMalloc(&s->quot, len * sizeof(Fe)));   // every round's quotient of one opening: 2^n - 1 elements
     return msm_reserve(ctx, s.get(), len);
 }
 void setup_delete(zk_kzg_setup* s) {
@@ -788,21 +826,41 @@ extern "C" int zk_kzg_commit(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* vals,
 }
 
 namespace {
-// `cur` holds the polynomial (it is consumed)
+// `cur` holds the polynomial (it is consumed).  All quotients are formed first -- round i's goes where level i + 1 of the
+// setup sits relative to level 1, so the quotients of the last rounds and the setup levels they meet are two parallel runs
+// of halving blocks -- then the large rounds are summed one by one and the small ones (<= 2^kBatchLog points) in one pass.
 int open_impl(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* opening, uint64_t eval[4], uint64_t* proofs) {
     const uint32_t n = s->n;
+    static const bool batch_small = !(getenv("ZKB200_KZG_BATCH") && atoi(getenv("ZKB200_KZG_BATCH")) == 0);
+    std::vector<uint64_t> qoff(n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) qoff[i + 1] = qoff[i] + (1ull << (n - i - 1));
     for (uint32_t i = 0; i < n; ++i) {
         const uint64_t half = 1ull << (n - i - 1);
         Fe r;
         memcpy(r.v, opening + 4 * i, sizeof r);
-        quotient_fold_kernel<<<blocks_for(ctx, half, kThreads, 8), kThreads, 0, ctx->stream>>>(s->cur, half, r, s->quot);
+        quotient_fold_kernel<<<blocks_for(ctx, half, kThreads, 8), kThreads, 0, ctx->stream>>>(s->cur, half, r, s->quot + qoff[i]);
         ++ctx->launches;
+    }
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpyAsync(eval, s->cur, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t first_small = n;   // rounds first_small .. n-1 are summed together
+    if (batch_small)
+        for (uint32_t i = 0; i < n; ++i)
+            if (n - i - 1 <= kBatchLog) { first_small = i; break; }
+    if (n - first_small < 2) first_small = n;
+    for (uint32_t i = 0; i < first_small; ++i) {
         HG1Affine pr;
-        int rc = g1_msm(ctx, s, s->quot, s->level[i + 1], half, &pr);
+        int rc = g1_msm(ctx, s, s->quot + qoff[i], s->level[i + 1], 1ull << (n - i - 1), &pr);
         if (rc) return rc;
         memcpy(proofs + 12 * i, &pr, sizeof pr);
     }
-    ZK_CUDA(cudaMemcpyAsync(eval, s->cur, sizeof(Fe), cudaMemcpyDeviceToHost, ctx->stream));
+    if (first_small < n) {
+        const uint32_t groups = n - first_small;
+        std::vector<HG1Affine> pr(groups);
+        int rc = g1_msm(ctx, s, s->quot + qoff[first_small], s->level[first_small + 1], (1ull << groups) - 1, pr.data(), groups);
+        if (rc) return rc;
+        memcpy(proofs + 12 * first_small, pr.data(), groups * sizeof(HG1Affine));
+    }
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     return ZK_OK;
 }
