@@ -67,29 +67,33 @@ static inline void q_sub(fq *r, const fq *a, const fq *b) {
     if (q_sub6(t, a->l, b->l)) q_add6(t, t, ZKC_Q_64);
     memcpy(r->l, t, 48);
 }
-static inline void q_mul(fq *r, const fq *a, const fq *b) {   /* CIOS */
-    uint64_t t[8] = {0};
+static inline void q_mul(fq *r, const fq *a, const fq *b) {   /* CIOS, the algorithm MontBackend::mul_assign implements */
+    uint64_t t[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma GCC unroll 6
     for (int i = 0; i < 6; ++i) {
-        u128 c = 0;
+        const uint64_t bi = b->l[i];
+        uint64_t carry = 0, t7;
+#pragma GCC unroll 6
         for (int j = 0; j < 6; ++j) {
-            c += (u128)t[j] + (u128)a->l[j] * b->l[i];
-            t[j] = (uint64_t)c;
-            c >>= 64;
+            const u128 p = (u128)a->l[j] * bi + t[j] + carry;   /* < 2^128: no overflow */
+            t[j] = (uint64_t)p;
+            carry = (uint64_t)(p >> 64);
         }
-        c += t[6];
-        t[6] = (uint64_t)c;
-        t[7] = (uint64_t)(c >> 64);
-        uint64_t m = t[0] * ZKC_INV64;
-        c = (u128)t[0] + (u128)m * ZKC_Q_64[0];
-        c >>= 64;
+        u128 s = (u128)t[6] + carry;
+        t[6] = (uint64_t)s;
+        t7 = (uint64_t)(s >> 64);
+        const uint64_t m = t[0] * ZKC_INV64;
+        u128 p = (u128)m * ZKC_Q_64[0] + t[0];
+        carry = (uint64_t)(p >> 64);
+#pragma GCC unroll 5
         for (int j = 1; j < 6; ++j) {
-            c += (u128)t[j] + (u128)m * ZKC_Q_64[j];
-            t[j - 1] = (uint64_t)c;
-            c >>= 64;
+            p = (u128)m * ZKC_Q_64[j] + t[j] + carry;
+            t[j - 1] = (uint64_t)p;
+            carry = (uint64_t)(p >> 64);
         }
-        c += t[6];
-        t[5] = (uint64_t)c;
-        t[6] = t[7] + (uint64_t)(c >> 64);
+        s = (u128)t[6] + carry;
+        t[5] = (uint64_t)s;
+        t[6] = t7 + (uint64_t)(s >> 64);
     }
     if (t[6] || q_ge(t)) q_sub6(t, t, ZKC_Q_64);
     memcpy(r->l, t, 48);
