@@ -312,6 +312,13 @@ int  zk_kzg_open(zk_ctx *, zk_kzg_setup *, const uint64_t *evaluated_values, uin
                  uint32_t n_opening, uint64_t evaluation[4], uint64_t *proofs /* 12 * n */);
 int  zk_kzg_open_device(zk_ctx *, zk_kzg_setup *, const zk_table *, const uint64_t *opening_values, uint32_t n_opening,
                         uint64_t evaluation[4], uint64_t *proofs);
+/* Several GPUs (one process per GPU, after zk_comm_init): the setup and the polynomial are replicated on every rank (like the
+ * circuit and the input layer of zk_gkr_prove_wide_sharded); rank q sums the q-th contiguous share of the points of every
+ * large sum, the partial results (96 bytes each) are all-gathered once per call and added in rank order: every rank returns
+ * the same points, equal to the unsharded calls'. */
+int  zk_kzg_commit_sharded(zk_ctx *, zk_kzg_setup *, const zk_table *, uint64_t commitment[12]);
+int  zk_kzg_open_sharded(zk_ctx *, zk_kzg_setup *, const zk_table *, const uint64_t *opening_values, uint32_t n_opening,
+                         uint64_t evaluation[4], uint64_t *proofs);
 /* The verifier's half, host only (no context, no GPU; the prover never calls these).  G2 points: affine x.c0, x.c1, y.c0,
  * y.c1 (4 x 6 limbs, Montgomery; `G2Affine`'s coordinates), infinity all zero.
  * compute_g2_powers_of_tau (trusted_setup.rs:65-78): out[i] = taus[i] * G2.  ZK_ERR_ASSERT for n == 0. */

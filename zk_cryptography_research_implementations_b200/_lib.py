@@ -114,6 +114,8 @@ SIGNATURES = {
     "zk_kzg_commit_device": (C.c_int, [vp, vp, vp, u64p]),
     "zk_kzg_open": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint32, u64p, u64p]),
     "zk_kzg_open_device": (C.c_int, [vp, vp, vp, u64p, C.c_uint32, u64p, u64p]),
+    "zk_kzg_commit_sharded": (C.c_int, [vp, vp, vp, u64p]),
+    "zk_kzg_open_sharded": (C.c_int, [vp, vp, vp, u64p, C.c_uint32, u64p, u64p]),
     "zk_g1_msm": (C.c_int, [vp, u64p, u64p, C.c_uint64, u64p]),
     "zk_kzg_g2_powers_of_tau": (C.c_int, [u64p, C.c_uint32, u64p]),
     "zk_kzg_verify": (C.c_int, [u64p, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p, C.c_uint32, C.POINTER(C.c_int)]),

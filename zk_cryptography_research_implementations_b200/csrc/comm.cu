@@ -291,6 +291,28 @@ static int exchange_sum(zk_ctx* ctx, HFe* vals, int ne) {
     return ZK_OK;
 }
 
+// recv[q * bytes ..] = rank q's `bytes` bytes of `send` (host buffers; staged through the device for NCCL).
+// `recv` must hold ctx->world * bytes.
+namespace zk {
+int allgather_host_bytes(zk_ctx* ctx, const void* send, size_t bytes, void* recv) {
+    const int G = ctx->world;
+    if (G == 1) {
+        memcpy(recv, send, bytes);
+        return ZK_OK;
+    }
+    if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_ARG, "zk_comm_init has not been called");
+    int rc = ensure_scratch(ctx, bytes * (size_t)(G + 1));
+    if (rc) return rc;
+    uint8_t* d_send = (uint8_t*)ctx->scratch;
+    uint8_t* d_recv = d_send + bytes;
+    ZK_CUDA(cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_NCCL(g_nccl.AllGather(d_send, d_recv, bytes, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(recv, d_recv, bytes * G, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+}  // namespace zk
+
 // all-gather every table of the sumpoly and interleave: afterwards each rank holds the full tables
 static int collapse(zk_ctx* ctx, zk_sumpoly* sp) {
     const int G = ctx->world;

@@ -32,6 +32,8 @@ int launch_fold0(zk_ctx* ctx, const TablePtrs& tp, int ntables, uint64_t len, co
 // sharded: the tables are this rank's shard and the partial evaluations are exchanged between the ranks' kernels over
 // peer memory (comm.cu must have attached the peers).  vals_out receives (D+1) elements per round, chal_out (may be
 // null) one; *rounds_run (may be null) the number of rounds the launch ran.
+// comm.cu: recv[q * bytes ..] = rank q's `send` (host buffers), over the communicator of zk_comm_init; world == 1 copies
+int allgather_host_bytes(zk_ctx* ctx, const void* send, size_t bytes, void* recv);
 bool dev_rounds_apply(const zk_ctx* ctx, uint64_t len, int tables, uint32_t flags);
 int run_dev_rounds(zk_ctx* ctx, const TablePtrs& tp, int P, int D, int nlin, int mode, uint64_t len, const HFe* pending_r, HostTranscript& tr,
                    uint64_t* vals_out, uint64_t* chal_out, uint64_t* finals, uint32_t max_rounds = 0, bool sharded = false,

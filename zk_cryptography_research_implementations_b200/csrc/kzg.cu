@@ -829,8 +829,19 @@ namespace {
 // `cur` holds the polynomial (it is consumed).  All quotients are formed first -- round i's goes where level i + 1 of the
 // setup sits relative to level 1, so the quotients of the last rounds and the setup levels they meet are two parallel runs
 // of halving blocks -- then the large rounds are summed one by one and the small ones (<= 2^kBatchLog points) in one pass.
-int open_impl(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* opening, uint64_t eval[4], uint64_t* proofs) {
+// sum over ranks, in rank order, of one partial affine point per rank and item: all[q * items + i]
+void sum_partials(const std::vector<HG1Affine>& all, int world, size_t items, uint64_t* out) {
+    for (size_t i = 0; i < items; ++i) {
+        HG1Xyzz acc = HostG1::infinity();
+        for (int q = 0; q < world; ++q) acc = HostG1::add(acc, HostG1::from_affine(all[(size_t)q * items + i]));
+        const HG1Affine r = HostG1::to_affine(acc);
+        memcpy(out + 12 * i, &r, sizeof r);
+    }
+}
+
+int open_impl(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* opening, uint64_t eval[4], uint64_t* proofs, bool sharded = false) {
     const uint32_t n = s->n;
+    const int G = sharded ? ctx->world : 1;
     static const bool batch_small = !(getenv("ZKB200_KZG_BATCH") && atoi(getenv("ZKB200_KZG_BATCH")) == 0);
     std::vector<uint64_t> qoff(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) qoff[i + 1] = qoff[i] + (1ull << (n - i - 1));
@@ -848,11 +859,21 @@ int open_impl(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* opening, uint64_t ev
         for (uint32_t i = 0; i < n; ++i)
             if (n - i - 1 <= kBatchLog) { first_small = i; break; }
     if (n - first_small < 2) first_small = n;
+    // the large rounds: over several ranks every rank sums its contiguous share of the points, the partial sums are
+    // exchanged once at the end and added in rank order by every rank (group elements: the affine result is canonical)
+    std::vector<HG1Affine> mine(first_small);
     for (uint32_t i = 0; i < first_small; ++i) {
-        HG1Affine pr;
-        int rc = g1_msm(ctx, s, s->quot + qoff[i], s->level[i + 1], 1ull << (n - i - 1), &pr);
+        const uint64_t half = 1ull << (n - i - 1), cnt = half / G, lo = cnt * (G > 1 ? ctx->rank : 0);
+        int rc = g1_msm(ctx, s, s->quot + qoff[i] + lo, s->level[i + 1] + lo, cnt, &mine[i]);
         if (rc) return rc;
-        memcpy(proofs + 12 * i, &pr, sizeof pr);
+    }
+    if (first_small && G > 1) {
+        std::vector<HG1Affine> all((size_t)G * first_small);   // G == ctx->world here: the gather fills world * bytes
+        int rc = allgather_host_bytes(ctx, mine.data(), first_small * sizeof(HG1Affine), all.data());
+        if (rc) return rc;
+        sum_partials(all, G, first_small, proofs);
+    } else if (first_small) {
+        memcpy(proofs, mine.data(), first_small * sizeof(HG1Affine));
     }
     if (first_small < n) {
         const uint32_t groups = n - first_small;
@@ -889,6 +910,33 @@ extern "C" int zk_kzg_open(zk_ctx* ctx, zk_kzg_setup* s, const uint64_t* vals, u
     if (rc) return rc;
     ZK_CUDA(cudaMemcpyAsync(s->cur, vals, (size_t)len * sizeof(Fe), cudaMemcpyHostToDevice, ctx->stream));
     return open_impl(ctx, s, opening, eval, proofs);
+}
+
+// ---- several GPUs (one process per GPU, zk_comm_init done): setup and polynomial replicated on every rank (like the circuit and
+// the input layer of zk_gkr_prove_wide_sharded); rank q sums the q-th contiguous share of the points of every large sum, the
+// 96-byte partial results are all-gathered over NCCL and added in rank order, so every rank returns the same canonical points.
+extern "C" int zk_kzg_commit_sharded(zk_ctx* ctx, zk_kzg_setup* s, const zk_table* t, uint64_t out[12]) {
+    int rc = require_fr(ctx);
+    if (rc) return rc;
+    if (t->len != (1ull << s->n)) return fail(ctx, ZK_ERR_ASSERT, "Polynomial evaluation must match g1 length");
+    const int G = ctx->world;
+    if (G == 1 || t->len < (uint64_t)G * 2) return zk_kzg_commit_device(ctx, s, t, out);
+    const uint64_t cnt = t->len / G, lo = cnt * ctx->rank;
+    HG1Affine mine;
+    rc = g1_msm(ctx, s, t->d + lo, s->level[0] + lo, cnt, &mine);
+    if (rc) return rc;
+    std::vector<HG1Affine> all(G);
+    rc = allgather_host_bytes(ctx, &mine, sizeof mine, all.data());
+    if (rc) return rc;
+    sum_partials(all, G, 1, out);
+    return ZK_OK;
+}
+extern "C" int zk_kzg_open_sharded(zk_ctx* ctx, zk_kzg_setup* s, const zk_table* t, const uint64_t* opening, uint32_t n_opening,
+                                   uint64_t eval[4], uint64_t* proofs) {
+    int rc = open_checks(ctx, s, t->len, n_opening);
+    if (rc) return rc;
+    ZK_CUDA(cudaMemcpyAsync(s->cur, t->d, (size_t)t->len * sizeof(Fe), cudaMemcpyDeviceToDevice, ctx->stream));
+    return open_impl(ctx, s, opening, eval, proofs, ctx->world > 1);
 }
 
 // sum_i scalars[i] * points[i] for caller-supplied points (host arrays; any n >= 1)

@@ -202,19 +202,22 @@ class SuccinctProof:                           # succinct_gkr_protocol.rs:22-32
     input_rc_proof: "MultilinearKZGProof"
 
 
-def prove_succinct(ctx: Context, circuit: WideCircuit, inputs, trusted_setup, flags: int = 0) -> SuccinctProof:
+def prove_succinct(ctx: Context, circuit: WideCircuit, inputs, trusted_setup, flags: int = 0, sharded: bool = False,
+                   collapse_len: int = 1 << 12) -> SuccinctProof:
     """succinct_gkr_protocol.rs:35-169.  The transcript flow is gkr_protocol::prove's (the commitment is not absorbed, :46-66);
     on top of it the input polynomial is committed (:43-44) and opened at rb and rc, the two halves of the input layer's
-    sumcheck challenges (:118-123, :151-154).  `ctx` must be a BLS12-381 Fr context; `inputs` host limbs or a DeviceTable."""
+    sumcheck challenges (:118-123, :151-154).  `ctx` must be a BLS12-381 Fr context; `inputs` host limbs or a DeviceTable.
+    sharded=True (after sharded.init_comm; circuit, setup and inputs replicated on every rank): the layer sumchecks and the
+    multi-scalar multiplications are spread over the ranks; every rank returns the same proof."""
     from .core import DeviceTable
     from .multilinear_kzg import MultilinearKZG
     table = inputs if isinstance(inputs, DeviceTable) else ctx.upload(as_elems(inputs).reshape(-1, 4))
-    commitment = MultilinearKZG.commit_to_polynomial(table, trusted_setup)
-    base = prove_wide(ctx, circuit, table, flags)
+    commitment = MultilinearKZG.commit_to_polynomial(table, trusted_setup, sharded=sharded)
+    base = prove_wide(ctx, circuit, table, flags, sharded=sharded, collapse_len=collapse_len)
     chal = base.sumcheck_proofs[-1].random_challenges
     mid = chal.shape[0] // 2
-    rb_proof = MultilinearKZG.open_and_prove(table, trusted_setup, chal[:mid])
-    rc_proof = MultilinearKZG.open_and_prove(table, trusted_setup, chal[mid:])
+    rb_proof = MultilinearKZG.open_and_prove(table, trusted_setup, chal[:mid], sharded=sharded)
+    rc_proof = MultilinearKZG.open_and_prove(table, trusted_setup, chal[mid:], sharded=sharded)
     return SuccinctProof(base.circuit_output, base.claimed_sum, base.sumcheck_proofs, base.wb_evaluations, base.wc_evaluations,
                          commitment, rb_proof, rc_proof)
 

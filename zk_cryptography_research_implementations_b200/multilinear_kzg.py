@@ -112,11 +112,17 @@ class MultilinearKZG:
     """`MultilinearKZG<F, P>`; `polynomial` is a MultilinearPolynomial / DeviceTable (resident) or host evaluations"""
 
     @staticmethod
-    def commit_to_polynomial(polynomial, trusted_setup: TrustedSetup) -> np.ndarray:
+    def commit_to_polynomial(polynomial, trusted_setup: TrustedSetup, sharded: bool = False) -> np.ndarray:
+        """sharded=True (after sharded.init_comm; setup and polynomial replicated on every rank, polynomial resident): every rank
+        sums its share of the points, all return the same commitment"""
         ctx = trusted_setup.ctx
         out = np.zeros(12, dtype=np.uint64)
         t = _table_of(polynomial)
-        if t is not None:
+        if sharded:
+            if t is None:
+                raise ValueError("the sharded calls take the polynomial as a DeviceTable / MultilinearPolynomial")
+            ctx.check(ctx.lib.zk_kzg_commit_sharded(ctx.h, trusted_setup.h, t.h, _ptr(out)))
+        elif t is not None:
             ctx.check(ctx.lib.zk_kzg_commit_device(ctx.h, trusted_setup.h, t.h, _ptr(out)))
         else:
             ev = as_elems(polynomial).reshape(-1, 4)
@@ -124,13 +130,18 @@ class MultilinearKZG:
         return out
 
     @staticmethod
-    def open_and_prove(polynomial, trusted_setup: TrustedSetup, opening_values) -> MultilinearKZGProof:
+    def open_and_prove(polynomial, trusted_setup: TrustedSetup, opening_values, sharded: bool = False) -> MultilinearKZGProof:
         ctx = trusted_setup.ctx
         op = as_elems(opening_values).reshape(-1, 4)
         ev_out = np.zeros(4, dtype=np.uint64)
         proofs = np.zeros((max(op.shape[0], 1), 12), dtype=np.uint64)
         t = _table_of(polynomial)
-        if t is not None:
+        if sharded:
+            if t is None:
+                raise ValueError("the sharded calls take the polynomial as a DeviceTable / MultilinearPolynomial")
+            ctx.check(ctx.lib.zk_kzg_open_sharded(ctx.h, trusted_setup.h, t.h, _ptr(op) if op.size else None, op.shape[0],
+                                                  _ptr(ev_out), _ptr(proofs)))
+        elif t is not None:
             ctx.check(ctx.lib.zk_kzg_open_device(ctx.h, trusted_setup.h, t.h, _ptr(op) if op.size else None, op.shape[0],
                                                  _ptr(ev_out), _ptr(proofs)))
         else:
