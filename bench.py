@@ -691,15 +691,20 @@ def run_kzg(args, wl, log2=None, steps=None, warmup=None):
 
 def run_succinct(args, wl, log2=None, steps=None, warmup=None):
     """SURVEY 8 f4, whole: prove_succinct (succinct_gkr_protocol.rs:35-169) = commit to the input polynomial + the GKR layer
-    sumchecks + two openings of the input polynomial at (rb, rc).  value = ms per proof, input layer resident in HBM."""
+    sumchecks + two openings of the input polynomial at (rb, rc).  value = ms per proof, input layer resident in HBM.
+    N > 1: circuit, setup and input layer replicated; the layer sumchecks and every large multi-scalar multiplication are
+    spread over the ranks (zk_gkr_prove_wide_sharded, zk_kzg_commit_sharded / zk_kzg_open_sharded); same proof on every rank."""
     field, fname, P, D, w_default, desc = wl
     w = log2 or (args.log2 if args.workload == "succinct" else 0) or w_default
     n_steps = steps or args.steps
     n_warm = args.warmup if warmup is None else warmup
     depth = 16
-    if int(os.environ.get("RANK", "0")) != 0:
-        return None
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if rank != 0:
+            return None
         # the reference's dense wiring tables cannot hold a 2^22-wide layer; its own largest succinct test is 3 layers over 8
         # inputs.  Timed sample: the reference-shaped GKR part (run_gkr) -- the commitment part is `--workload kzg`.
         args.workload = "gkr"
@@ -708,8 +713,19 @@ def run_succinct(args, wl, log2=None, steps=None, warmup=None):
     import zk_cryptography_research_implementations_b200 as zk
     from zk_cryptography_research_implementations_b200 import gkr
     from zk_cryptography_research_implementations_b200.multilinear_kzg import TrustedSetup
-    torch.cuda.set_device(0)
-    ctx = zk.Context(field, 0, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.set_device(local_rank)
+    ctx = zk.Context(field, local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        import torch.distributed as dist
+        from zk_cryptography_research_implementations_b200 import sharded
+        sharded.init_comm(ctx)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     bits, flat = wide_circuit_arrays(w, depth)
     t0 = time.perf_counter()
     circuit = gkr.WideCircuit(ctx, bits, flat=flat)
@@ -721,51 +737,65 @@ def run_succinct(args, wl, log2=None, steps=None, warmup=None):
     ctx.synchronize()
     setup_s = time.perf_counter() - t0
     dev_I = ctx.generate(SEED + 1, 0, 1 << w)
+
+    def prove(inputs=None):
+        return gkr.prove_succinct(ctx, circuit, dev_I if inputs is None else inputs, setup, sharded=world > 1, collapse_len=args.collapse_len)
     proof = None
     for _ in range(n_warm):
-        proof = gkr.prove_succinct(ctx, circuit, dev_I, setup)
-    sampler = ClockSampler(0)
+        barrier()
+        proof = prove()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.reset_stats()
     ts = []
     for _ in range(n_steps):
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        proof = gkr.prove_succinct(ctx, circuit, dev_I, setup)
+        proof = prove()
         torch.cuda.synchronize()
         ts.append((time.perf_counter() - t0) * 1e3)
     ms = statistics.mean(ts)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     launches = ctx.stats()["launches"] // max(n_steps, 1)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     e2e_ms = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         host_I = dev_I.download()
-        gkr.prove_succinct(ctx, circuit, host_I, setup)
+        prove(host_I)
         t0 = time.perf_counter()
-        pe = gkr.prove_succinct(ctx, circuit, host_I, setup)
+        pe = prove(host_I)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         assert np.array_equal(pe.input_polynomial_commitment, proof.input_polynomial_commitment)
-    t0 = time.perf_counter()
-    verified = bool(gkr.verify_succinct(ctx, circuit, proof, setup)) and bool(gkr.verify_succinct(ctx, circuit, proof, setup, bind_input_openings=True))
-    verify_s = time.perf_counter() - t0
-    rounds = circuit.total_rounds()
-    line = {"metric": "succinct_gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": 1, "steps": n_steps, "warmup": n_warm, "ms_per_step": ms,
-            "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u256 scalars / u384 curve coordinates (u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
-            "config": {"workload": "succinct: " + desc, "field": fname, "curve": "BLS12-381 G1", "depth": depth, "width_log2": w,
-                       "sumcheck_rounds": rounds, "circuit_setup_s": circuit_s, "trusted_setup_s": setup_s,
-                       "timer": "host wall clock around prove_succinct (commit + GKR + two openings; each part ends on the host)"},
-            "roofline": None,
-            "roofline_note": "three kernels families with different bounds: see the gkr_wide line (round latency / HBM) and the kzg line (integer multiplier)",
-            "cpu_baseline": None,
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": (32 << w), "d2h_bytes_per_step": int(rounds * 4 * 32 + (2 * w + 1) * 96),
-                    "call": "gkr.prove_succinct with the input layer in host memory"},
-            "gpu_launches": launches, "clocks": clocks, "verified": verified, "verify_s": verify_s,
-            "verified_by": "after the timed region: verify_succinct (succinct_gkr_protocol.rs:172-283): every layer's sumcheck and claim check on the GPU, "
-                           "the two input openings by the pairing check on the host; and again with the opened values bound to the last sumcheck claim",
-            "result_digest": keccak_digest([np.ascontiguousarray(proof.input_polynomial_commitment.reshape(-1, 4)),
-                                            np.ascontiguousarray(proof.input_rb_proof.proofs.reshape(-1, 4)),
-                                            np.ascontiguousarray(proof.input_rc_proof.proofs.reshape(-1, 4)), proof.claimed_sum])}
+    barrier()
+    line = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        verified = bool(gkr.verify_succinct(ctx, circuit, proof, setup)) and bool(gkr.verify_succinct(ctx, circuit, proof, setup, bind_input_openings=True))
+        verify_s = time.perf_counter() - t0
+        rounds = circuit.total_rounds()
+        line = {"metric": "succinct_gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": n_steps, "warmup": n_warm, "ms_per_step": ms,
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u256 scalars / u384 curve coordinates (u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
+                "config": {"workload": "succinct: " + desc, "field": fname, "curve": "BLS12-381 G1", "depth": depth, "width_log2": w,
+                           "sumcheck_rounds": rounds, "circuit_setup_s": circuit_s, "trusted_setup_s": setup_s,
+                           "sharding": ("none" if world == 1 else "circuit, setup, input layer and transcript replicated; layer sumchecks sharded on the low index bits, "
+                                        "every large multi-scalar multiplication by contiguous shares of the points, across %d ranks" % world),
+                           "timer": "host wall clock around prove_succinct (commit + GKR + two openings; each part ends on the host), max over ranks"},
+                "roofline": None,
+                "roofline_note": "three kernel families with different bounds: see the gkr_wide line (round latency / HBM) and the kzg line (integer multiplier)",
+                "cpu_baseline": None,
+                "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": (32 << w), "d2h_bytes_per_step": int(rounds * 4 * 32 + (2 * w + 1) * 96),
+                        "call": "gkr.prove_succinct with the input layer in host memory"},
+                "gpu_launches": launches, "clocks": clocks, "verified": verified, "verify_s": verify_s,
+                "verified_by": "after the timed region: verify_succinct (succinct_gkr_protocol.rs:172-283): every layer's sumcheck and claim check on the GPU, "
+                               "the two input openings by the pairing check on the host; and again with the opened values bound to the last sumcheck claim",
+                "result_digest": keccak_digest([np.ascontiguousarray(proof.input_polynomial_commitment.reshape(-1, 4)),
+                                                np.ascontiguousarray(proof.input_rb_proof.proofs.reshape(-1, 4)),
+                                                np.ascontiguousarray(proof.input_rc_proof.proofs.reshape(-1, 4)), proof.claimed_sum])}
+    barrier()
     setup.release()
     circuit.close()
     ctx.close()
@@ -1236,6 +1266,7 @@ def run_extras(args):
         lg = min(32, 29 + world.bit_length())       # 2^31 at 2 ranks, 2^32 at 4 and 8 (configs[4]: 2^32 sharded over 8 GPUs)
         attempt("mle", lambda: run_mle(args, WORKLOADS["mle"], log2=lg, sweep="", steps=min(args.steps, 5), warmup=min(args.warmup, 3)))
         attempt("gkr_wide", lambda: run_gkr_wide(args, WORKLOADS["gkr_wide"], steps=min(args.steps, 5), warmup=min(args.warmup, 2)))   # configs[3]: "on 8 x B200"
+        attempt("succinct", lambda: run_succinct(args, WORKLOADS["succinct"], log2=22, steps=min(args.steps, 3), warmup=1))
     return extras
 
 

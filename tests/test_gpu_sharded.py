@@ -130,7 +130,29 @@ def _worker(rank, world, port, q):
                 ok &= same
                 ok &= bool(gkr.verify_wide(ctx, wc, proof, dev_in))
             wc.close()
-        # multilinear KZG and succinct GKR over the ranks (BLS12-381 Fr context with its own communicator): setup, polynomial and
+        q.put((rank, bool(ok), peer, notes))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, False, None, [repr(e), traceback.format_exc()[-1500:]]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _kzg_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    import coracle as co
+    import zk_cryptography_research_implementations_b200 as zk
+    from zk_cryptography_research_implementations_b200 import gkr, sharded
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    ok = True
+    notes = []
+    try:
+        # multilinear KZG and succinct GKR over the ranks (BLS12-381 Fr context): setup, polynomial and
         # circuit replicated, every rank sums its share of the points; all ranks must return the oracle's points
         from zk_cryptography_research_implementations_b200.multilinear_kzg import MultilinearKZG, TrustedSetup
         fr = 2
@@ -190,7 +212,7 @@ def _worker(rank, world, port, q):
         co.set_threads(1)
         wc.close()
         setup.release()
-        q.put((rank, bool(ok), peer, notes))
+        q.put((rank, bool(ok), None, notes))
     except Exception as e:  # pragma: no cover
         import traceback
         q.put((rank, False, None, [repr(e), traceback.format_exc()[-1500:]]))
@@ -198,8 +220,9 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_provers_match_the_oracle(world):
+def _run_ranks(worker, world, budget_s):
+    import queue as _queue
+    import time as _time
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
@@ -207,12 +230,10 @@ def test_sharded_provers_match_the_oracle(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    import queue as _queue
-    import time as _time
-    res, deadline = [], _time.time() + 900
+    res, deadline = [], _time.time() + budget_s
     while len(res) < world and _time.time() < deadline:
         try:
             res.append(q.get(timeout=5))
@@ -225,4 +246,15 @@ def test_sharded_provers_match_the_oracle(world):
             p.kill()
     assert len(res) == world, "rank exit codes: %s" % [p.exitcode for p in procs]
     assert sorted((r[0], r[1]) for r in res) == [(r, True) for r in range(world)], [r[3] for r in res]
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_kzg_and_succinct_gkr_match_the_oracle(world):
+    _run_ranks(_kzg_worker, world, 600)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_provers_match_the_oracle(world):
+    res = _run_ranks(_worker, world, 900)
     print("peer-memory exchange attached:", [r[2] for r in res])
