@@ -46,6 +46,9 @@ typedef unsigned long long u64;
 #ifndef ZK_MSM_MIN_BLOCKS
 #define ZK_MSM_MIN_BLOCKS 3
 #endif
+#ifndef ZK_MSM_PREFETCH
+#define ZK_MSM_PREFETCH 1
+#endif
 constexpr int kMsmThreads = ZK_MSM_THREADS;   // the group law needs ~150-250 registers: small blocks keep the SMs evenly filled
 // open_and_prove sums the quotients of its last levels (2^kBatchLog points and fewer: each too small to fill the GPU) in ONE pass
 constexpr uint32_t kBatchLog = 15;
@@ -262,12 +265,30 @@ __global__ void __launch_bounds__(kMsmThreads, ZK_MSM_MIN_BLOCKS) msm_bucket_ker
     const uint64_t sidx = order ? order[t] : t;
     const u64 lo = seg_lo[sidx], hi = lo + seg_len[sidx];
     G1Xyzz acc = G1::infinity();
+#if ZK_MSM_PREFETCH
+    // the next point travels while the current one is added: index load -> 96-byte gather is a dependent pair of misses
+    uint32_t v = sorted[lo];
+    G1Affine p = load_affine(bases + (v & 0x7fffffffu));
+#pragma unroll 1
+    for (u64 e = lo; e < hi; ++e) {
+        uint32_t vn = 0;
+        G1Affine pn = p;
+        if (e + 1 < hi) {
+            vn = sorted[e + 1];
+            pn = load_affine(bases + (vn & 0x7fffffffu));
+        }
+        G1::add_affine(acc, p, (v >> 31) != 0);
+        v = vn;
+        p = pn;
+    }
+#else
 #pragma unroll 1
     for (u64 e = lo; e < hi; ++e) {
         const uint32_t v = sorted[e];
         const G1Affine p = load_affine(bases + (v & 0x7fffffffu));
         G1::add_affine(acc, p, (v >> 31) != 0);
     }
+#endif
     store_xyzz(part0 + sidx, acc);
 }
 __global__ void __launch_bounds__(kMsmThreads) msm_merge_kernel(const u64* seg0, const u64* seg1, const G1Xyzz* part0, uint64_t n_keys,
