@@ -635,10 +635,16 @@ def run_kzg(args, wl, log2=None, steps=None, warmup=None):
     # e2e: evaluations in pinned host memory -> commitment on the host
     e2e = None
     if not args.no_e2e:
-        host_vals = table.download()
-        ms_e2e = timed(lambda: MultilinearKZG.commit_to_polynomial(host_vals, setup), max(1, min(n_steps, 3)), 1)
-        e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Mpoints/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": 96,
-               "ms_per_step": ms_e2e, "call": "zk_kzg_commit (host evaluations -> HBM -> commitment on the host)"}
+        pin = C.c_void_p()
+        if lib.zk_pinned_alloc(C.c_size_t(N * 32), C.byref(pin)) == 0:
+            host_vals = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint64)), shape=(N * 4,)).reshape(N, 4)
+            ctx.check(lib.zk_table_download(ctx.h, table.h, C.cast(pin, C.POINTER(C.c_uint64))))
+            ms_e2e = timed(lambda: box.__setitem__("ce", MultilinearKZG.commit_to_polynomial(host_vals, setup)), max(1, min(n_steps, 3)), 1)
+            assert np.array_equal(box["ce"], commitment)
+            e2e = {"value": N / (ms_e2e * 1e-3) / MEGA, "unit": "Mpoints/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": 96,
+                   "ms_per_step": ms_e2e, "call": "zk_kzg_commit (evaluations in pinned host memory -> HBM -> commitment on the host)"}
+            del host_vals
+            lib.zk_pinned_free(pin)
     # the multiplier ceiling: register-resident mixed additions and 381-bit products on the full grid
     peak_madd = peak_mul = None
     if not args.no_probe:
@@ -762,13 +768,19 @@ def run_succinct(args, wl, log2=None, steps=None, warmup=None):
     clocks = sampler.stop() if sampler else None
     e2e_ms = None
     if not args.no_e2e and world == 1:
-        host_I = dev_I.download()
-        prove(host_I)
-        t0 = time.perf_counter()
-        pe = prove(host_I)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        assert np.array_equal(pe.input_polynomial_commitment, proof.input_polynomial_commitment)
+        pin = C.c_void_p()
+        n_in = 1 << w
+        if ctx.lib.zk_pinned_alloc(C.c_size_t(n_in * 32), C.byref(pin)) == 0:
+            host_I = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint64)), shape=(n_in * 4,)).reshape(n_in, 4)
+            ctx.check(ctx.lib.zk_table_download(ctx.h, dev_I.h, C.cast(pin, C.POINTER(C.c_uint64))))
+            prove(host_I)
+            t0 = time.perf_counter()
+            pe = prove(host_I)
+            torch.cuda.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
+            assert np.array_equal(pe.input_polynomial_commitment, proof.input_polynomial_commitment)
+            del host_I
+            ctx.lib.zk_pinned_free(pin)
     barrier()
     line = None
     if rank == 0:
@@ -788,7 +800,7 @@ def run_succinct(args, wl, log2=None, steps=None, warmup=None):
                 "roofline_note": "three kernel families with different bounds: see the gkr_wide line (round latency / HBM) and the kzg line (integer multiplier)",
                 "cpu_baseline": None,
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": (32 << w), "d2h_bytes_per_step": int(rounds * 4 * 32 + (2 * w + 1) * 96),
-                        "call": "gkr.prove_succinct with the input layer in host memory"},
+                        "call": "gkr.prove_succinct with the input layer in pinned host memory"},
                 "gpu_launches": launches, "clocks": clocks, "verified": verified, "verify_s": verify_s,
                 "verified_by": "after the timed region: verify_succinct (succinct_gkr_protocol.rs:172-283): every layer's sumcheck and claim check on the GPU, "
                                "the two input openings by the pairing check on the host; and again with the opened values bound to the last sumcheck claim",
