@@ -22,7 +22,7 @@ def run_bench(*args, timeout=600):
 
 
 @pytest.mark.parametrize("workload,extra", [("product30", ["--cpu-log2", "10"]), ("plain24", ["--cpu-log2", "10"]),
-                                            ("gkr", ["--cpu-depth", "3"]), ("mle", ["--cpu-log2", "10"])])
+                                            ("gkr", ["--cpu-depth", "3"]), ("mle", ["--cpu-log2", "10"]), ("kzg", ["--log2", "6"])])
 def test_reference_arm_line(workload, extra):
     d = run_bench("--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0", *extra)
     assert BASE_KEYS <= set(d)

@@ -44,3 +44,18 @@ def test_gpu_arm_other_workloads_verify_their_proofs():
         d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
         assert d["verified"] is True, (args, d.get("verify"))
         assert d["roofline"]["frac"] > 0 and d["clocks"] is not None
+
+
+def test_gpu_arm_kzg_and_succinct_lines_verify_with_pairings():
+    """the multilinear-KZG line (commitment + opening checked by the pairing verifier and against the oracle's commitment of the
+    CPU sample) and the succinct-GKR line (verify_succinct) at small sizes"""
+    for args, metric in ((["--workload", "kzg", "--log2", "14"], "kzg_commit_Mpoints_per_s"),
+                         (["--workload", "succinct", "--log2", "12"], "succinct_gkr_prove_ms")):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args, "--steps", "2", "--warmup", "1"],
+                             capture_output=True, text=True, timeout=900, cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-2000:]
+        d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+        assert d["metric"] == metric and d["verified"] is True and d["value"] > 0 and d["gpu_launches"] > 0
+        assert d["e2e"]["value"] > 0 and d["clocks"] is not None and len(d["result_digest"]) == 64
+        if metric.startswith("kzg"):
+            assert d["cpu_baseline"]["kind"] == "port" and d["roofline"]["bound"] == "imad" and d["roofline"]["peak"] > 0
