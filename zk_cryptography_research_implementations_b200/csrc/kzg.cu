@@ -5,14 +5,17 @@
 // multiplications -- and opens with n more such sums over the full setup, each against a quotient "blown up" to 2^n
 // entries (multilinear_kzg.rs:93-108, :183-214).  Here:
 //   * every sum is one bucket-method multi-scalar multiplication: signed c-bit digits of the canonical scalars, a
-//     histogram / scan / scatter that groups the (window, digit) occurrences (no sort), one thread per bucket adding
-//     affine points into an XYZZ accumulator (g1.cuh), running sums per chunk of a few buckets, the chunk results summed by
+//     histogram / scan / scatter that groups the (window, digit) occurrences (no sort), bucket sums in three bounded
+//     levels (one thread per segment of <= 128 entries adding affine points into an XYZZ accumulator, g1.cuh; segments run
+//     longest first), running sums per chunk of a few buckets, the chunk results summed by
 //     bit planes of the chunk index (one block per plane), and a host finish of ~450 group operations (one doubling per
 //     scalar bit, one addition per plane, one inversion for the affine result);
 //   * the blow-up is never materialised: the quotient of round k repeats with period 2^(n-k-1), so its sum against the
 //     setup equals its sum against the setup FOLDED k+1 times (S_{k+1}[j] = S_k[j] + S_k[j + half]) -- the Lagrange basis
 //     of the remaining variables -- which is built once per setup.  Openings cost 2^n point additions in total, not n 2^n;
-//   * f - v is never formed: the quotient hi - lo does not see the constant, and v falls out of the last fold.
+//   * f - v is never formed: the quotient hi - lo does not see the constant, and v falls out of the last fold;
+//   * the last 16 rounds of an opening (<= 2^15 points each) are summed in ONE grouped pass (MsmPlan::groups);
+//   * several GPUs: every rank sums a contiguous share of the points, one 96-byte all-gather per call (zk_kzg_*_sharded).
 // Group elements leave in affine form (canonical), so neither the coordinate system nor the order of the additions can show
 // in a result: outputs are bit-identical to the reference's `P::G1` values converted with `into_affine()`.
 #include <algorithm>
