@@ -23,6 +23,18 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def kzg_golden():
+    """tests/golden/kzg_golden.json (made by tests/golden/make_golden_kzg.py from the Python big-int model)"""
+    with open(os.path.join(ROOT, "tests", "golden", "kzg_golden.json")) as f:
+        return json.load(f)
+
+
+def golden_point(p):
+    """golden affine point -> (x, y) ints or None"""
+    return None if p is None else (int(p[0], 16), int(p[1], 16))
+
+
+@pytest.fixture(scope="session")
 def co():
     """the C oracle (test infrastructure)"""
     import coracle

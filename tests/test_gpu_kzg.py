@@ -49,6 +49,23 @@ def test_reference_kzg_tests(co, ctx_for, kzg, case):
     assert pk.verify(psetup, co.g1_to_ints(c)[0], [x % R for x in opening], co.to_ints(FR, proof.evaluation)[0], co.g1_to_ints(proof.proofs))
 
 
+def test_golden_vectors(co, ctx_for, kzg, kzg_golden):
+    """the committed golden commitments and openings (tests/golden/kzg_golden.json, Python big-int model, pairing-verified)"""
+    from conftest import golden_point
+    ctx = ctx_for(FR)
+    for e in kzg_golden["generated"]:
+        taus, vals, opening = ([int(x) for x in e[k]] for k in ("taus", "values", "opening"))
+        t, v, o = _fe(co, taus), _fe(co, vals), _fe(co, opening)
+        setup = kzg.TrustedSetup.initialize_setup(ctx, t)
+        pts = co.g1_to_ints(setup.g1_powers_of_tau)
+        assert pts[0] == golden_point(e["g1_powers_of_tau_first"]) and pts[-1] == golden_point(e["g1_powers_of_tau_last"]), e["src"]
+        assert co.g1_to_ints(kzg.MultilinearKZG.commit_to_polynomial(v, setup))[0] == golden_point(e["commitment"]), e["src"]
+        proof = kzg.MultilinearKZG.open_and_prove(v, setup, o)
+        assert co.to_ints(FR, proof.evaluation)[0] == int(e["evaluation"])
+        assert co.g1_to_ints(proof.proofs) == [golden_point(p) for p in e["proofs"]], e["src"]
+        assert kzg.MultilinearKZG.verify(setup, kzg.MultilinearKZG.commit_to_polynomial(v, setup), o, proof)
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 9, 12])
 def test_setup_commit_open_match_oracle(co, ctx_for, kzg, zk, n):
     ctx = ctx_for(FR)

@@ -96,6 +96,25 @@ def test_reference_kzg_proofs_verify(co, lib, case):
     assert verify(lib, g2, c, o, ev, off)[0] == -3                           # a point off the curve
 
 
+def test_golden_proofs_verify(co, lib, kzg_golden):
+    """the committed golden commitments / openings (tests/golden/kzg_golden.json) through the product's pairing verifier"""
+    from conftest import golden_point
+    g2gen = np.zeros(24, dtype=np.uint64)
+    lib.zk_g2_generator(_p(g2gen))
+    want = kzg_golden["curve"]["g2_generator"]
+    assert _g2_to_ints(co, g2gen)[0] == ((int(want[0][0], 16), int(want[0][1], 16)), (int(want[1][0], 16), int(want[1][1], 16)))
+    for e in kzg_golden["generated"]:
+        taus, opening = ([int(x) for x in e[k]] for k in ("taus", "opening"))
+        t, o = co.from_ints(FR, taus), co.from_ints(FR, opening)
+        g2 = np.zeros((len(taus), 24), dtype=np.uint64)
+        assert lib.zk_kzg_g2_powers_of_tau(_p(t), len(taus), _p(g2)) == 0
+        c = co.g1_from_ints([golden_point(e["commitment"])])[0]
+        proofs = co.g1_from_ints([golden_point(p) for p in e["proofs"]])
+        ev = co.from_ints(FR, [int(e["evaluation"])])[0]
+        assert verify(lib, g2, c, o, ev, proofs) == (0, 1), e["src"]
+        assert verify(lib, g2, c, o, co.from_ints(FR, [(int(e["evaluation"]) + 1) % R])[0], proofs) == (0, 0)
+
+
 def test_random_polynomial_and_infinity_proofs(co, lib):
     rnd = random.Random(9)
     n = 5

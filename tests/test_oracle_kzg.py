@@ -81,6 +81,27 @@ def test_random_polynomial_against_python_model(co):
           [rnd.randrange(R) for _ in range(n)], pairing=False)
 
 
+def test_golden_vectors(co, kzg_golden):
+    """tests/golden/kzg_golden.json: the reference's Lagrange-basis known answers, and the commitments / openings of its three
+    KZG tests as the Python model computed (and pairing-verified) them, against the C oracle and the Python model of today"""
+    from conftest import golden_point
+    assert golden_point(kzg_golden["curve"]["g1_generator"]) == pk.G1_GEN and int(kzg_golden["curve"]["r"], 16) == R
+    for k in kzg_golden["reference_kats"]["lagrange_basis"]:
+        assert pk.lagrange_basis(k["taus"]) == [x % R for x in k["out"]], k["src"]
+    for e in kzg_golden["generated"]:
+        taus, vals, opening = ([int(x) for x in e[k]] for k in ("taus", "values", "opening"))
+        t, v, o = (co.from_ints(FR, x) for x in (taus, vals, opening))
+        setup = co.kzg_setup_g1(t)
+        got_setup = co.g1_to_ints(setup)
+        assert got_setup[0] == golden_point(e["g1_powers_of_tau_first"]) and got_setup[-1] == golden_point(e["g1_powers_of_tau_last"]), e["src"]
+        assert co.g1_to_ints(co.kzg_commit(v, setup))[0] == golden_point(e["commitment"]), e["src"]
+        ev, proofs = co.kzg_open(v, setup, o)
+        assert co.to_ints(FR, ev)[0] == int(e["evaluation"]) and co.g1_to_ints(proofs) == [golden_point(p) for p in e["proofs"]], e["src"]
+        if len(taus) <= 3:
+            psetup = pk.TrustedSetup.initialize(taus)
+            assert pk.commit(vals, psetup) == golden_point(e["commitment"])
+
+
 def test_threads_do_not_change_results(co):
     rnd = random.Random(12)
     n = 6
