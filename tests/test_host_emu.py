@@ -37,6 +37,21 @@ def test_fq381_and_g1_host_emulation(tmp_path):
     assert out.stdout.count("ok") == 3, out.stdout[-2000:]
 
 
+def test_msm_reduction_replayed_on_the_cpu(tmp_path):
+    """the multi-scalar multiplication's own plan, signed-digit decomposition (csrc/msm_plan.cuh) and host combine
+    (csrc/msm_host.h) driven through buckets, chunk running sums and bit planes on the CPU, against sums of the oracle's scalar
+    multiplications: window widths 2..16, the library's plans, the grouped (halving) layout of the batched opening rounds"""
+    exe = str(tmp_path / "emu_msm")
+    cmd = ["g++", "-O2", "-std=c++17", "-DZK_HOST_EMU", "-x", "c++", "-w",
+           "-I", os.path.join(ROOT, "zk_cryptography_research_implementations_b200", "csrc"),
+           os.path.join(ROOT, "tests", "host_emu", "emu_msm.cpp"), os.path.join(ROOT, "oracle", "zkoracle.c"),
+           os.path.join(ROOT, "oracle", "zkoracle_kzg.c"), "-o", exe]
+    subprocess.check_call(cmd)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert out.stdout.count("ok") == 3, out.stdout[-2000:]
+
+
 def test_warp_keccak_lane_tables_match_their_generator():
     """the packed lane-routing words in csrc/dev_transcript.cuh are exactly what tools/gen_keccak_lanes.py derives (and
     checks against a textbook Keccak-f[1600] and hashlib's SHA3-256)"""

@@ -28,6 +28,8 @@
 #include "g1.cuh"
 #include "host_curve.h"
 #include "scan.cuh"
+#include "msm_plan.cuh"
+#include "msm_host.h"
 
 using namespace zk;
 
@@ -57,37 +59,6 @@ constexpr int kMsmThreads = ZK_MSM_THREADS;   // the group law needs ~150-250 re
 constexpr uint32_t kBatchLog = 15;
 constexpr int kFixedWindows = 32;    // fixed-base table of the generator: 32 windows of 8 bits
 
-struct MsmPlan {
-    int c;            // window width in bits (signed digits in [-2^(c-1), 2^(c-1)])
-    int W;            // windows = ceil(256 / c): the top window also takes the last carry (scalars are < 2^255)
-    uint32_t B;       // buckets per window = 2^(c-1); bucket b holds the points whose digit is +-(b + 1)
-    uint32_t S;       // buckets per running-sum chunk
-    uint32_t cap0;    // entries per level-0 segment of the bucket sums
-    // several sums in one pass (the small levels of an opening): `groups` consecutive index ranges of halving size, the first
-    // 2^n0_log long (2^n0_log, 2^(n0_log-1), .., 1); every group has its own windows.  groups == 1: one plain sum.
-    uint32_t groups, n0_log;
-};
-MsmPlan plan_for(uint64_t n, uint32_t groups = 1, uint32_t n0_log = 0) {
-    int c = n >= (1u << 20) ? 16 : n >= (1u << 16) ? 13 : n >= (1u << 12) ? 10 : n >= (1u << 8) ? 7 : 4;
-    if (const char* e = getenv("ZKB200_MSM_WINDOW")) {
-        const int v = atoi(e);
-        if (v >= 2 && v <= 16) c = v;
-    }
-    MsmPlan p;
-    p.c = c;
-    p.W = (256 + c - 1) / c;
-    p.B = 1u << (c - 1);
-    // serial depth of the window sums: 2 S additions per chunk, then B / (128 S) + 8 in the block-per-plane reduction
-    p.S = p.B >= 16384 ? 8 : p.B >= 2048 ? 4 : p.B >= 256 ? 2 : 1;
-    // level-0 segments: long enough to amortise a thread, short enough that a small problem still fills the machine
-    const uint64_t entries = n * (uint64_t)p.W;
-    p.cap0 = 8;
-    while (p.cap0 < 128 && entries / p.cap0 > 65536) p.cap0 <<= 1;
-    p.groups = groups;
-    p.n0_log = n0_log;
-    return p;
-}
-
 // ---------------------------------------------------------------- 16-byte vector moves of points
 __device__ __forceinline__ G1Affine load_affine(const G1Affine* p) {
     G1Affine r;
@@ -116,45 +87,6 @@ __device__ __forceinline__ void store_xyzz(G1Xyzz* p, const G1Xyzz& v) {
     const uint4* s = reinterpret_cast<const uint4*>(&v);
 #pragma unroll
     for (int i = 0; i < 12; ++i) d[i] = s[i];
-}
-
-// ---------------------------------------------------------------- scalars -> signed digits
-// `into_bigint()`: the canonical integer of a Montgomery-form scalar
-__device__ __forceinline__ void canonical_scalar(uint32_t k[8], const Fe& s) {
-    Fe one, r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) one.v[i] = i == 0 ? 1u : 0u;
-    Fr::mont_mul(r, s, one);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) k[i] = r.v[i];
-}
-__device__ __forceinline__ uint32_t window_bits(const uint32_t k[8], int lo, int c) {
-    const int word = lo >> 5, sh = lo & 31;
-    uint64_t v = k[word];
-    if (word + 1 < 8) v |= (uint64_t)k[word + 1] << 32;
-    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
-}
-// the group of index i under the halving layout: group g covers 2^(n0_log - g) indices
-__device__ __forceinline__ uint32_t group_of(uint64_t i, const MsmPlan& pl) {
-    if (pl.groups == 1) return 0;
-    const uint64_t r = ((2ull << pl.n0_log) - 1) - i;   // counts down from 2^(n0_log+1) - 1
-    return pl.n0_log - (63 - __clzll((long long)r));
-}
-// calls f(window, bucket, negative) for every non-zero digit of k; `window` already carries the group's offset
-template <typename Fn> __device__ __forceinline__ void for_each_digit(const uint32_t k[8], const MsmPlan& pl, uint32_t group, Fn f) {
-    uint32_t carry = 0;
-    const int w0 = (int)group * pl.W;
-    for (int w = 0; w < pl.W; ++w) {
-        uint32_t d = window_bits(k, w * pl.c, pl.c) + carry;
-        carry = 0;
-        bool neg = false;
-        if (d > pl.B) {
-            d = (1u << pl.c) - d;
-            neg = true;
-            carry = 1;
-        }
-        if (d) f(w0 + w, d - 1u, neg);
-    }
 }
 
 // off[key + 1] += 1 for every non-zero digit (off zeroed before); key = window * B + bucket
@@ -644,24 +576,7 @@ int g1_msm(zk_ctx* ctx, zk_kzg_setup* s, const Fe* scalars, const G1Affine* base
     ZK_CUDA(cudaStreamSynchronize(st));
     // window_w = A_w + S sum_p 2^p P_{w,p};  result = sum_w 2^(c w) window_w = sum over bit positions: A_w sits at c w and
     // P_{w,p} at c w + log2(S) + p < c (w + 1).  One pass from the top bit down: a doubling per position, an addition per term.
-    auto combine = [&](uint32_t g) {
-        std::vector<const HG1Xyzz*> at((size_t)pl.W * pl.c, nullptr), at2((size_t)pl.W * pl.c, nullptr);
-        for (int w = 0; w < pl.W; ++w) {
-            const HG1Xyzz* base = s->win_host + ((size_t)g * pl.W + w) * (nb + 1);
-            at[(size_t)w * pl.c] = base + nb;
-            for (uint32_t p = 0; p < nb; ++p) {
-                const size_t pos = (size_t)w * pl.c + log_s + p;
-                (at[pos] ? at2[pos] : at[pos]) = base + p;
-            }
-        }
-        HG1Xyzz acc = HostG1::infinity();
-        for (size_t pos = at.size(); pos-- > 0;) {
-            acc = HostG1::dbl(acc);
-            if (at[pos]) acc = HostG1::add(acc, *at[pos]);
-            if (at2[pos]) acc = HostG1::add(acc, *at2[pos]);
-        }
-        out[g] = HostG1::to_affine(acc);
-    };
+    auto combine = [&](uint32_t g) { out[g] = msm_combine_planes(s->win_host + (size_t)g * pl.W * (nb + 1), pl, nb, log_s); };
     if (groups == 1) {
         combine(0);
     } else {   // the groups' finishes are independent: a few host threads
