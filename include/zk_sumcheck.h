@@ -328,6 +328,8 @@ int  zk_kzg_g2_powers_of_tau(const uint64_t *taus, uint32_t n, uint64_t *out /* 
 int  zk_kzg_verify(const uint64_t *g2_powers_of_tau, uint32_t n_g2, const uint64_t commitment[12],
                    const uint64_t *opening_values, uint32_t n_opening, const uint64_t evaluation[4], const uint64_t *proofs,
                    uint32_t n_proofs, int *ok);
+/* prod_i e(g1_points[i], g2_points[i]) == 1 -- the check zk_kzg_verify is built on (one final exponentiation for all pairs) */
+int  zk_pairing_product_is_one(const uint64_t *g1_points /* 12*n */, const uint64_t *g2_points /* 24*n */, uint32_t n, int *ok);
 int  zk_g1_is_on_curve(const uint64_t point[12]);
 void zk_g1_generator(uint64_t out[12]);
 void zk_g2_generator(uint64_t out[24]);

@@ -134,3 +134,35 @@ def test_random_polynomial_and_infinity_proofs(co, lib):
     ev, proofs = co.kzg_open(const, g1, o)
     assert not proofs.any() and co.to_ints(FR, ev)[0] == 7
     assert verify(lib, g2, c, o, ev, proofs) == (0, 1)
+
+
+def test_pairing_is_bilinear_and_non_degenerate(co, lib):
+    """e(aP, bQ) e(-abP, Q) == 1, e(P, Q) != 1, infinity pairs to one -- through zk_pairing_product_is_one, with the G2 multiples
+    taken from the product's own setup routine and checked against the Python model"""
+    rnd = random.Random(4)
+    g1 = co.g1_generator()
+    g2 = np.zeros(24, dtype=np.uint64)
+    lib.zk_g2_generator(_p(g2))
+
+    def check(p1s, p2s):
+        ok = C.c_int(-1)
+        a = np.ascontiguousarray(np.stack(p1s), dtype=np.uint64)
+        b = np.ascontiguousarray(np.stack(p2s), dtype=np.uint64)
+        rc = lib.zk_pairing_product_is_one(_p(a), _p(b), len(p1s), C.byref(ok))
+        return rc, ok.value
+
+    for _ in range(3):
+        a, b = rnd.randrange(1, R), rnd.randrange(1, R)
+        bq = np.zeros((1, 24), dtype=np.uint64)
+        assert lib.zk_kzg_g2_powers_of_tau(_p(co.from_ints(FR, [b])), 1, _p(bq)) == 0          # b * G2
+        assert _g2_to_ints(co, bq)[0] == pk.g2_mul(pk.G2_GEN, b)
+        ap = co.g1_mul(g1, a)
+        minus_abp = co.g1_mul(g1, (R - a * b % R) % R)
+        assert check([ap, minus_abp], [bq[0], g2]) == (0, 1)
+        assert check([ap, co.g1_mul(g1, (R - a * b % R + 1) % R)], [bq[0], g2]) == (0, 0)
+    assert check([g1], [g2]) == (0, 0)                                                             # non-degenerate
+    inf1, inf2 = np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64)
+    assert check([inf1, g1], [g2, inf2]) == (0, 1)
+    bad = g2.copy()
+    bad[0] ^= 1
+    assert check([g1], [bad])[0] == -3

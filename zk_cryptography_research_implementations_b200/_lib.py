@@ -119,6 +119,7 @@ SIGNATURES = {
     "zk_g1_msm": (C.c_int, [vp, u64p, u64p, C.c_uint64, u64p]),
     "zk_kzg_g2_powers_of_tau": (C.c_int, [u64p, C.c_uint32, u64p]),
     "zk_kzg_verify": (C.c_int, [u64p, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p, C.c_uint32, C.POINTER(C.c_int)]),
+    "zk_pairing_product_is_one": (C.c_int, [u64p, u64p, C.c_uint32, C.POINTER(C.c_int)]),
     "zk_g1_is_on_curve": (C.c_int, [u64p]),
     "zk_g1_generator": (None, [u64p]),
     "zk_g2_generator": (None, [u64p]),

@@ -82,6 +82,23 @@ extern "C" int zk_kzg_verify(const uint64_t* g2_powers_of_tau, uint32_t n_g2, co
     return ZK_OK;
 }
 
+// prod_i e(g1[i], g2[i]) == 1 (one product of Miller loops, one final exponentiation): the primitive zk_kzg_verify is built on,
+// exported for callers that batch several checks into one.  ZK_ERR_ARG: a point off its curve.
+extern "C" int zk_pairing_product_is_one(const uint64_t* g1_points, const uint64_t* g2_points, uint32_t n, int* ok) {
+    *ok = 0;
+    std::vector<HG1Affine> ps;
+    std::vector<HG2Affine> qs;
+    for (uint32_t i = 0; i < n; ++i) {
+        const HG1Affine p = g1_at(g1_points + 12 * i);
+        const HG2Affine q = g2_at(g2_points + 24 * i);
+        if (!HostG1::on_curve(p) || !HostG2::on_curve(q)) return ZK_ERR_ARG;
+        ps.push_back(p);
+        qs.push_back(q);
+    }
+    *ok = HostPairing::product_is_one(ps, qs) ? 1 : 0;
+    return ZK_OK;
+}
+
 // host helpers for callers that hold points as plain integers (tests, bindings)
 extern "C" int zk_g1_is_on_curve(const uint64_t p[12]) { return HostG1::on_curve(g1_at(p)) ? 1 : 0; }
 extern "C" void zk_g1_generator(uint64_t out[12]) {
