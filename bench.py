@@ -136,6 +136,25 @@ def cpu_gkr_once(field: int, depth: int):
     return time.perf_counter() - t0
 
 
+def cpu_succinct_once(depth: int):
+    """prove_succinct the way the reference runs it (succinct_gkr_protocol.rs:35-169), oracle port, one thread: commitment to the
+    2^depth inputs + gkr_protocol::prove of a reference-shaped depth-`depth` circuit + two openings; seconds"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import coracle as co
+    field = 2
+    c = co.Circuit(synthetic_circuit(depth))
+    I = gkr_inputs(field, depth)
+    taus = co.table_generate(field, SEED, 98, 64)[:depth].copy()
+    g1 = co.kzg_setup_g1(taus)                       # the trusted setup is an input of prove_succinct, not part of it
+    t0 = time.perf_counter()
+    co.kzg_commit(I, g1)
+    proof = co.gkr_prove(field, c, I)
+    chal = proof.challenges[-2 * depth:]
+    co.kzg_open(I, g1, chal[:depth])
+    co.kzg_open(I, g1, chal[depth:])
+    return time.perf_counter() - t0
+
+
 def wide_circuit_arrays(width_log2: int, depth: int = 16, seed: int = SEED):
     """depth layers of 2^w gates each.  Layers 1..depth-1: gate g drives output g from two seeded wires of the layer below;
     layer 0 reduces the 2^w wires below it into TWO outputs (gate g reads wire g and a seeded wire, output g mod 2), so the
@@ -788,6 +807,17 @@ def run_succinct(args, wl, log2=None, steps=None, warmup=None):
         verified = bool(gkr.verify_succinct(ctx, circuit, proof, setup)) and bool(gkr.verify_succinct(ctx, circuit, proof, setup, bind_input_openings=True))
         verify_s = time.perf_counter() - t0
         rounds = circuit.total_rounds()
+        cpu = None
+        if not args.no_cpu and world == 1:
+            try:
+                d = min(args.cpu_depth, 7)
+                t = cpu_succinct_once(d)
+                cpu = {"value": t * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+                       "sample": "prove_succinct of a reference-shaped depth-%d circuit (2^%d inputs: commitment + GKR + two openings, the openings "
+                                 "against blown-up quotients as the reference does); the reference's dense wiring tables cannot hold a 2^%d-wide "
+                                 "layer; oracle C restatement, 1 thread" % (d, d, w)}
+            except Exception as ex:       # the baseline must never cost the line
+                cpu = {"error": repr(ex)}
         line = {"metric": "succinct_gkr_prove_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": n_steps, "warmup": n_warm, "ms_per_step": ms,
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u256 scalars / u384 curve coordinates (u32 Montgomery limbs, integer IMAD arithmetic)", "data": "synthetic",
@@ -798,7 +828,7 @@ def run_succinct(args, wl, log2=None, steps=None, warmup=None):
                            "timer": "host wall clock around prove_succinct (commit + GKR + two openings; each part ends on the host), max over ranks"},
                 "roofline": None,
                 "roofline_note": "three kernel families with different bounds: see the gkr_wide line (round latency / HBM) and the kzg line (integer multiplier)",
-                "cpu_baseline": None,
+                "cpu_baseline": cpu,
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": (32 << w), "d2h_bytes_per_step": int(rounds * 4 * 32 + (2 * w + 1) * 96),
                         "call": "gkr.prove_succinct with the input layer in pinned host memory"},
                 "gpu_launches": launches, "clocks": clocks, "verified": verified, "verify_s": verify_s,
